@@ -1,0 +1,525 @@
+// C-ABI entry points of libbags_b200.so (see include/bags_b200.h).
+// Host side only: argument validation, TMA descriptor encoding, kernel launches.
+// No torch, no allocations, no device synchronisation.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/bags_b200.h"
+#include "bags_gemm.cuh"
+#include "bags_kernels.cuh"
+
+using namespace bags;
+
+// ----------------------------------------------------------------------------
+// error handling
+// ----------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define BAGS_CUDA(expr)                                                                   \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess)                                                                \
+      return fail(BAGS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),  \
+                  __FILE__, __LINE__);                                                    \
+  } while (0)
+
+#define BAGS_REQUIRE(cond, ...)                              \
+  do {                                                       \
+    if (!(cond)) return fail(BAGS_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+extern "C" int bags_abi_version(void) { return BAGS_ABI_VERSION; }
+extern "C" const char* bags_last_error(void) { return g_last_error.c_str(); }
+
+// ----------------------------------------------------------------------------
+// per-process device info (SM count, arch check) and driver entry point
+// ----------------------------------------------------------------------------
+struct DeviceInfo {
+  int num_sms = 0;
+  int cc_major = 0;
+};
+static std::mutex g_mutex;
+static DeviceInfo g_dev[64];
+static bool g_dev_ok[64] = {false};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int device_info(DeviceInfo& out) {
+  int dev = 0;
+  BAGS_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(BAGS_ERR_INVALID, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lk(g_mutex);
+  if (!g_dev_ok[dev]) {
+    DeviceInfo d;
+    BAGS_CUDA(cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev));
+    BAGS_CUDA(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    g_dev[dev] = d;
+    g_dev_ok[dev] = true;
+  }
+  out = g_dev[dev];
+  if (out.cc_major != 10)
+    return fail(BAGS_ERR_ARCH, "libbags_b200 requires an sm_100 (B200) device; found compute capability %d.x",
+                out.cc_major);
+  if (g_encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    BAGS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (fn == nullptr || qres != cudaDriverEntryPointSuccess)
+      return fail(BAGS_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  return BAGS_OK;
+}
+
+// 2-D row-major tensor [outer, inner] (inner contiguous), 128B-swizzled boxes.
+static int make_tmap(CUtensorMap* tm, const void* ptr, int dtype, long long inner, long long outer,
+                     long long ld_elems, int box_inner, int box_outer, bool atom32 = false) {
+  const int elt = (dtype == BAGS_DTYPE_BF16) ? 2 : 4;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0)
+    return fail(BAGS_ERR_INVALID, "operand pointer %p is not 16-byte aligned", ptr);
+  if (((ld_elems * elt) & 15) != 0)
+    return fail(BAGS_ERR_INVALID, "operand row stride %lld bytes is not a multiple of 16", ld_elems * elt);
+  if (box_inner * elt != 128) return fail(BAGS_ERR_INVALID, "internal: box inner must span 128 bytes");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld_elems * elt)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(tm, dtype == BAGS_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                        2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(BAGS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%lld outer=%lld ld=%lld box=%dx%d)",
+                (int)r, inner, outer, ld_elems, box_inner, box_outer);
+  return BAGS_OK;
+}
+
+static int make_group_table(GroupTable& gt, const int32_t* slices_host, int G, int C) {
+  BAGS_REQUIRE(slices_host != nullptr, "slices_host is NULL");
+  BAGS_REQUIRE(G >= 1 && G <= kMaxG, "G=%d outside [1,%d]", G, kMaxG);
+  gt.G = G;
+  int prev_end = 0;
+  for (int g = 0; g < kMaxG; ++g) {
+    gt.start[g] = 0;
+    gt.len[g] = 0;
+    if (g < G) {
+      const int s = slices_host[2 * g], l = slices_host[2 * g + 1];
+      BAGS_REQUIRE(s >= prev_end && l >= 1 && s + l <= C,
+                   "pred_slice row %d = (%d,%d) is not an ascending, in-range slice of %d logits", g, s, l, C);
+      gt.start[g] = s;
+      gt.len[g] = l;
+      prev_end = s + l;
+    }
+  }
+  return BAGS_OK;
+}
+
+// ----------------------------------------------------------------------------
+// GEMM launcher
+// ----------------------------------------------------------------------------
+struct GemmArgs {
+  const void* a; long long lda; bool a_mn;
+  const void* b; long long ldb; bool b_mn;
+  int M, N, K;
+  int dtype;
+  int splits;
+  GemmParams p;  // epilogue fields pre-filled (out, ldo, bias, gscale, ...)
+};
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool TF32, int STAGES>
+static int launch_gemm(const GemmArgs& ga, const DeviceInfo& di, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N, A_MN, B_MN, EPI, TF32, STAGES>;
+  auto kernel = bags_gemm_kernel<BLOCK_N, A_MN, B_MN, EPI, TF32, STAGES>;
+  CUtensorMap ta, tb;
+  int rc;
+  // A
+  if (A_MN) rc = make_tmap(&ta, ga.a, ga.dtype, ga.M, ga.K, ga.lda, Cfg::SLAB, Cfg::BLOCK_K, TF32);
+  else      rc = make_tmap(&ta, ga.a, ga.dtype, ga.K, ga.M, ga.lda, Cfg::BLOCK_K, Cfg::BLOCK_M);
+  if (rc) return rc;
+  if (B_MN) rc = make_tmap(&tb, ga.b, ga.dtype, ga.N, ga.K, ga.ldb, Cfg::SLAB, Cfg::BLOCK_K, TF32);
+  else      rc = make_tmap(&tb, ga.b, ga.dtype, ga.K, ga.N, ga.ldb, Cfg::BLOCK_K, Cfg::UMMA_N);
+  if (rc) return rc;
+
+  GemmParams p = ga.p;
+  p.M = ga.M; p.N = ga.N; p.K = ga.K;
+  p.num_m_tiles = (ga.M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
+  p.num_n_tiles = (ga.N + BLOCK_N - 1) / BLOCK_N;
+  p.kblocks_total = (ga.K + Cfg::BLOCK_K - 1) / Cfg::BLOCK_K;
+  int splits = ga.splits < 1 ? 1 : ga.splits;
+  if (splits > p.kblocks_total) splits = p.kblocks_total;
+  if (EPI != EPI_RED_F32) splits = 1;
+  p.num_splits = splits;
+  const int units = p.num_m_tiles * p.num_n_tiles * splits;
+  if (units == 0) return BAGS_OK;
+  const int grid = units < di.num_sms ? units : di.num_sms;
+
+  BAGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  kernel<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  BAGS_CUDA(cudaGetLastError());
+  return BAGS_OK;
+}
+
+static int pick_splits(int tiles, int kblocks, int num_sms) {
+  int s = num_sms / (tiles > 0 ? tiles : 1);
+  if (s < 1) s = 1;
+  if (s > kblocks) s = kblocks;
+  return s;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+// forward tile width: fewest (waves x tile width)
+static int pick_fwd_block_n(int N, int C, int num_sms) {
+  const int forced = env_int("BAGS_FWD_BN", 0);
+  if (forced == 256 || forced == 320) return forced;
+  const int mt = (N + 127) / 128;
+  auto cost = [&](int bn) {
+    const int tiles = mt * ((C + bn - 1) / bn);
+    return ((tiles + num_sms - 1) / num_sms) * bn;
+  };
+  return cost(320) < cost(256) ? 320 : 256;
+}
+
+// ----------------------------------------------------------------------------
+// public entry points
+// ----------------------------------------------------------------------------
+extern "C" size_t bags_workspace_bytes(void) { return 256 + 4096 * kMaxG * sizeof(float); }
+
+extern "C" int bags_linear_fwd(const void* x, long long ldx, const void* w, long long ldw,
+                               const float* bias, float* out, long long ldo, int N, int K, int C,
+                               int dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BAGS_REQUIRE(x && w && out, "bags_linear_fwd: NULL operand");
+  BAGS_REQUIRE(N >= 0 && K >= 1 && C >= 1, "bags_linear_fwd: bad shape N=%d K=%d C=%d", N, K, C);
+  BAGS_REQUIRE(dtype == BAGS_DTYPE_F32 || dtype == BAGS_DTYPE_BF16, "bags_linear_fwd: bad dtype %d", dtype);
+  BAGS_REQUIRE(ldx >= K && ldw >= K && ldo >= C, "bags_linear_fwd: leading dimension smaller than row");
+  if (N == 0) return BAGS_OK;
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  if (bias != nullptr) BAGS_REQUIRE((reinterpret_cast<uintptr_t>(bias) & 15) == 0, "bias must be 16-byte aligned");
+  BAGS_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "out must be 16-byte aligned");
+  GemmArgs ga{};
+  ga.a = x; ga.lda = ldx; ga.a_mn = false;
+  ga.b = w; ga.ldb = ldw; ga.b_mn = false;
+  ga.M = N; ga.N = C; ga.K = K; ga.dtype = dtype; ga.splits = 1;
+  ga.p.out = out; ga.p.ldo = ldo; ga.p.bias = bias; ga.p.gscale = nullptr; ga.p.G = 0;
+  ga.p.colsum_in = nullptr; ga.p.colsum_out = nullptr;
+  const int bn = pick_fwd_block_n(N, C, di.num_sms);
+  if (dtype == BAGS_DTYPE_BF16) {
+    return bn == 320 ? launch_gemm<320, false, false, EPI_STORE_F32, false, 4>(ga, di, stream)
+                     : launch_gemm<256, false, false, EPI_STORE_F32, false, 4>(ga, di, stream);
+  }
+  return bn == 320 ? launch_gemm<320, false, false, EPI_STORE_F32, true, 4>(ga, di, stream)
+                   : launch_gemm<256, false, false, EPI_STORE_F32, true, 4>(ga, di, stream);
+}
+
+extern "C" int bags_sample_others(const int64_t* labels, const int32_t* label2bin, int N, int G,
+                                  int classes, double ratio, uint64_t seed, uint8_t* wmask,
+                                  float* avg, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BAGS_REQUIRE(labels && label2bin && wmask && avg, "bags_sample_others: NULL argument");
+  BAGS_REQUIRE(G >= 1 && G <= kMaxG && classes >= 1 && N >= 0, "bags_sample_others: bad shape");
+  BAGS_REQUIRE(ratio >= 0.0, "bags_sample_others: negative ratio");
+  sample_others_kernel<<<G, 1024, 0, stream>>>(reinterpret_cast<const long long*>(labels), label2bin,
+                                               classes, G, N, ratio, static_cast<unsigned long long>(seed),
+                                               wmask, avg);
+  BAGS_CUDA(cudaGetLastError());
+  return BAGS_OK;
+}
+
+extern "C" int bags_mask_avg(const uint8_t* wmask, int N, int G, float* avg, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BAGS_REQUIRE(wmask && avg, "bags_mask_avg: NULL argument");
+  BAGS_REQUIRE(G >= 1 && G <= kMaxG && N >= 0, "bags_mask_avg: bad shape");
+  mask_avg_kernel<<<G, 256, 0, stream>>>(wmask, N, avg);
+  BAGS_CUDA(cudaGetLastError());
+  return BAGS_OK;
+}
+
+template <int NV>
+static int launch_group_ce(const float* logits, long long ldz, const int64_t* labels,
+                           const int32_t* label2bin, const GroupTable& gt, const uint8_t* wmask,
+                           const float* avg, int N, int C, int classes, float* loss, float* lse,
+                           void* dz, long long ldd, int dz_dtype, float* colsum, void* workspace,
+                           int num_sms, cudaStream_t stream) {
+  const int smem = 8 * NV * 128 * (int)sizeof(float);
+  int per_sm = (200 * 1024) / (smem + 2048);
+  if (per_sm > 6) per_sm = 6;
+  if (per_sm < 1) per_sm = 1;
+  int grid = (N + 7) / 8;
+  if (grid > num_sms * per_sm) grid = num_sms * per_sm;
+  if (grid > 4096) grid = 4096;
+  if (grid < 1) grid = 1;
+  unsigned int* counter = reinterpret_cast<unsigned int*>(workspace);
+  float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
+  const long long* lab = reinterpret_cast<const long long*>(labels);
+  if (dz_dtype == BAGS_DTYPE_F32) {
+    auto k = group_ce_kernel<NV, true>;
+    BAGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k<<<grid, 256, smem, stream>>>(logits, ldz, lab, label2bin, classes, gt, wmask, avg, N, C, loss, lse, dz, ldd,
+                                   colsum, part, counter);
+  } else {
+    auto k = group_ce_kernel<NV, false>;
+    BAGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k<<<grid, 256, smem, stream>>>(logits, ldz, lab, label2bin, classes, gt, wmask, avg, N, C, loss, lse, dz, ldd,
+                                   colsum, part, counter);
+  }
+  BAGS_CUDA(cudaGetLastError());
+  return BAGS_OK;
+}
+
+extern "C" int bags_group_ce(const float* logits, long long ldz, const int64_t* labels,
+                             const int32_t* label2bin, const int32_t* slices_host,
+                             const uint8_t* wmask, const float* avg, int N, int C, int G,
+                             int classes, float* loss, float* lse, void* dz, long long ldd,
+                             int dz_dtype, float* colsum, void* workspace, size_t workspace_bytes,
+                             void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BAGS_REQUIRE(logits && labels && label2bin && loss && workspace, "bags_group_ce: NULL argument");
+  BAGS_REQUIRE(workspace_bytes >= bags_workspace_bytes(), "bags_group_ce: workspace too small (%zu < %zu)",
+               workspace_bytes, bags_workspace_bytes());
+  BAGS_REQUIRE(N >= 0 && C >= 4 && (C % 4) == 0 && C <= 4096, "bags_group_ce: C=%d must be a multiple of 4 in [4,4096]", C);
+  BAGS_REQUIRE((ldz % 4) == 0 && ldz >= C, "bags_group_ce: ldz=%lld must be a multiple of 4 and >= C", ldz);
+  BAGS_REQUIRE((reinterpret_cast<uintptr_t>(logits) & 15) == 0, "bags_group_ce: logits not 16-byte aligned");
+  BAGS_REQUIRE(dz_dtype == BAGS_DTYPE_F32 || dz_dtype == BAGS_DTYPE_BF16, "bags_group_ce: bad dz dtype");
+  if (dz != nullptr) {
+    BAGS_REQUIRE(ldd >= C && (ldd % 8) == 0, "bags_group_ce: ldd=%lld must be a multiple of 8 and >= C", ldd);
+    BAGS_REQUIRE((reinterpret_cast<uintptr_t>(dz) & 15) == 0, "bags_group_ce: dz not 16-byte aligned");
+  }
+  if (colsum != nullptr)
+    BAGS_REQUIRE((reinterpret_cast<uintptr_t>(colsum) & 15) == 0, "bags_group_ce: colsum not 16-byte aligned");
+  GroupTable gt;
+  if (int rc = make_group_table(gt, slices_host, G, C)) return rc;
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  if (colsum != nullptr) BAGS_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * C, stream));
+  if (N == 0) {
+    BAGS_CUDA(cudaMemsetAsync(loss, 0, sizeof(float) * G, stream));
+    return BAGS_OK;
+  }
+  const int nv = (C / 4 + 31) / 32;
+  if (nv <= 10)
+    return launch_group_ce<10>(logits, ldz, labels, label2bin, gt, wmask, avg, N, C, classes, loss, lse, dz, ldd,
+                               dz_dtype, colsum, workspace, di.num_sms, stream);
+  if (nv <= 16)
+    return launch_group_ce<16>(logits, ldz, labels, label2bin, gt, wmask, avg, N, C, classes, loss, lse, dz, ldd,
+                               dz_dtype, colsum, workspace, di.num_sms, stream);
+  return launch_group_ce<32>(logits, ldz, labels, label2bin, gt, wmask, avg, N, C, classes, loss, lse, dz, ldd,
+                             dz_dtype, colsum, workspace, di.num_sms, stream);
+}
+
+extern "C" int bags_fwd(const void* x, long long ldx, const void* w, long long ldw,
+                        const float* bias, const int64_t* labels, const int32_t* label2bin,
+                        const int32_t* slices_host, const uint8_t* wmask, const float* avg, int N,
+                        int K, int C, int G, int classes, int dtype, float* logits, long long ldz,
+                        float* loss, float* lse, void* dz, long long ldd, float* colsum,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = bags_linear_fwd(x, ldx, w, ldw, bias, logits, ldz, N, K, C, dtype, stream)) return rc;
+  return bags_group_ce(logits, ldz, labels, label2bin, slices_host, wmask, avg, N, C, G, classes, loss,
+                       lse, dz, ldd, dtype, colsum, workspace, workspace_bytes, stream);
+}
+
+// dst[r, :] = src[r, :] * gout[bin(r)]   (rows = logit columns)
+template <typename T>
+__global__ void __launch_bounds__(256)
+scale_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, long long ld, int rows, int cols,
+                  GroupTable gt, const float* __restrict__ gout) {
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    float s = 0.f;
+    for (int g = 0; g < gt.G; ++g)
+      if (r >= gt.start[g] && r < gt.start[g] + gt.len[g]) s = __ldg(gout + g);
+    for (int c = threadIdx.x; c < cols; c += 256) {
+      const float v = static_cast<float>(src[(long long)r * ld + c]) * s;
+      dst[(long long)r * ld + c] = static_cast<T>(v);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+scale_colsum_kernel(const float* __restrict__ colsum, float* __restrict__ db, int C, GroupTable gt,
+                    const float* __restrict__ gout) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  float s = (gout == nullptr) ? 1.f : 0.f;
+  if (gout != nullptr)
+    for (int g = 0; g < gt.G; ++g)
+      if (c >= gt.start[g] && c < gt.start[g] + gt.len[g]) s = __ldg(gout + g);
+  db[c] = s * colsum[c];
+}
+
+extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long ldx, const void* w,
+                        long long ldw, const float* gout, const int32_t* slices_host,
+                        const float* colsum, float* dW, long long lddw, float* db, void* dX,
+                        long long lddx, void* wscratch, int N, int K, int C, int G, int dtype,
+                        void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BAGS_REQUIRE(dz != nullptr, "bags_bwd: dz is NULL");
+  BAGS_REQUIRE(dtype == BAGS_DTYPE_F32 || dtype == BAGS_DTYPE_BF16, "bags_bwd: bad dtype %d", dtype);
+  BAGS_REQUIRE(N >= 0 && K >= 1 && C >= 1, "bags_bwd: bad shape");
+  GroupTable gt;
+  if (int rc = make_group_table(gt, slices_host, G, C)) return rc;
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  if (db != nullptr) BAGS_REQUIRE(colsum != nullptr, "bags_bwd: db requested but colsum is NULL");
+
+  if (dW != nullptr) {
+    BAGS_REQUIRE(x != nullptr, "bags_bwd: x is NULL but dW requested");
+    BAGS_REQUIRE(lddw >= K && (lddw % 4) == 0 && (reinterpret_cast<uintptr_t>(dW) & 15) == 0,
+                 "bags_bwd: dW must be 16-byte aligned with lddw %% 4 == 0");
+    BAGS_CUDA(cudaMemset2DAsync(dW, lddw * sizeof(float), 0, K * sizeof(float), C, stream));
+    if (N > 0) {
+      GemmArgs ga{};
+      ga.a = dz; ga.lda = ldd; ga.a_mn = true;   // A = dz^T : [C, N_roi], stored [N_roi, C]
+      ga.b = x;  ga.ldb = ldx; ga.b_mn = true;   // B = x^T  : [K, N_roi], stored [N_roi, K]
+      ga.M = C; ga.N = K; ga.K = N; ga.dtype = dtype;
+      const int tiles = ((C + 127) / 128) * ((K + 255) / 256);
+      const int kblocks = (N + (dtype == BAGS_DTYPE_BF16 ? 63 : 31)) / (dtype == BAGS_DTYPE_BF16 ? 64 : 32);
+      ga.splits = env_int("BAGS_DW_SPLITS", pick_splits(tiles, kblocks, di.num_sms));
+      ga.p.out = dW; ga.p.ldo = lddw; ga.p.bias = nullptr;
+      ga.p.gscale = gout; ga.p.G = gt.G;
+      for (int g = 0; g < kMaxGroups; ++g) { ga.p.gstart[g] = gt.start[g]; ga.p.glen[g] = gt.len[g]; }
+      if (gout == nullptr) { ga.p.G = 0; }
+      ga.p.colsum_in = (db != nullptr) ? colsum : nullptr;
+      ga.p.colsum_out = (db != nullptr && colsum != nullptr) ? db : nullptr;
+      int rc = (dtype == BAGS_DTYPE_BF16)
+                   ? launch_gemm<256, true, true, EPI_RED_F32, false, 4>(ga, di, stream)
+                   : launch_gemm<256, true, true, EPI_RED_F32, true, 4>(ga, di, stream);
+      if (rc) return rc;
+    }
+  }
+  if (db != nullptr && (dW == nullptr || N == 0)) {
+    scale_colsum_kernel<<<(C + 255) / 256, 256, 0, stream>>>(colsum, db, C, gt, gout);
+    BAGS_CUDA(cudaGetLastError());
+  }
+
+  if (dX != nullptr && N > 0) {
+    BAGS_REQUIRE(w != nullptr, "bags_bwd: w is NULL but dX requested");
+    const void* wb = w;
+    if (gout != nullptr) {
+      BAGS_REQUIRE(wscratch != nullptr, "bags_bwd: wscratch is required when dX and gout are both given");
+      const int grid = C < 2 * di.num_sms ? C : 2 * di.num_sms;
+      if (dtype == BAGS_DTYPE_BF16)
+        scale_rows_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
+            reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<__nv_bfloat16*>(wscratch), ldw, C, K, gt, gout);
+      else
+        scale_rows_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(w),
+                                                           reinterpret_cast<float*>(wscratch), ldw, C, K, gt, gout);
+      BAGS_CUDA(cudaGetLastError());
+      wb = wscratch;
+    }
+    GemmArgs ga{};
+    ga.a = dz; ga.lda = ldd; ga.a_mn = false;  // A = dz : [N_roi, C]
+    ga.b = wb; ga.ldb = ldw; ga.b_mn = true;   // B = W^T: [K, C], stored [C, K]
+    ga.M = N; ga.N = K; ga.K = C; ga.dtype = dtype; ga.splits = 1;
+    ga.p.out = dX; ga.p.ldo = lddx; ga.p.bias = nullptr; ga.p.gscale = nullptr; ga.p.G = 0;
+    ga.p.colsum_in = nullptr; ga.p.colsum_out = nullptr;
+    BAGS_REQUIRE((reinterpret_cast<uintptr_t>(dX) & 15) == 0, "bags_bwd: dX not 16-byte aligned");
+    int rc = (dtype == BAGS_DTYPE_BF16)
+                 ? launch_gemm<256, false, true, EPI_STORE_BF16, false, 4>(ga, di, stream)
+                 : launch_gemm<256, false, true, EPI_STORE_F32, true, 4>(ga, di, stream);
+    if (rc) return rc;
+  }
+  return BAGS_OK;
+}
+
+extern "C" int bags_merge_scores(const float* logits, long long ldz, const int32_t* slices_host,
+                                 const int32_t* cls2col, int N, int C, int G, int classes,
+                                 float* scores, long long lds, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BAGS_REQUIRE(logits && cls2col && scores, "bags_merge_scores: NULL argument");
+  BAGS_REQUIRE(N >= 0 && C >= 4 && (C % 4) == 0 && C <= 4096, "bags_merge_scores: C=%d must be a multiple of 4 in [4,4096]", C);
+  BAGS_REQUIRE((ldz % 4) == 0 && ldz >= C && lds >= classes, "bags_merge_scores: bad leading dimension");
+  BAGS_REQUIRE((reinterpret_cast<uintptr_t>(logits) & 15) == 0, "bags_merge_scores: logits not 16-byte aligned");
+  GroupTable gt;
+  if (int rc = make_group_table(gt, slices_host, G, C)) return rc;
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  if (N == 0) return BAGS_OK;
+  const int nv = (C / 4 + 31) / 32;
+  int grid = (N + 7) / 8;
+  if (grid > di.num_sms * 4) grid = di.num_sms * 4;
+#define BAGS_LAUNCH_MERGE(NV)                                                                              \
+  do {                                                                                                     \
+    const int smem = 8 * NV * 128 * (int)sizeof(float);                                                    \
+    auto k = merge_scores_kernel<NV>;                                                                      \
+    BAGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));               \
+    k<<<grid, 256, smem, stream>>>(logits, ldz, gt, cls2col, N, C, classes, scores, lds);                  \
+  } while (0)
+  if (nv <= 10) BAGS_LAUNCH_MERGE(10);
+  else if (nv <= 16) BAGS_LAUNCH_MERGE(16);
+  else BAGS_LAUNCH_MERGE(32);
+#undef BAGS_LAUNCH_MERGE
+  BAGS_CUDA(cudaGetLastError());
+  return BAGS_OK;
+}
+
+extern "C" int bags_cast_bf16(const float* src, long long lds, void* dst, long long ldd, int rows,
+                              int cols, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BAGS_REQUIRE(src && dst, "bags_cast_bf16: NULL argument");
+  BAGS_REQUIRE(rows >= 0 && cols >= 0 && (cols % 4) == 0 && (lds % 4) == 0 && (ldd % 4) == 0,
+               "bags_cast_bf16: cols and leading dims must be multiples of 4");
+  if (rows == 0 || cols == 0) return BAGS_OK;
+  const long long total = (long long)rows * (cols / 4);
+  long long grid = (total + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  cast_bf16_kernel<<<(int)grid, 256, 0, stream>>>(src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, rows, cols);
+  BAGS_CUDA(cudaGetLastError());
+  return BAGS_OK;
+}
+
+extern "C" int bags_gemm_probe(const void* a, long long lda, int a_mn, const void* b, long long ldb,
+                               int b_mn, void* out, long long ldo, int M, int N, int K, int dtype,
+                               int block_n, int splits, int epi, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BAGS_REQUIRE(a && b && out, "bags_gemm_probe: NULL argument");
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  GemmArgs ga{};
+  ga.a = a; ga.lda = lda; ga.a_mn = a_mn != 0;
+  ga.b = b; ga.ldb = ldb; ga.b_mn = b_mn != 0;
+  ga.M = M; ga.N = N; ga.K = K; ga.dtype = dtype; ga.splits = splits;
+  ga.p.out = out; ga.p.ldo = ldo; ga.p.bias = nullptr; ga.p.gscale = nullptr; ga.p.G = 0;
+  ga.p.colsum_in = nullptr; ga.p.colsum_out = nullptr;
+  const bool bf = dtype == BAGS_DTYPE_BF16;
+  BAGS_REQUIRE(bf || dtype == BAGS_DTYPE_F32, "bags_gemm_probe: bad dtype");
+  // the instantiations the product uses
+  if (!a_mn && !b_mn && epi == 0 && block_n == 320)
+    return bf ? launch_gemm<320, false, false, EPI_STORE_F32, false, 4>(ga, di, stream)
+              : launch_gemm<320, false, false, EPI_STORE_F32, true, 4>(ga, di, stream);
+  if (!a_mn && !b_mn && epi == 0 && block_n == 256)
+    return bf ? launch_gemm<256, false, false, EPI_STORE_F32, false, 4>(ga, di, stream)
+              : launch_gemm<256, false, false, EPI_STORE_F32, true, 4>(ga, di, stream);
+  if (!a_mn && b_mn && block_n == 256 && ((bf && epi == 1) || (!bf && epi == 0)))
+    return bf ? launch_gemm<256, false, true, EPI_STORE_BF16, false, 4>(ga, di, stream)
+              : launch_gemm<256, false, true, EPI_STORE_F32, true, 4>(ga, di, stream);
+  if (a_mn && b_mn && block_n == 256 && epi == 2)
+    return bf ? launch_gemm<256, true, true, EPI_RED_F32, false, 4>(ga, di, stream)
+              : launch_gemm<256, true, true, EPI_RED_F32, true, 4>(ga, di, stream);
+  return fail(BAGS_ERR_INVALID, "bags_gemm_probe: configuration a_mn=%d b_mn=%d block_n=%d epi=%d dtype=%d not instantiated",
+              a_mn, b_mn, block_n, epi, dtype);
+}

@@ -1,0 +1,333 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   D[M,N] (+)= A[M,K] * B[N,K]^T       fp32 accumulation in TMEM
+//
+// A and B are each either "K-major" (contraction index contiguous in HBM, i.e.
+// a row-major [rows,K] matrix) or "MN-major" (row-major [K,rows]: contraction
+// index strided).  That covers the three contractions of the BAGS head without
+// any transposed copies in HBM:
+//
+//   forward  z  = X  W^T  : A = X   [N_roi,K]  K-major , B = W   [C,K]      K-major
+//   backward dX = dz W    : A = dz  [N_roi,C]  K-major , B = W   [C,K]      MN-major
+//   backward dW = dz^T X  : A = dz  [N_roi,C]  MN-major, B = X   [N_roi,K]  MN-major
+//
+// Pipeline (one CTA per SM, 192 threads):
+//   warp 0      : TMA producer   (cp.async.bulk.tensor, 128B swizzle, mbarrier tx)
+//   warp 1      : UMMA issuer    (one thread; tcgen05.mma cta_group::1, M=128)
+//   warps 2..5  : epilogue       (tcgen05.ld 32x32b -> registers -> global)
+// smem ring of kStages {A tile, B tile}; TMEM holds kAccStages accumulators so
+// the epilogue of tile i overlaps the mainloop of tile i+1.
+#pragma once
+#include "bags_ptx.cuh"
+
+namespace bags {
+
+enum EpiMode : int {
+  EPI_STORE_F32 = 0,   // out fp32 = acc (+ bias[n])
+  EPI_STORE_BF16 = 1,  // out bf16 = acc
+  EPI_RED_F32 = 2,     // out fp32 += rowscale(m) * acc   (split-K via red.global)
+};
+
+constexpr int kMaxGroups = 8;
+
+struct GemmParams {
+  int M, N, K;         // logical problem
+  int num_m_tiles, num_n_tiles, num_splits;
+  int kblocks_total;   // ceil(K / BLOCK_K)
+  void* out;           // [M, ldo]
+  long long ldo;       // elements
+  const float* bias;   // [N] or nullptr                    (EPI_STORE_F32)
+  // EPI_RED_F32: per-row scale = gscale[group(m)], groups = [gstart, gstart+glen)
+  const float* gscale; // device [G] or nullptr (=> 1.0)
+  int G;
+  int gstart[kMaxGroups];
+  int glen[kMaxGroups];
+  const float* colsum_in;  // optional [M]: db_out[m] = rowscale(m) * colsum_in[m]
+  float* colsum_out;       // written by the (n_tile==0, split==0) unit
+};
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool TF32, int STAGES>
+struct GemmCfg {
+  static constexpr int BLOCK_M = 128;
+  static constexpr int ELT = TF32 ? 4 : 2;
+  static constexpr int BLOCK_K = 128 / ELT;          // 64 bf16 / 32 tf32 : one 128B swizzle row
+  static constexpr int UMMA_K = 32 / ELT;            // 16 bf16 / 8 tf32
+  static constexpr int K_STEPS = BLOCK_K / UMMA_K;   // 4
+  static constexpr int N_MMA = (BLOCK_N > 256) ? 2 : 1;
+  static constexpr int UMMA_N = BLOCK_N / N_MMA;
+  static constexpr int ACC_STAGES = (2 * BLOCK_N <= 512) ? 2 : 1;
+  static constexpr int TMEM_COLS_RAW = ACC_STAGES * BLOCK_N;
+  static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128 : TMEM_COLS_RAW <= 256 ? 256 : 512;
+  static constexpr int A_BYTES = BLOCK_M * 128;      // 16 KB
+  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SLAB = 128 / ELT;             // MN elements per 128B (MN-major slab width)
+  // TMA boxes per stage
+  static constexpr int A_BOXES = A_MN ? BLOCK_M / SLAB : 1;
+  static constexpr int A_BOX_BYTES = A_BYTES / A_BOXES;
+  static constexpr int B_BOXES = B_MN ? BLOCK_N / SLAB : N_MMA;
+  static constexpr int B_BOX_BYTES = B_BYTES / B_BOXES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int NUM_THREADS = 192;
+  static_assert(UMMA_N % 16 == 0 && UMMA_N >= 16 && UMMA_N <= 256, "invalid UMMA N");
+  static_assert(!B_MN || (BLOCK_N % SLAB == 0 && N_MMA == 1), "MN-major B needs slab-aligned single MMA");
+  static_assert((UMMA_N * 128) % 1024 == 0, "B half offset must keep 1024B swizzle alignment");
+  static_assert(TMEM_COLS_RAW <= 512, "accumulators exceed TMEM");
+};
+
+__device__ __forceinline__ float row_group_scale(const GemmParams& p, int m) {
+  if (p.gscale == nullptr) return 1.0f;
+  float s = 0.0f;
+#pragma unroll
+  for (int g = 0; g < kMaxGroups; ++g) {
+    if (g < p.G && m >= p.gstart[g] && m < p.gstart[g] + p.glen[g]) s = __ldg(p.gscale + g);
+  }
+  return s;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool TF32, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+bags_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N, A_MN, B_MN, EPI, TF32, STAGES>;
+  constexpr int BLOCK_M = Cfg::BLOCK_M;
+  constexpr int BLOCK_K = Cfg::BLOCK_K;
+
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle atoms.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + Cfg::ACC_STAGES;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * Cfg::ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+#pragma unroll
+    for (int a = 0; a < Cfg::ACC_STAGES; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  const int units_per_split = p.num_m_tiles * p.num_n_tiles;
+  const int num_units = units_per_split * p.num_splits;
+  // balanced k-block ranges per split
+  auto split_range = [&](int split, int& kb0, int& kb1) {
+    const int base = p.kblocks_total / p.num_splits, rem = p.kblocks_total % p.num_splits;
+    kb0 = split * base + (split < rem ? split : rem);
+    kb1 = kb0 + base + (split < rem ? 1 : 0);
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        const int split = u / units_per_split;
+        const int t = u - split * units_per_split;
+        const int m_tile = t / p.num_n_tiles, n_tile = t - m_tile * p.num_n_tiles;
+        const int m0 = m_tile * BLOCK_M, n0 = n_tile * BLOCK_N;
+        int kb0, kb1;
+        split_range(split, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          const int k0 = kb * BLOCK_K;
+          uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
+          uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
+#pragma unroll
+          for (int i = 0; i < Cfg::A_BOXES; ++i) {
+            if (A_MN) tma_load_2d(sa + i * Cfg::A_BOX_BYTES, &tmap_a, &full_bar[stage], m0 + i * Cfg::SLAB, k0);
+            else      tma_load_2d(sa + i * Cfg::A_BOX_BYTES, &tmap_a, &full_bar[stage], k0, m0);
+          }
+#pragma unroll
+          for (int i = 0; i < Cfg::B_BOXES; ++i) {
+            if (B_MN) tma_load_2d(sb + i * Cfg::B_BOX_BYTES, &tmap_b, &full_bar[stage], n0 + i * Cfg::SLAB, k0);
+            else      tma_load_2d(sb + i * Cfg::B_BOX_BYTES, &tmap_b, &full_bar[stage], k0, n0 + i * Cfg::UMMA_N);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== UMMA issuer (single thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_instr_desc(TF32 ? 2u : 1u, A_MN, B_MN, BLOCK_M, Cfg::UMMA_N);
+      // K-major (128B swizzle): rows are 128 B, 8-row atoms are 1024 B apart (SBO);
+      //   a K step of UMMA_K elements advances the start address by 32 B.
+      // MN-major (128B swizzle): 64(bf16)-wide MN slabs, each K row is 128 B, 8-row
+      //   K groups 1024 B apart (SBO), slabs BLOCK_K*128 B apart (LBO);
+      //   a K step advances UMMA_K rows = UMMA_K*128 B.
+      // MN-major tf32 must use the 32B-atom swizzle: K atoms are 4 rows (512 B) instead of 8.
+      constexpr uint64_t A_LAYOUT = (A_MN && TF32) ? kSwizzle128B_Base32B : kSwizzle128B;
+      constexpr uint64_t B_LAYOUT = (B_MN && TF32) ? kSwizzle128B_Base32B : kSwizzle128B;
+      constexpr uint32_t A_LBO = A_MN ? BLOCK_K * 128 : 16, A_SBO = (A_MN && TF32) ? 512 : 1024;
+      constexpr uint32_t B_LBO = B_MN ? BLOCK_K * 128 : 16, B_SBO = (B_MN && TF32) ? 512 : 1024;
+      constexpr uint32_t A_KSTEP = A_MN ? Cfg::UMMA_K * 128 : 32;
+      constexpr uint32_t B_KSTEP = B_MN ? Cfg::UMMA_K * 128 : 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++local) {
+        const int split = u / units_per_split;
+        int kb0, kb1;
+        split_range(split, kb0, kb1);
+        const int acc = local % Cfg::ACC_STAGES;
+        const uint32_t acc_phase = (local / Cfg::ACC_STAGES) & 1u;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_a + stage * Cfg::A_BYTES);
+          const uint32_t sb = smem_u32(smem_b + stage * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < Cfg::K_STEPS; ++k) {
+            const uint64_t adesc = make_smem_desc(sa + k * A_KSTEP, A_LBO, A_SBO, A_LAYOUT);
+#pragma unroll
+            for (int h = 0; h < Cfg::N_MMA; ++h) {
+              const uint64_t bdesc = make_smem_desc(sb + h * Cfg::UMMA_N * 128 + k * B_KSTEP, B_LBO, B_SBO, B_LAYOUT);
+              const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+              if (TF32) umma_tf32(d_tmem + h * Cfg::UMMA_N, adesc, bdesc, idesc, accum);
+              else      umma_bf16(d_tmem + h * Cfg::UMMA_N, adesc, bdesc, idesc, accum);
+            }
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    int local = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++local) {
+      const int split = u / units_per_split;
+      const int t = u - split * units_per_split;
+      const int m_tile = t / p.num_n_tiles, n_tile = t - m_tile * p.num_n_tiles;
+      const int m = m_tile * BLOCK_M + quarter * 32 + lane;
+      const int n0 = n_tile * BLOCK_N;
+      const int acc = local % Cfg::ACC_STAGES;
+      const uint32_t acc_phase = (local / Cfg::ACC_STAGES) & 1u;
+      int kb0, kb1;
+      split_range(split, kb0, kb1);
+
+      float scale = 1.0f;
+      if (EPI == EPI_RED_F32) {
+        scale = (m < p.M) ? row_group_scale(p, m) : 0.0f;
+        if (p.colsum_out != nullptr && n_tile == 0 && split == 0 && m < p.M)
+          p.colsum_out[m] = scale * __ldg(p.colsum_in + m);
+      }
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+      const bool row_ok = (m < p.M) && (kb1 > kb0);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_row + c, v);
+        tmem_ld_wait();
+        const int n = n0 + c;
+        if (row_ok && n < p.N) {
+          if (EPI == EPI_STORE_F32) {
+            float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(m) * p.ldo + n;
+            const bool vec_ok = ((p.ldo & 3) == 0) && (n + 32 <= p.N);
+            if (vec_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 r;
+                r.x = __uint_as_float(v[j + 0]); r.y = __uint_as_float(v[j + 1]);
+                r.z = __uint_as_float(v[j + 2]); r.w = __uint_as_float(v[j + 3]);
+                if (p.bias != nullptr) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+                  r.x += b.x; r.y += b.y; r.z += b.z; r.w += b.w;
+                }
+                *reinterpret_cast<float4*>(o + j) = r;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (n + j < p.N) {
+                  float r = __uint_as_float(v[j]);
+                  if (p.bias != nullptr) r += __ldg(p.bias + n + j);
+                  o[j] = r;
+                }
+              }
+            }
+          } else if (EPI == EPI_STORE_BF16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(m) * p.ldo + n;
+            const bool vec_ok = ((p.ldo & 7) == 0) && (n + 32 <= p.N);
+            if (vec_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 r;
+                r.x = pack_bf16x2(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
+                r.y = pack_bf16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                r.z = pack_bf16x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+                r.w = pack_bf16x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+                *reinterpret_cast<uint4*>(o + j) = r;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n + j < p.N) o[j] = __float2bfloat16_rn(__uint_as_float(v[j]));
+            }
+          } else {  // EPI_RED_F32
+            float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(m) * p.ldo + n;
+            const bool vec_ok = ((p.ldo & 3) == 0) && (n + 32 <= p.N);
+            if (vec_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                red_add_v4_f32(o + j, scale * __uint_as_float(v[j + 0]), scale * __uint_as_float(v[j + 1]),
+                               scale * __uint_as_float(v[j + 2]), scale * __uint_as_float(v[j + 3]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n + j < p.N) red_add_f32(o + j, scale * __uint_as_float(v[j]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace bags

@@ -1,0 +1,476 @@
+// HBM-bound kernels of the BAGS head (everything that is not the fc_cls contraction):
+//
+//   group_ce_kernel      per-bin log-softmax / NLL over logit slices, per-bin loss,
+//                        and the un-scaled logit gradient dz~ ("grad in forward")
+//                        reference: gs_bbox_head_with0.py:91-112,134-171 ;
+//                                   losses/cross_entropy_loss.py:9-19 ; losses/utils.py:26-53
+//   sample_others_kernel device replacement of _sample_others (gs_bbox_head_with0.py:63-89):
+//                        exact-k uniform subset of the "others" rows, no host sync
+//   mask_avg_kernel      avg_g = max(sum_n w_g[n], 1)   (gs_bbox_head_with0.py:109)
+//   merge_scores_kernel  test-time score merge (gs_bbox_head_with0.py:239-273)
+//   cast kernels         fp32 -> bf16 operand staging
+#pragma once
+#include "bags_ptx.cuh"
+
+namespace bags {
+
+constexpr int kMaxG = 8;
+
+struct GroupTable {
+  int G;
+  int start[kMaxG];
+  int len[kMaxG];
+};
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// ----------------------------------------------------------------------------
+// grouped softmax cross-entropy, forward + logit gradient
+// ----------------------------------------------------------------------------
+// One warp per RoI row, the row staged in shared memory (coalesced 16 B loads),
+// then per bin: max -> exp/sum (exp written back to smem) -> loss; finally one
+// vectorised pass writes dz~ = w/avg * (softmax - onehot) for every column.
+//
+//   z        [N, ldz] fp32 logits (ldz % 4 == 0, 16 B aligned rows)
+//   labels   [N] int64 in [0, classes)
+//   l2b      [G, classes] int32 : label -> in-bin label (0 = "others")
+//   wmask    [G, N] uint8 0/1 sample weights, or nullptr (all ones)
+//   avg      [G] fp32 normalisers (device), or nullptr (=> N)
+//   loss     [G] fp32 out : sum_n w*(lse - z_t) / avg
+//   lse      [N, G] fp32 out (optional)
+//   dz       [N, ldd] bf16 (DZ_F32 = false) or fp32 (true), optional
+//   colsum   [C] fp32, += sum_n dz~[n, c]  (optional; caller zeroes)
+//   part     [gridDim.x, kMaxG] fp32 scratch ; counter: 1 uint32 (zero on entry, reset on exit)
+template <int NV, bool DZ_F32>
+__global__ void __launch_bounds__(256)
+group_ce_kernel(const float* __restrict__ z, long long ldz, const long long* __restrict__ labels,
+                const int* __restrict__ l2b, int classes, GroupTable gt,
+                const uint8_t* __restrict__ wmask, const float* __restrict__ avg, int N, int C,
+                float* __restrict__ loss, float* __restrict__ lse, void* __restrict__ dz,
+                long long ldd, float* __restrict__ colsum, float* __restrict__ part,
+                unsigned int* __restrict__ counter) {
+  extern __shared__ __align__(16) float smem_rows[];  // [8 warps][NV*128]
+  __shared__ float s_scale[8][kMaxG];   // coef / sum   per (warp, bin) for the current row
+  __shared__ float s_coef[8][kMaxG];    // w / avg
+  __shared__ int s_tcol[8][kMaxG];      // absolute target column
+  __shared__ float s_lacc[8][kMaxG];    // per-warp loss accumulators
+  __shared__ float s_inv_avg[kMaxG];
+  __shared__ bool s_last;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* row = smem_rows + warp * (NV * 128);
+  const int nchunks = C >> 2;  // float4 chunks (C % 4 == 0 checked on host)
+
+  if (threadIdx.x < kMaxG) {
+    const int g = threadIdx.x;
+    s_inv_avg[g] = (g < gt.G) ? 1.0f / (avg != nullptr ? __ldg(avg + g) : fmaxf((float)N, 1.0f)) : 0.f;
+  }
+  if (lane < kMaxG) s_lacc[warp][lane] = 0.f;
+
+  // Row-invariant map: bin of float4 chunk (lane + 32 j); -1 = no bin, -2 = straddles a boundary.
+  int gidx[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c0 = 4 * (lane + 32 * j);
+    int g0 = -1, g3 = -1;
+    for (int g = 0; g < gt.G; ++g) {
+      if (c0 >= gt.start[g] && c0 < gt.start[g] + gt.len[g]) g0 = g;
+      if (c0 + 3 >= gt.start[g] && c0 + 3 < gt.start[g] + gt.len[g]) g3 = g;
+    }
+    gidx[j] = (g0 == g3) ? g0 : -2;
+  }
+  float csum[NV][4];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) { csum[j][0] = csum[j][1] = csum[j][2] = csum[j][3] = 0.f; }
+  __syncthreads();
+
+  for (int n = blockIdx.x * 8 + warp; n < N; n += gridDim.x * 8) {
+    // ---- stage the row (coalesced 16 B loads) ----
+    const float4* zr = reinterpret_cast<const float4*>(z + (long long)n * ldz);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = lane + 32 * j;
+      if (c < nchunks) reinterpret_cast<float4*>(row)[c] = ldg_stream_f4(zr + c);
+    }
+    __syncwarp();
+    const long long lab = __ldg(labels + n);
+    const bool lab_ok = (lab >= 0 && lab < classes);
+
+    for (int g = 0; g < gt.G; ++g) {
+      const int s = gt.start[g], len = gt.len[g];
+      int t = lab_ok ? __ldg(l2b + g * classes + (int)lab) : 0;
+      t = (t >= 0 && t < len) ? t : 0;
+      const float w = (wmask != nullptr) ? (float)__ldg(wmask + (long long)g * N + n) : 1.0f;
+      // pass 1: max
+      float m = -INFINITY;
+      for (int i = lane; i < len; i += 32) m = fmaxf(m, row[s + i]);
+      m = warp_max(m);
+      const float zt = row[s + t];  // broadcast read, before pass 2 overwrites
+      __syncwarp();
+      // pass 2: e = exp(v - m) kept in smem, sum
+      const float mb = m * kLog2e;
+      float sum = 0.f;
+      for (int i = lane; i < len; i += 32) {
+        const float e = exp2f(fmaf(row[s + i], kLog2e, -mb));
+        row[s + i] = e;
+        sum += e;
+      }
+      sum = warp_sum(sum);
+      const float lse_v = m + logf(sum);
+      if (lane == 0) {
+        if (lse != nullptr) lse[(long long)n * gt.G + g] = lse_v;
+        s_lacc[warp][g] += w * (lse_v - zt);
+        const float coef = w * s_inv_avg[g];
+        s_coef[warp][g] = coef;
+        s_scale[warp][g] = coef / sum;
+        s_tcol[warp][g] = s + t;
+      }
+    }
+    __syncwarp();
+
+    // ---- pass 3: dz~ = w/avg * (softmax - onehot) for the whole row, vectorised ----
+    if (dz != nullptr || colsum != nullptr) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int c = lane + 32 * j;
+        if (c < nchunks) {
+          const float4 e4 = reinterpret_cast<const float4*>(row)[c];
+          const float e[4] = {e4.x, e4.y, e4.z, e4.w};
+          float d[4];
+          const int gj = gidx[j];
+          if (gj >= 0) {
+            const float sc = s_scale[warp][gj], cf = s_coef[warp][gj];
+            const int tq = s_tcol[warp][gj] - 4 * c;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) d[q] = e[q] * sc - (q == tq ? cf : 0.f);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int col = 4 * c + q;
+              float v = 0.f;
+              if (gj == -2) {
+                for (int g = 0; g < gt.G; ++g)
+                  if (col >= gt.start[g] && col < gt.start[g] + gt.len[g])
+                    v = e[q] * s_scale[warp][g] - (col == s_tcol[warp][g] ? s_coef[warp][g] : 0.f);
+              }
+              d[q] = v;
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) csum[j][q] += d[q];
+          if (dz != nullptr) {
+            if (DZ_F32) {
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(dz) + (long long)n * ldd + 4 * c) =
+                  make_float4(d[0], d[1], d[2], d[3]);
+            } else {
+              uint2 o;
+              o.x = pack_bf16x2(d[0], d[1]);
+              o.y = pack_bf16x2(d[2], d[3]);
+              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dz) + (long long)n * ldd + 4 * c) = o;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---- bias-gradient column sums: warp registers -> global atomics ----
+  if (colsum != nullptr) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = lane + 32 * j;
+      if (c < nchunks) red_add_v4_f32(colsum + 4 * c, csum[j][0], csum[j][1], csum[j][2], csum[j][3]);
+    }
+  }
+
+  // ---- per-bin loss: fixed-order two-level reduction (reproducible for a fixed grid) ----
+  __syncthreads();
+  if (threadIdx.x < kMaxG) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += s_lacc[w][threadIdx.x];
+    part[blockIdx.x * kMaxG + threadIdx.x] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(counter, 1u);
+    s_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    if (warp < gt.G) {
+      const int g = warp;
+      float s = 0.f;
+      for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(part + b * kMaxG + g);
+      s = warp_sum(s);
+      if (lane == 0) loss[g] = s * s_inv_avg[g];
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// "others" sampler  (device replacement of np.random.choice on the host)
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {  // murmur3 finaliser
+  x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t sample_key(unsigned long long seed, int g, int n) {
+  uint32_t h = mix32(static_cast<uint32_t>(seed) ^ 0x9e3779b9u);
+  h = mix32(h ^ static_cast<uint32_t>(seed >> 32));
+  h = mix32(h ^ (static_cast<uint32_t>(g) * 0x632be5abu + 0x7f4a7c15u));
+  h = mix32(h ^ static_cast<uint32_t>(n));
+  return h;
+}
+
+// One CTA (1024 threads) per bin.  Bin 0: all ones.  Bin g>=1:
+//   F = #rows with in-bin label > 0 ; k = int(F * ratio) ; O = N - F
+//   F == 0 -> w = 0 ; k >= O -> w = 1 ; else in-bin rows + the k "others" rows with
+//   the smallest (random key, row index) pairs  (a uniform k-subset).
+//   avg_g = max(sum w, 1).
+__global__ void __launch_bounds__(1024)
+sample_others_kernel(const long long* __restrict__ labels, const int* __restrict__ l2b, int classes,
+                     int G, int N, double ratio, unsigned long long seed,
+                     uint8_t* __restrict__ wmask, float* __restrict__ avg) {
+  const int g = blockIdx.x;
+  const int tid = threadIdx.x;
+  __shared__ int s_hist[256];
+  __shared__ int s_warp[32];
+  __shared__ int s_F;
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_need;
+  __shared__ int s_base;
+  uint8_t* w = wmask + (long long)g * N;
+
+  if (g == 0) {
+    for (int n = tid; n < N; n += 1024) w[n] = 1;
+    if (tid == 0) avg[0] = fmaxf((float)N, 1.0f);
+    return;
+  }
+  const int* map = l2b + g * classes;
+  // ---- count in-bin rows ----
+  int cnt = 0;
+  for (int n = tid; n < N; n += 1024) {
+    const long long lab = labels[n];
+    const int t = (lab >= 0 && lab < classes) ? map[lab] : 0;
+    cnt += (t > 0);
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if ((tid & 31) == 0) s_warp[tid >> 5] = cnt;
+  __syncthreads();
+  if (tid == 0) {
+    int F = 0;
+    for (int i = 0; i < 32; ++i) F += s_warp[i];
+    s_F = F;
+  }
+  __syncthreads();
+  const int F = s_F;
+  const int O = N - F;
+  const long long k_ll = (long long)((double)F * ratio);  // Python int(): truncation
+  if (F == 0) {
+    for (int n = tid; n < N; n += 1024) w[n] = 0;
+    if (tid == 0) avg[g] = 1.0f;
+    return;
+  }
+  if (k_ll >= (long long)O) {
+    for (int n = tid; n < N; n += 1024) w[n] = 1;
+    if (tid == 0) avg[g] = fmaxf((float)N, 1.0f);
+    return;
+  }
+  const int k = (int)k_ll;  // 0 <= k < O
+  if (tid == 0) avg[g] = fmaxf((float)(F + k), 1.0f);
+  if (k == 0) {
+    for (int n = tid; n < N; n += 1024) {
+      const long long lab = labels[n];
+      const int t = (lab >= 0 && lab < classes) ? map[lab] : 0;
+      w[n] = (t > 0) ? 1 : 0;
+    }
+    return;
+  }
+  // ---- radix select: the k-th smallest key among "others" ----
+  // after the loop: keys < prefix are all selected; `need` rows with key == prefix remain.
+  uint32_t prefix = 0, mask = 0;
+  int need = k;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    if (tid < 256) s_hist[tid] = 0;
+    __syncthreads();
+    for (int n = tid; n < N; n += 1024) {
+      const long long lab = labels[n];
+      const int t = (lab >= 0 && lab < classes) ? map[lab] : 0;
+      if (t == 0) {
+        const uint32_t key = sample_key(seed, g, n);
+        if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int acc = 0, d = 0;
+      for (; d < 256; ++d) {
+        if (acc + s_hist[d] >= need) break;
+        acc += s_hist[d];
+      }
+      s_prefix = prefix | (static_cast<uint32_t>(d) << shift);
+      s_need = need - acc;
+    }
+    __syncthreads();
+    prefix = s_prefix;
+    need = s_need;
+    mask |= (0xFFu << shift);
+    __syncthreads();
+  }
+  // ---- write weights; ties on the threshold key broken by ascending row index ----
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int n0 = 0; n0 < N; n0 += 1024) {
+    const int n = n0 + tid;
+    bool other = false, tie = false;
+    uint32_t key = 0;
+    int t = 0;
+    if (n < N) {
+      const long long lab = labels[n];
+      t = (lab >= 0 && lab < classes) ? map[lab] : 0;
+      other = (t == 0);
+      if (other) { key = sample_key(seed, g, n); tie = (key == prefix); }
+    }
+    // block-wide exclusive rank of `tie` in row order
+    const unsigned bal = __ballot_sync(0xffffffffu, tie);
+    const int wrank = __popc(bal & ((1u << (tid & 31)) - 1u));
+    if ((tid & 31) == 0) s_warp[tid >> 5] = __popc(bal);
+    __syncthreads();
+    int woff = 0;
+    for (int i = 0; i < (tid >> 5); ++i) woff += s_warp[i];
+    const int rank = s_base + woff + wrank;
+    if (n < N) {
+      uint8_t wv;
+      if (!other) wv = 1;
+      else if (key < prefix) wv = 1;
+      else if (tie && rank < need) wv = 1;
+      else wv = 0;
+      w[n] = wv;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int i = 0; i < 32; ++i) tot += s_warp[i];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+}
+
+// avg_g = max(sum_n w_g[n], 1) for caller-provided masks (parity mode)
+__global__ void __launch_bounds__(256)
+mask_avg_kernel(const uint8_t* __restrict__ wmask, int N, float* __restrict__ avg) {
+  const int g = blockIdx.x;
+  __shared__ int s_w[8];
+  int c = 0;
+  for (int n = threadIdx.x; n < N; n += 256) c += wmask[(long long)g * N + n];
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < 8; ++i) t += s_w[i];
+    avg[g] = fmaxf((float)t, 1.0f);
+  }
+}
+
+// ----------------------------------------------------------------------------
+// test-time score merge
+// ----------------------------------------------------------------------------
+//   p_g = softmax(z[:, slice_g]) ; score[:,0] = p_0[:,0]
+//   score[:, cls] = p_0[:,1] * p_g[:, j]  for the (g>=1, j>=1) column that maps to cls.
+//   cls2col [classes] int32: logit column feeding class `cls` (cls2col[0] = start_0), -1 => 0.
+template <int NV>
+__global__ void __launch_bounds__(256)
+merge_scores_kernel(const float* __restrict__ z, long long ldz, GroupTable gt,
+                    const int* __restrict__ cls2col, int N, int C, int classes,
+                    float* __restrict__ scores, long long lds) {
+  extern __shared__ __align__(16) float smem_rows[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* row = smem_rows + warp * (NV * 128);
+  const int nchunks = C >> 2;
+  for (int n = blockIdx.x * 8 + warp; n < N; n += gridDim.x * 8) {
+    const float4* zr = reinterpret_cast<const float4*>(z + (long long)n * ldz);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = lane + 32 * j;
+      if (c < nchunks) reinterpret_cast<float4*>(row)[c] = ldg_stream_f4(zr + c);
+    }
+    __syncwarp();
+    float inv_sum[kMaxG];
+#pragma unroll
+    for (int g = 0; g < kMaxG; ++g) {
+      inv_sum[g] = 0.f;
+      if (g < gt.G) {
+        const int s = gt.start[g], len = gt.len[g];
+        float m = -INFINITY;
+        for (int i = lane; i < len; i += 32) m = fmaxf(m, row[s + i]);
+        m = warp_max(m);
+        __syncwarp();
+        float sum = 0.f;
+        for (int i = lane; i < len; i += 32) {
+          const float e = expf(row[s + i] - m);
+          row[s + i] = e;
+          sum += e;
+        }
+        sum = warp_sum(sum);
+        inv_sum[g] = 1.0f / sum;
+      }
+    }
+    __syncwarp();
+    const float pfg = (gt.len[0] > 1) ? row[gt.start[0] + 1] * inv_sum[0] : 0.f;
+    float* out = scores + (long long)n * lds;
+    for (int cls = lane; cls < classes; cls += 32) {
+      const int col = __ldg(cls2col + cls);
+      float v = 0.f;
+      if (col >= 0 && col < C) {
+        float is = 0.f;
+        int gsel = -1;
+#pragma unroll
+        for (int g = 0; g < kMaxG; ++g)
+          if (g < gt.G && col >= gt.start[g] && col < gt.start[g] + gt.len[g]) { is = inv_sum[g]; gsel = g; }
+        const float p = row[col] * is;
+        v = (gsel == 0) ? p : pfg * p;
+      }
+      out[cls] = v;
+    }
+    __syncwarp();
+  }
+}
+
+// ----------------------------------------------------------------------------
+// fp32 -> bf16 staging (rows x cols, independent leading dims; cols % 4 == 0 fast path)
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cast_bf16_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst,
+                 long long ldd, int rows, int cols) {
+  const int cv = cols >> 2;
+  const long long total = (long long)rows * cv;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+    const int r = (int)(i / cv), c = (int)(i - (long long)r * cv);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + (long long)r * lds) + c);
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(dst + (long long)r * ldd + 4 * c) = o;
+  }
+}
+
+}  // namespace bags

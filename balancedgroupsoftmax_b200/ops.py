@@ -1,0 +1,351 @@
+"""Tensor-level wrappers over the C ABI + the autograd Functions of the BAGS head.
+
+Layering (mirrors the reference's own plugin pattern, e.g.
+mmdet/ops/sigmoid_focal_loss/sigmoid_focal_loss.py:8-35: an autograd.Function
+whose forward/backward call a compiled ``forward``/``backward``):
+
+    GroupSoftmaxFunction.forward/backward      <- torch.autograd.Function
+        -> bags_fwd / bags_bwd                 <- C ABI (include/bags_b200.h), ctypes
+            -> sm_100a kernels                 <- csrc/*.cuh
+
+Nothing in this file computes on the CPU or with torch math ops; torch is used
+for device memory, streams and autograd bookkeeping only.  Every entry point
+raises if the inputs are not CUDA tensors or the extension is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .tables import GroupTables
+
+
+# --------------------------------------------------------------------------- helpers
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise nat.BagsNativeError(
+                'BAGS ops run on a B200 GPU only (got a %s tensor); there is no CPU fallback' % t.device)
+
+
+def _dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return nat.DTYPE_F32
+    if dt == torch.bfloat16:
+        return nat.DTYPE_BF16
+    raise nat.BagsNativeError('unsupported operand dtype %s (float32 or bfloat16)' % dt)
+
+
+def _row_major(t: torch.Tensor) -> torch.Tensor:
+    if t.dim() != 2 or t.stride(1) != 1:
+        t = t.contiguous()
+    return t
+
+
+_workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def _workspace(device: torch.device) -> torch.Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream_ptr(device))
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = torch.zeros(nat.lib().bags_workspace_bytes(), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+@dataclass
+class DeviceTables:
+    """Group tables resident on one GPU (int32), converted once from the reference's int64 tables
+    (gs_bbox_head_with0.py:37-49)."""
+    G: int
+    num_classes: int
+    num_logits: int
+    label2bin: torch.Tensor     # [G, num_classes] int32, device
+    cls2col: torch.Tensor       # [num_classes] int32, device
+    slices_host: C.Array        # int32 [G*2] host
+    pred_slice: np.ndarray      # [G, 2] int64 host copy
+
+    @staticmethod
+    def from_tables(t: GroupTables, device) -> 'DeviceTables':
+        if t.num_bins > nat.MAX_BINS:
+            raise nat.BagsNativeError('at most %d bins are supported (got %d)' % (nat.MAX_BINS, t.num_bins))
+        l2b = torch.from_numpy(np.ascontiguousarray(t.label2binlabel.astype(np.int32))).to(device)
+        c2c = torch.from_numpy(np.ascontiguousarray(t.cls2col())).to(device)
+        flat = [int(v) for v in np.asarray(t.pred_slice).reshape(-1)]
+        return DeviceTables(t.num_bins, t.num_classes, t.num_logits, l2b, c2c, nat.int32_array(flat),
+                            np.asarray(t.pred_slice, dtype=np.int64).copy())
+
+
+def pad_cols(c: int, mult: int = 64) -> int:
+    return (c + mult - 1) // mult * mult
+
+
+# --------------------------------------------------------------------------- raw ops
+def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _require_cuda(src)
+    src = _row_major(src)
+    assert src.dtype == torch.float32
+    rows, cols = src.shape
+    if out is None:
+        out = torch.empty((rows, cols), dtype=torch.bfloat16, device=src.device)
+    nat.check(nat.lib().bags_cast_bf16(src.data_ptr(), src.stride(0), out.data_ptr(), out.stride(0), rows, cols,
+                                       _stream_ptr(src.device)), 'bags_cast_bf16')
+    return out
+
+
+def linear_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor],
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[N,C] fp32 = x @ w^T + bias   (a1: convfc_bbox_head.py:166)."""
+    _require_cuda(x, w, bias)
+    x, w = _row_major(x), _row_major(w)
+    if x.dtype != w.dtype:
+        raise nat.BagsNativeError('x (%s) and w (%s) must share a dtype' % (x.dtype, w.dtype))
+    N, K = x.shape
+    Cc = w.shape[0]
+    if out is None:
+        out = torch.empty((N, Cc), dtype=torch.float32, device=x.device)
+    if bias is not None:
+        bias = bias.contiguous()
+        assert bias.dtype == torch.float32
+    nat.check(nat.lib().bags_linear_fwd(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), nat.ptr(bias),
+                                        out.data_ptr(), out.stride(0), N, K, Cc, _dtype_code(x.dtype),
+                                        _stream_ptr(x.device)), 'bags_linear_fwd')
+    return out
+
+
+def sample_others(labels: torch.Tensor, dt: DeviceTables, ratio: float, seed: int
+                  ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Device sampler: (wmask [G,N] uint8, avg [G] fp32)   (a3/a4)."""
+    _require_cuda(labels)
+    labels = labels.contiguous()
+    assert labels.dtype == torch.int64
+    N = labels.numel()
+    wmask = torch.empty((dt.G, N), dtype=torch.uint8, device=labels.device)
+    avg = torch.empty((dt.G,), dtype=torch.float32, device=labels.device)
+    nat.check(nat.lib().bags_sample_others(labels.data_ptr(), dt.label2bin.data_ptr(), N, dt.G, dt.num_classes,
+                                           float(ratio), int(seed) & 0xFFFFFFFFFFFFFFFF, wmask.data_ptr(),
+                                           avg.data_ptr(), _stream_ptr(labels.device)), 'bags_sample_others')
+    return wmask, avg
+
+
+def mask_avg(wmask: torch.Tensor) -> torch.Tensor:
+    _require_cuda(wmask)
+    wmask = wmask.contiguous()
+    assert wmask.dtype == torch.uint8 and wmask.dim() == 2
+    G, N = wmask.shape
+    avg = torch.empty((G,), dtype=torch.float32, device=wmask.device)
+    nat.check(nat.lib().bags_mask_avg(wmask.data_ptr(), N, G, avg.data_ptr(), _stream_ptr(wmask.device)),
+              'bags_mask_avg')
+    return avg
+
+
+def group_ce(logits: torch.Tensor, labels: torch.Tensor, dt: DeviceTables,
+             wmask: Optional[torch.Tensor], avg: Optional[torch.Tensor], want_dz: bool = True,
+             dz_dtype: torch.dtype = torch.bfloat16, want_lse: bool = False):
+    """(loss[G], lse[N,G] | None, dz[N, ldd] | None, colsum[C] | None)   (a5-a7 + grad-in-forward)."""
+    _require_cuda(logits, labels, wmask, avg)
+    assert logits.dtype == torch.float32 and logits.dim() == 2 and logits.stride(1) == 1
+    labels = labels.contiguous()
+    N, Cc = logits.shape
+    dev = logits.device
+    loss = torch.empty((dt.G,), dtype=torch.float32, device=dev)
+    lse = torch.empty((N, dt.G), dtype=torch.float32, device=dev) if want_lse else None
+    dz = colsum = None
+    ldd = 0
+    if want_dz:
+        ldd = pad_cols(Cc)
+        dz = torch.empty((N, ldd), dtype=dz_dtype, device=dev)
+        colsum = torch.empty((Cc,), dtype=torch.float32, device=dev)
+    ws = _workspace(dev)
+    nat.check(nat.lib().bags_group_ce(
+        logits.data_ptr(), logits.stride(0), labels.data_ptr(), dt.label2bin.data_ptr(), dt.slices_host,
+        nat.ptr(wmask), nat.ptr(avg), N, Cc, dt.G, dt.num_classes, loss.data_ptr(), nat.ptr(lse), nat.ptr(dz), ldd,
+        _dtype_code(dz_dtype), nat.ptr(colsum), ws.data_ptr(), ws.numel(), _stream_ptr(dev)), 'bags_group_ce')
+    return loss, lse, dz, colsum
+
+
+def fused_fwd(x, w, bias, labels, dt: DeviceTables, wmask, avg, logits: Optional[torch.Tensor] = None,
+              want_dz: bool = True, want_lse: bool = False):
+    """bags_fwd: fc_cls + grouped CE in one ABI call.  Returns (loss, logits, lse, dz, colsum)."""
+    _require_cuda(x, w, bias, labels, wmask, avg)
+    x, w = _row_major(x), _row_major(w)
+    if x.dtype != w.dtype:
+        raise nat.BagsNativeError('x (%s) and w (%s) must share a dtype' % (x.dtype, w.dtype))
+    labels = labels.contiguous()
+    N, K = x.shape
+    Cc = w.shape[0]
+    dev = x.device
+    if logits is None:
+        logits = torch.empty((N, Cc), dtype=torch.float32, device=dev)
+    loss = torch.empty((dt.G,), dtype=torch.float32, device=dev)
+    lse = torch.empty((N, dt.G), dtype=torch.float32, device=dev) if want_lse else None
+    dz = colsum = None
+    ldd = 0
+    if want_dz:
+        ldd = pad_cols(Cc)
+        dz = torch.empty((N, ldd), dtype=x.dtype, device=dev)
+        colsum = torch.empty((Cc,), dtype=torch.float32, device=dev)
+    ws = _workspace(dev)
+    nat.check(nat.lib().bags_fwd(
+        x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), nat.ptr(bias), labels.data_ptr(),
+        dt.label2bin.data_ptr(), dt.slices_host, nat.ptr(wmask), nat.ptr(avg), N, K, Cc, dt.G, dt.num_classes,
+        _dtype_code(x.dtype), logits.data_ptr(), logits.stride(0), loss.data_ptr(), nat.ptr(lse), nat.ptr(dz), ldd,
+        nat.ptr(colsum), ws.data_ptr(), ws.numel(), _stream_ptr(dev)), 'bags_fwd')
+    return loss, logits, lse, dz, colsum
+
+
+def fused_bwd(dz, x, w, gout, dt: DeviceTables, colsum, need_dw=True, need_db=True, need_dx=True,
+              dW: Optional[torch.Tensor] = None, dX: Optional[torch.Tensor] = None,
+              wscratch: Optional[torch.Tensor] = None, db: Optional[torch.Tensor] = None):
+    """bags_bwd: (dW fp32 [C,K] | None, db fp32 [C] | None, dX [N,K] operand dtype | None)   (a8)."""
+    _require_cuda(dz, x, w, gout, colsum)
+    x, w = _row_major(x), _row_major(w)
+    N, K = x.shape
+    Cc = w.shape[0]
+    dev = x.device
+    if need_dw and dW is None:
+        dW = torch.empty((Cc, K), dtype=torch.float32, device=dev)
+    if need_db and db is None:
+        db = torch.empty((Cc,), dtype=torch.float32, device=dev)
+    if not need_db:
+        db = None
+    if need_dx and dX is None:
+        dX = torch.empty((N, K), dtype=x.dtype, device=dev)
+    if need_dx and gout is not None and wscratch is None:
+        wscratch = torch.empty_like(w)
+    if gout is not None:
+        gout = gout.contiguous()
+        assert gout.dtype == torch.float32 and gout.numel() == dt.G
+    nat.check(nat.lib().bags_bwd(
+        dz.data_ptr(), dz.stride(0), x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), nat.ptr(gout),
+        dt.slices_host, nat.ptr(colsum), nat.ptr(dW) if need_dw else None, dW.stride(0) if need_dw else 0,
+        nat.ptr(db), nat.ptr(dX) if need_dx else None, dX.stride(0) if need_dx else 0,
+        nat.ptr(wscratch) if (need_dx and gout is not None) else None, N, K, Cc, dt.G, _dtype_code(x.dtype),
+        _stream_ptr(dev)), 'bags_bwd')
+    return (dW if need_dw else None), db, (dX if need_dx else None)
+
+
+def merge_scores(logits: torch.Tensor, dt: DeviceTables) -> torch.Tensor:
+    """scores [N, num_classes] fp32   (a10: gs_bbox_head_with0.py:239-273)."""
+    _require_cuda(logits)
+    if logits.dtype != torch.float32:
+        raise nat.BagsNativeError('merge_scores expects fp32 logits')
+    logits = _row_major(logits)
+    N, Cc = logits.shape
+    scores = torch.empty((N, dt.num_classes), dtype=torch.float32, device=logits.device)
+    nat.check(nat.lib().bags_merge_scores(logits.data_ptr(), logits.stride(0), dt.slices_host,
+                                          dt.cls2col.data_ptr(), N, Cc, dt.G, dt.num_classes, scores.data_ptr(),
+                                          scores.stride(0), _stream_ptr(logits.device)), 'bags_merge_scores')
+    return scores
+
+
+def gemm_probe(a, a_mn: bool, b, b_mn: bool, M: int, N: int, K: int, block_n: int = 256, splits: int = 1,
+               epi: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Test hook for one tcgen05 GEMM (see bags_gemm_probe)."""
+    _require_cuda(a, b)
+    dev = a.device
+    if out is None:
+        out_dtype = torch.bfloat16 if epi == 1 else torch.float32
+        out = torch.zeros((M, N), dtype=out_dtype, device=dev)
+    nat.check(nat.lib().bags_gemm_probe(a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0), int(b_mn),
+                                        out.data_ptr(), out.stride(0), M, N, K, _dtype_code(a.dtype), block_n,
+                                        splits, epi, _stream_ptr(dev)), 'bags_gemm_probe')
+    return out
+
+
+# --------------------------------------------------------------------------- autograd
+class GroupSoftmaxFunction(torch.autograd.Function):
+    """losses[G] = BAGS(fc_cls(x)) with a fused backward.
+
+    forward : bags_fwd  (tcgen05 fc_cls GEMM -> grouped softmax-CE, saves dz~ and its column sums)
+    backward: bags_bwd  (dW = dz^T x, db, dX = dz W on tcgen05; per-bin upstream gradients applied
+              in the GEMM epilogue / on a scaled copy of W)
+
+    compute_dtype torch.bfloat16: x and W are used as bf16 operands (fp32 masters are cast by
+    bags_cast_bf16); torch.float32: fp32 operands, TF32 products.  Accumulation, softmax, loss
+    and dW/db are always fp32.
+    """
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, labels, dt: DeviceTables, wmask, avg, compute_dtype, logits_out):
+        _require_cuda(x, weight, bias, labels)
+        xin = x.detach()
+        win = weight.detach()
+        if compute_dtype == torch.bfloat16:
+            xc = xin if xin.dtype == torch.bfloat16 else cast_bf16(_row_major(xin.float()))
+            wc = win if win.dtype == torch.bfloat16 else cast_bf16(_row_major(win.float()))
+        elif compute_dtype == torch.float32:
+            if xin.dtype != torch.float32 or win.dtype != torch.float32:
+                raise nat.BagsNativeError('float32 compute needs float32 x and weight')
+            xc, wc = _row_major(xin), _row_major(win)
+        else:
+            raise nat.BagsNativeError('compute_dtype must be torch.bfloat16 or torch.float32')
+        b32 = None if bias is None else bias.detach().float().contiguous()
+        need_grad = any(ctx.needs_input_grad[:3])
+        loss, logits, _, dz, colsum = fused_fwd(xc, wc, b32, labels, dt, wmask, avg, logits=logits_out,
+                                                want_dz=need_grad)
+        ctx.dt = dt
+        ctx.x_dtype = x.dtype
+        ctx.w_dtype = weight.dtype
+        ctx.has_bias = bias is not None
+        ctx.bias_dtype = None if bias is None else bias.dtype
+        if need_grad:
+            ctx.save_for_backward(xc, wc, dz, colsum)
+        ctx.mark_non_differentiable(logits)
+        return loss, logits
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_loss, _grad_logits):
+        xc, wc, dz, colsum = ctx.saved_tensors
+        need_dx, need_dw, need_db = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        gout = grad_loss.detach().to(torch.float32).contiguous()
+        dW, db, dX = fused_bwd(dz, xc, wc, gout, ctx.dt, colsum, need_dw=need_dw,
+                               need_db=(need_db and ctx.has_bias), need_dx=need_dx)
+        if dX is not None and dX.dtype != ctx.x_dtype:
+            dX = dX.to(ctx.x_dtype)
+        if dW is not None and dW.dtype != ctx.w_dtype:
+            dW = dW.to(ctx.w_dtype)
+        if db is not None and db.dtype != ctx.bias_dtype:
+            db = db.to(ctx.bias_dtype)
+        return dX, dW, db, None, None, None, None, None, None
+
+
+class GroupCEFunction(torch.autograd.Function):
+    """losses[G] from materialised logits (used when loss() is handed a plain cls_score tensor).
+    backward returns d/dlogits = gout ⊙ dz~ (computed by torch on the saved dz~; this path exists for API
+    completeness -- the hot path is GroupSoftmaxFunction)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, dt: DeviceTables, wmask, avg):
+        _require_cuda(logits, labels)
+        z = _row_major(logits.detach().float())
+        need = ctx.needs_input_grad[0]
+        loss, _, dz, _ = group_ce(z, labels, dt, wmask, avg, want_dz=need, dz_dtype=torch.float32)
+        ctx.dt = dt
+        ctx.in_dtype = logits.dtype
+        if need:
+            ctx.save_for_backward(dz)
+        return loss
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_loss):
+        (dz,) = ctx.saved_tensors
+        dt = ctx.dt
+        Cc = dt.num_logits
+        out = torch.zeros((dz.shape[0], Cc), dtype=torch.float32, device=dz.device)
+        for g in range(dt.G):
+            s, l = int(dt.pred_slice[g, 0]), int(dt.pred_slice[g, 1])
+            out[:, s:s + l] = dz[:, s:s + l] * grad_loss[g]
+        return out.to(ctx.in_dtype), None, None, None, None

@@ -1,0 +1,499 @@
+#!/usr/bin/env python
+"""bench.py -- RoIs/s through the BAGS head fwd+bwd (1231 classes -> 1236 logits, 5 bins).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of 4096 synthetic RoIs per GPU
+(BASELINE.json configs[1]: 4096 RoIs x 1024 feat x 1231 cls, 5 bins, bf16):
+
+    sample "others" masks -> fc_cls GEMM + grouped softmax-CE (5 bins) -> dW, db, dX
+    (+ NCCL all-reduce(avg) of the fc_cls gradient bucket when N > 1, restating
+     mmdet/core/utils/dist_utils.py:9-41)
+
+`value`  : whole-job RoIs/s with inputs resident in HBM, K steps replayed from a CUDA graph
+           (launch-bound inner loop), timed with CUDA events on the launching stream, max over
+           ranks.  Each step uses a different member of a rotating pool of buffer sets larger than
+           the 126 MB L2, so no step finds its inputs in cache.
+`e2e`    : the same metric through the public autograd API (GroupSoftmaxFunction behind
+           balancedgroupsoftmax_b200.bags_head_loss) with HOST (pinned) features/labels copied
+           H2D and the per-bin losses read back D2H inside the timed region.
+`roofline`: the dominant kernel (by measured duration) against MEASURED_PEAKS.json.
+`cpu_baseline`: the oracle port of the reference's PyTorch CPU path on this box's host cores.
+
+--impl reference: the reference's own CPU implementation of the path (its source through
+oracle/ref_shim.py when a checkout is reachable, else the oracle port), same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ROIS = 4096
+K_FEAT = 1024
+NUM_CLASSES = 1231
+RATIO = 8.0
+METRIC = 'RoIs/sec through BAGS head fwd+bwd (1231 cls, 5 bins)'
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(p):
+        try:
+            d = json.load(open(p))
+            return dict(hbm_gbs=float(d['hbm_gbs']), bf16_tflops=float(d['bf16_tflops']),
+                        bf16_tflops_sustained=float(d.get('bf16_tflops_sustained', d['bf16_tflops'])),
+                        source='measured')
+        except Exception:
+            pass
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source='fallback')
+
+
+def make_labels(torch, n, num_classes, gen):
+    """25 % positives first in every 512-block (RandomSampler num=512, pos_fraction=.25;
+    mmdet/core/bbox/bbox_target.py:44-51), class ids uniform on 1..num_classes-1."""
+    labels = torch.zeros(n, dtype=torch.int64)
+    for s in range(0, n, 512):
+        e = min(n, s + 512)
+        npos = (e - s) // 4
+        labels[s:s + npos] = torch.randint(1, num_classes, (npos,), generator=gen)
+    return labels
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._halt = threading.Event()
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(',')]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for nm, v in zip(names, f[2:6]):
+                    if v.lower().startswith('active'):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._halt.wait(0.1)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=5)
+        s = sorted(self.samples)
+        return dict(sm_mhz=(s[len(s) // 2] if s else None), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
+                    samples=len(s))
+
+
+# ======================================================================================= reference arm
+def run_reference(args):
+    import numpy as np
+    import torch
+    from balancedgroupsoftmax_b200.tables import synthetic_tables
+    from oracle import bags_oracle as O
+    from oracle import ref_shim
+
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tables = synthetic_tables(NUM_CLASSES, seed=0)
+    gen = torch.Generator().manual_seed(0)
+    n = args.rois
+    x = torch.relu(torch.randn(n, K_FEAT, generator=gen))
+    labels = make_labels(torch, n, NUM_CLASSES, gen)
+    l2b, ps = torch.from_numpy(tables.label2binlabel), torch.from_numpy(tables.pred_slice)
+    np.random.seed(0)
+
+    if ref_shim.available():
+        kind = 'reference'
+        head = ref_shim.build_reference_head(tables, RATIO)
+        head.init_weights()
+
+        def step():
+            xr = x.detach().requires_grad_(True)
+            head.zero_grad()
+            z = head.fc_cls(xr)
+            losses = head.loss(z, None, labels, None, None, None)
+            sum(losses.values()).backward()
+    else:
+        kind = 'port'
+        W = torch.randn(tables.num_logits, K_FEAT, generator=gen) * 0.01
+        b = torch.zeros(tables.num_logits)
+
+        def step():
+            O.head_step(x, W, b, labels, l2b, ps, RATIO, need_dx=True)
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = n / dt
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'RoIs/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'BAGS head fwd+loss+bwd(dW,db,dX), %d RoIs x %d feat x %d logits, 5 bins, '
+                               'PyTorch CPU fp32' % (n, K_FEAT, tables.num_logits)},
+        'cpu_baseline': {'value': value, 'unit': 'RoIs/s', 'cores': torch.get_num_threads(), 'kind': kind,
+                         'sample': '%d steps of %d RoIs' % (args.steps, n)},
+        'e2e': {'value': value, 'unit': 'RoIs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def cpu_baseline(torch, tables, n, budget_s=15.0):
+    """Oracle port of the reference CPU path, timed on the host cores (bounded sample)."""
+    import numpy as np
+    from oracle import bags_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    gen = torch.Generator().manual_seed(0)
+    x = torch.relu(torch.randn(n, K_FEAT, generator=gen))
+    W = torch.randn(tables.num_logits, K_FEAT, generator=gen) * 0.01
+    b = torch.zeros(tables.num_logits)
+    labels = make_labels(torch, n, NUM_CLASSES, gen)
+    l2b, ps = torch.from_numpy(tables.label2binlabel), torch.from_numpy(tables.pred_slice)
+    np.random.seed(0)
+    for _ in range(2):
+        O.head_step(x, W, b, labels, l2b, ps, RATIO)
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < 20 and (time.perf_counter() - t_start) < budget_s:
+        t0 = time.perf_counter()
+        O.head_step(x, W, b, labels, l2b, ps, RATIO)
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return {'value': n / med, 'unit': 'RoIs/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': 'median of %d fwd+bwd iterations of %d RoIs (fp32, torch CPU)' % (len(times), n),
+            'ms_per_step': med * 1e3}
+
+
+# ======================================================================================= our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from balancedgroupsoftmax_b200 import ops
+    from balancedgroupsoftmax_b200.api import bags_head_loss
+    from balancedgroupsoftmax_b200.tables import synthetic_tables
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a B200 GPU (no CPU fallback); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    dtype = torch.bfloat16 if args.dtype == 'bf16' else torch.float32
+    tables = synthetic_tables(NUM_CLASSES, seed=0)
+    dt = ops.DeviceTables.from_tables(tables, dev)
+    C = tables.num_logits
+    n = args.rois
+    gen = torch.Generator().manual_seed(1234 + rank)
+
+    # ---- rotating pool of buffer sets, total footprint > 2x L2 ------------------------------
+    elt = 2 if dtype == torch.bfloat16 else 4
+    ldd = ops.pad_cols(C)
+    per_set = n * K_FEAT * elt * 2 + n * C * 4 + n * ldd * elt + C * K_FEAT * 4 + C * K_FEAT * elt * 2
+    pool = max(2, int(np.ceil(2.2 * 126e6 / per_set)))
+    sets = []
+    W_master = (torch.randn(C, K_FEAT, generator=gen) * 0.01)
+    for i in range(pool):
+        s = {}
+        s['x'] = torch.relu(torch.randn(n, K_FEAT, generator=gen)).to(dev).to(dtype)
+        s['w'] = W_master.to(dev).to(dtype)
+        s['bias'] = torch.zeros(C, device=dev)
+        s['labels'] = make_labels(torch, n, NUM_CLASSES, gen).to(dev)
+        s['logits'] = torch.empty(n, C, device=dev)
+        s['grad'] = torch.empty(C * K_FEAT + C, device=dev)           # flat fc_cls gradient bucket
+        s['dW'] = s['grad'][:C * K_FEAT].view(C, K_FEAT)
+        s['db'] = s['grad'][C * K_FEAT:]
+        s['dX'] = torch.empty(n, K_FEAT, device=dev, dtype=dtype)
+        s['wscratch'] = torch.empty_like(s['w'])
+        sets.append(s)
+    gout = torch.ones(dt.G, device=dev)
+    seed_ctr = [0]
+    last = {}
+
+    def one_step(s):
+        seed_ctr[0] += 1
+        wmask, avg = ops.sample_others(s['labels'], dt, RATIO, seed_ctr[0])
+        loss, _, _, dz, colsum = ops.fused_fwd(s['x'], s['w'], s['bias'], s['labels'], dt, wmask, avg,
+                                               logits=s['logits'])
+        ops.fused_bwd(dz, s['x'], s['w'], gout, dt, colsum, dW=s['dW'], dX=s['dX'], wscratch=s['wscratch'],
+                      db=s['db'])
+        if world > 1:
+            dist.all_reduce(s['grad'], op=dist.ReduceOp.AVG)
+        last['loss'] = loss
+        return loss
+
+    kernels_per_step = 6  # sampler, fwd GEMM, grouped CE, W row-scale, dW GEMM, dX GEMM (+2 memset nodes)
+
+    stream = torch.cuda.Stream(device=dev)
+    use_graph = not args.no_graph
+    graph = None
+    with torch.cuda.stream(stream):
+        for s in sets[:2]:
+            one_step(s)
+        stream.synchronize()
+        if use_graph:
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=stream):
+                    for s in sets:
+                        one_step(s)
+            except Exception as e:  # pragma: no cover
+                log('graph capture failed (%s); timing eager launches' % (e,))
+                graph = None
+                use_graph = False
+        torch.cuda.synchronize()
+
+        def run_steps(k):
+            """exactly k steps"""
+            if graph is not None:
+                full, rem = divmod(k, pool)
+                for _ in range(full):
+                    graph.replay()
+                for s in sets[:rem]:
+                    one_step(s)
+            else:
+                for i in range(k):
+                    one_step(sets[i % pool])
+
+        run_steps(max(args.warmup, 3))
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = ClockSampler(local_rank)
+        clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        run_steps(args.steps)
+        e1.record(stream)
+        stream.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms_total = e0.elapsed_time(e1)
+        # keep the sampler alive for at least a few samples on very short runs
+        t_hold = time.time()
+        while len(clocks.samples) < 3 and time.time() - t_hold < 2.0:
+            run_steps(pool)
+            stream.synchronize()
+        clk = clocks.stop()
+    ms_step = ms_total / args.steps
+    if world > 1:
+        t = torch.tensor([ms_step], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item())
+    value = world * n / (ms_step * 1e-3)
+
+    # ---- e2e: public API, host buffers, H2D + D2H inside the timed region -------------------
+    e2e = None
+    try:
+        x_host = torch.relu(torch.randn(n, K_FEAT, generator=gen)).to(dtype).pin_memory()
+        lab_host = make_labels(torch, n, NUM_CLASSES, gen).pin_memory()
+        w_param = torch.nn.Parameter(W_master.to(dev).to(dtype))
+        b_param = torch.nn.Parameter(torch.zeros(C, device=dev))
+        loss_host = torch.empty(dt.G, dtype=torch.float32).pin_memory()
+        e2e_steps = max(10, min(args.steps, 200))
+
+        def e2e_step():
+            xd = x_host.to(dev, non_blocking=True).requires_grad_(True)
+            ld = lab_host.to(dev, non_blocking=True)
+            w_param.grad = None
+            b_param.grad = None
+            losses = bags_head_loss(xd, w_param, b_param, ld, dt, RATIO, compute_dtype=dtype)
+            losses.sum().backward()
+            if world > 1:
+                dist.all_reduce(w_param.grad, op=dist.ReduceOp.AVG)
+            loss_host.copy_(losses.detach(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()   # the step's result is on the host
+
+        for _ in range(3):
+            e2e_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
+        if world > 1:
+            t = torch.tensor([e2e_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        e2e = {'value': world * n / (e2e_ms * 1e-3), 'unit': 'RoIs/s',
+               'h2d_bytes_per_step': int(x_host.numel() * x_host.element_size() + lab_host.numel() * 8),
+               'd2h_bytes_per_step': int(loss_host.numel() * 4), 'ms_per_step': e2e_ms, 'steps': e2e_steps}
+    except Exception as ex:  # pragma: no cover
+        log('e2e arm failed: %r' % (ex,))
+
+    # ---- per-kernel durations (CUDA events, rotating sets) for the roofline ------------------
+    roof = None
+    kernel_us = {}
+    if rank == 0:
+        pk = peaks()
+
+        def time_kernel(fn, reps=3):
+            with torch.cuda.stream(stream):
+                for s in sets:
+                    fn(s)
+                stream.synchronize()
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                for _ in range(reps):
+                    for s in sets:
+                        fn(s)
+                b_.record(stream)
+                stream.synchronize()
+            return a.elapsed_time(b_) / (reps * pool) * 1e3
+
+        with torch.cuda.stream(stream):
+            wmask, avg = ops.sample_others(sets[0]['labels'], dt, RATIO, 1)
+            _, _, _, dz0, colsum0 = ops.fused_fwd(sets[0]['x'], sets[0]['w'], sets[0]['bias'], sets[0]['labels'], dt,
+                                                  wmask, avg, logits=sets[0]['logits'])
+            dzs = [torch.empty_like(dz0).copy_(dz0) for _ in sets]
+            stream.synchronize()
+
+        def graphed(fn):
+            """time fn(s) over the pool from a CUDA graph to exclude host launch gaps"""
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(stream):
+                for s in sets:
+                    fn(s)
+                stream.synchronize()
+                with torch.cuda.graph(g, stream=stream):
+                    for s in sets:
+                        fn(s)
+                g.replay()
+                stream.synchronize()
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                for _ in range(5):
+                    g.replay()
+                b_.record(stream)
+                stream.synchronize()
+            return a.elapsed_time(b_) / (5 * pool) * 1e3
+
+        idx = {id(s): i for i, s in enumerate(sets)}
+        try:
+            kernel_us['fc_cls_gemm'] = graphed(lambda s: ops.linear_fwd(s['x'], s['w'], s['bias'], out=s['logits']))
+            kernel_us['group_ce'] = graphed(lambda s: ops.group_ce(s['logits'], s['labels'], dt, wmask, avg,
+                                                                   dz_dtype=dtype))
+            kernel_us['dW_gemm'] = graphed(lambda s: ops.fused_bwd(dzs[idx[id(s)]], s['x'], s['w'], gout, dt, colsum0,
+                                                                   need_dx=False, dW=s['dW']))
+            kernel_us['dX_gemm'] = graphed(lambda s: ops.fused_bwd(dzs[idx[id(s)]], s['x'], s['w'], None, dt, colsum0,
+                                                                   need_dw=False, need_db=False, dX=s['dX']))
+            kernel_us['sample_others'] = graphed(lambda s: ops.sample_others(s['labels'], dt, RATIO, 7))
+        except Exception as ex:  # pragma: no cover
+            log('per-kernel timing failed: %r' % (ex,))
+        flops = {'fc_cls_gemm': 2.0 * n * K_FEAT * C, 'dW_gemm': 2.0 * n * K_FEAT * C, 'dX_gemm': 2.0 * n * K_FEAT * C}
+        bytes_ce = n * C * 4 + n * C * elt + n * 8 + dt.G * n   # read fp32 logits, write dz, labels, masks
+        if kernel_us:
+            dom = max(kernel_us, key=lambda k_: kernel_us[k_])
+            if dom in flops:
+                peak = pk['bf16_tflops_sustained'] if dtype == torch.bfloat16 else pk['bf16_tflops_sustained'] / 2.0
+                ach = flops[dom] / (kernel_us[dom] * 1e-6) / 1e12
+                roof = {'kernel': dom, 'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
+                        'frac': ach / peak, 'traffic': None,
+                        'peak_source': pk['source'] + (' (sustained bf16)' if dtype == torch.bfloat16 else
+                                                       ' (sustained bf16 / 2 for tf32)')}
+            else:
+                ach = bytes_ce / (kernel_us[dom] * 1e-6) / 1e9
+                roof = {'kernel': dom, 'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                        'frac': ach / pk['hbm_gbs'], 'traffic': None, 'peak_source': pk['source'],
+                        'algorithmic_bytes': bytes_ce}
+        step_flops = 6.0 * n * K_FEAT * C
+        peak_t = pk['bf16_tflops_sustained'] if dtype == torch.bfloat16 else pk['bf16_tflops_sustained'] / 2.0
+        step_roof = {'bound': 'tensor', 'achieved': step_flops / (ms_step * 1e-3) / 1e12, 'peak': peak_t,
+                     'unit': 'TFLOP/s', 'algorithmic_flops_per_step': step_flops}
+        step_roof['frac'] = step_roof['achieved'] / peak_t
+
+    if rank == 0:
+        cb = cpu_baseline(torch, tables, n) if world == 1 else None
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'RoIs/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
+            'config': {
+                'workload': 'BASELINE.json configs[1]: fused BAGS fwd+bwd, %d RoIs/GPU x %d feat x %d cls (%d logits), '
+                            '5 bins, %s operands, dW+db+dX, device sampler' % (n, K_FEAT, NUM_CLASSES, C, args.dtype),
+                'rois_per_gpu': n, 'parallelism': 'dp%d' % world,
+                'l2': 'rotating pool of %d buffer sets (%.0f MB > 126 MB L2); no step re-reads cached inputs'
+                      % (pool, pool * per_set / 1e6),
+                'launch': 'cuda-graph replay' if graph is not None else 'eager',
+                'collective': ('nccl all_reduce(avg) of %d fp32 fc_cls grads per step' % (C * K_FEAT + C))
+                if world > 1 else 'none',
+            },
+            'clocks': clk,
+            'e2e': e2e,
+            'gpu_launches': kernels_per_step * args.steps,
+            'roofline': roof,
+            'roofline_step': step_roof,
+            'kernel_us': kernel_us,
+            'loss_bins': [float(v) for v in last['loss'].detach().float().cpu().tolist()],
+        }
+        if cb is not None:
+            line['cpu_baseline'] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=None)
+    ap.add_argument('--warmup', type=int, default=None)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--rois', type=int, default=N_ROIS)
+    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--no-graph', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        args.steps = args.steps or 20
+        args.warmup = 3 if args.warmup is None else args.warmup
+        return run_reference(args)
+    args.steps = args.steps or 600
+    args.warmup = 20 if args.warmup is None else args.warmup
+    return run_ours(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -1,0 +1,134 @@
+/*
+ * bags_b200.h -- C ABI of the B200-native Balanced Group Softmax (BAGS) RoI
+ * classification head hot path.
+ *
+ * This is the drop-in boundary for the reference's fc_cls -> grouped softmax /
+ * cross-entropy path (FishYuLi/BalancedGroupSoftmax, mmdetection v1.0rc0 fork):
+ *
+ *   reference interface                                   replaced by
+ *   ---------------------------------------------------   -------------------------
+ *   ConvFCBBoxHead.forward: self.fc_cls(x_cls)            bags_linear_fwd
+ *     mmdet/models/bbox_heads/convfc_bbox_head.py:166
+ *   GSBBoxHeadWith0._sample_others                        bags_sample_others
+ *     mmdet/models/bbox_heads/gs_bbox_head_with0.py:63-89
+ *   GSBBoxHeadWith0._remap_labels (avg_factor)            bags_mask_avg
+ *     gs_bbox_head_with0.py:91-112 (:109)
+ *   _remap_labels + _slice_preds + 5x CrossEntropyLoss    bags_group_ce
+ *     gs_bbox_head_with0.py:134-171 ;
+ *     mmdet/models/losses/cross_entropy_loss.py:9-19,86-103 ;
+ *     mmdet/models/losses/utils.py:26-53
+ *   fc_cls + loss in one call                             bags_fwd
+ *   autograd backward of the above (dW, db, dX)           bags_bwd
+ *     triggered at mmdet/core/utils/dist_utils.py:53
+ *   GSBBoxHeadWith0._merge_score                          bags_merge_scores
+ *     gs_bbox_head_with0.py:239-273
+ *
+ * The reference's own native plugins export pybind11 `forward`/`backward`
+ * functions over at::Tensor (e.g. mmdet/ops/sigmoid_focal_loss/src/
+ * sigmoid_focal_loss.cpp:40-45) and launch on the current stream.  This ABI is
+ * the torch-free equivalent: plain device pointers + sizes + an explicit
+ * cudaStream_t, loadable with ctypes / dlopen.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`
+ *   - the caller owns all buffers, including workspaces; the library allocates nothing
+ *   - no call synchronises the device or reads device data on the host
+ *   - return value 0 = success; otherwise a negative error code and a message
+ *     retrievable with bags_last_error() (thread-local)
+ *   - dtype: BAGS_DTYPE_F32 = fp32 operands (TF32 tensor-core products, fp32 accumulate)
+ *            BAGS_DTYPE_BF16 = bf16 operands (fp32 accumulate, fp32 softmax / loss)
+ *   - `stream` is a cudaStream_t passed as void*
+ *   - slices_host is int32 [G,2] = (start, len) per bin, ascending and non-overlapping
+ *     (tools/lvis_analyse.py:45-50), G <= BAGS_MAX_BINS
+ *   - requires an sm_100 (B200) device; there is no CPU or other-arch fallback
+ */
+#ifndef BAGS_B200_H_
+#define BAGS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BAGS_ABI_VERSION 1
+#define BAGS_MAX_BINS 8
+#define BAGS_DTYPE_F32 0
+#define BAGS_DTYPE_BF16 1
+
+#define BAGS_OK 0
+#define BAGS_ERR_INVALID (-1)   /* bad argument / unsupported shape */
+#define BAGS_ERR_CUDA (-2)      /* CUDA runtime / driver error */
+#define BAGS_ERR_ARCH (-3)      /* device is not sm_100 */
+
+int bags_abi_version(void);
+const char* bags_last_error(void);
+
+/* bytes the caller must provide (zero-initialised ONCE) as `workspace` to bags_group_ce / bags_fwd */
+size_t bags_workspace_bytes(void);
+
+/* out[N,C] = x[N,K] @ w[C,K]^T + bias[C]      (fp32 output)
+ * x, w: dtype elements with leading dims ldx, ldw (elements; rows 16-byte aligned). bias may be NULL. */
+int bags_linear_fwd(const void* x, long long ldx, const void* w, long long ldw, const float* bias,
+                    float* out, long long ldo, int N, int K, int C, int dtype, void* stream);
+
+/* wmask[G,N] (uint8 0/1) and avg[G] = max(sum w, 1): bin 0 all ones; bins >= 1 keep every in-bin row
+ * and a uniform random subset of k = int(F * ratio) "others" rows (F = #in-bin rows), exactly as
+ * _sample_others does, but on the device with a counter-based RNG keyed by `seed`. */
+int bags_sample_others(const int64_t* labels, const int32_t* label2bin, int N, int G, int classes,
+                       double ratio, uint64_t seed, uint8_t* wmask, float* avg, void* stream);
+
+/* avg[g] = max(sum_n wmask[g,n], 1) for caller-provided masks */
+int bags_mask_avg(const uint8_t* wmask, int N, int G, float* avg, void* stream);
+
+/* Per-bin softmax cross-entropy over logit slices.
+ *   loss[g] = sum_n w[g,n] * (logsumexp(z[n, slice_g]) - z[n, start_g + label2bin[g, labels[n]]]) / avg[g]
+ * Optional outputs (NULL to skip): lse[N,G]; dz[N,ldd] (dtype elements) = w/avg * (softmax - onehot),
+ * i.e. d(sum_g loss_g)/dz before the per-bin upstream gradients are applied; colsum[C] = sum_n dz.
+ * wmask NULL => all ones; avg NULL => N.  C % 4 == 0, ldz % 4 == 0, C <= 4096. */
+int bags_group_ce(const float* logits, long long ldz, const int64_t* labels,
+                  const int32_t* label2bin, const int32_t* slices_host, const uint8_t* wmask,
+                  const float* avg, int N, int C, int G, int classes, float* loss, float* lse,
+                  void* dz, long long ldd, int dz_dtype, float* colsum, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
+/* bags_linear_fwd into `logits` followed by bags_group_ce (same arguments). */
+int bags_fwd(const void* x, long long ldx, const void* w, long long ldw, const float* bias,
+             const int64_t* labels, const int32_t* label2bin, const int32_t* slices_host,
+             const uint8_t* wmask, const float* avg, int N, int K, int C, int G, int classes,
+             int dtype, float* logits, long long ldz, float* loss, float* lse, void* dz,
+             long long ldd, float* colsum, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of bags_fwd given dz (and colsum) saved by the forward and gout[G] = dL/dloss_g (NULL => 1):
+ *   dW[C,K]  = (gout ⊙ dz)^T x      fp32, overwritten         (NULL to skip)
+ *   db[C]    = gout ⊙ colsum         fp32                      (NULL to skip)
+ *   dX[N,K]  = (gout ⊙ dz) w         dtype elements            (NULL to skip)
+ * wscratch: [C, ldw] dtype elements, required when dX != NULL and gout != NULL. */
+int bags_bwd(const void* dz, long long ldd, const void* x, long long ldx, const void* w,
+             long long ldw, const float* gout, const int32_t* slices_host, const float* colsum,
+             float* dW, long long lddw, float* db, void* dX, long long lddx, void* wscratch, int N,
+             int K, int C, int G, int dtype, void* stream);
+
+/* scores[N,classes]: scores[:,0] = softmax(z[:,slice_0])[:,0];
+ * scores[:,c] = softmax(z[:,slice_0])[:,1] * softmax(z[:,slice_g])[:,j] where cls2col[c] = start_g + j.
+ * cls2col: int32 [classes] (device), -1 => score 0. */
+int bags_merge_scores(const float* logits, long long ldz, const int32_t* slices_host,
+                      const int32_t* cls2col, int N, int C, int G, int classes, float* scores,
+                      long long lds, void* stream);
+
+/* dst[rows, cols] (bf16, leading dim ldd) = bf16(src[rows, cols] fp32, leading dim lds); cols % 4 == 0 */
+int bags_cast_bf16(const float* src, long long lds, void* dst, long long ldd, int rows, int cols,
+                   void* stream);
+
+/* Test hook: one tcgen05 GEMM, out[M,N] = A * B^T with either operand K-major ([rows,K]) or
+ * MN-major ([K,rows]).  epi: 0 = fp32 store, 1 = bf16 store, 2 = fp32 reduce-add (split-K).
+ * block_n in {256, 320}; 320 only with K-major B and epi 0. */
+int bags_gemm_probe(const void* a, long long lda, int a_mn, const void* b, long long ldb, int b_mn,
+                    void* out, long long ldo, int M, int N, int K, int dtype, int block_n,
+                    int splits, int epi, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAGS_B200_H_ */

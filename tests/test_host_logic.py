@@ -1,0 +1,174 @@
+"""CPU: the host-side mirror of the reference's BBoxHead API (registry, config build, state dict,
+decorators, sampler host logic).  No kernels run here."""
+import numpy as np
+import pytest
+import torch
+
+from balancedgroupsoftmax_b200 import registry
+from balancedgroupsoftmax_b200.fp16 import auto_fp16, force_fp32
+from balancedgroupsoftmax_b200.head import ClsScoreHandle, GSBBoxHead, GSBBoxHeadWith0, delta2bbox
+from balancedgroupsoftmax_b200.losses import CrossEntropyLoss, SmoothL1Loss
+from balancedgroupsoftmax_b200.tables import save_reference_files, synthetic_tables
+
+
+class ConfigDict(dict):
+    __getattr__ = dict.__getitem__
+
+
+def bags_cfg(paths, attr_style):
+    """bbox_head block of configs/bags/gs_faster_rcnn_r50_fpn_1x_lvis_with0_bg8.py:34-59."""
+    mk = ConfigDict if attr_style else dict
+    return dict(
+        type='GSBBoxHeadWith0', num_fcs=2, in_channels=256, fc_out_channels=1024,
+        gs_config=mk(label2binlabel=paths['label2binlabel'], pred_slice=paths['pred_slice'],
+                     fg_split=paths['fg_split'], others_sample_ratio=8.0,
+                     loss_bg=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0), num_bins=5,
+                     loss_bin=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0)),
+        roi_feat_size=7, num_classes=1231, target_means=[0., 0., 0., 0.], target_stds=[0.1, 0.1, 0.2, 0.2],
+        reg_class_agnostic=False,
+        loss_cls=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0),
+        loss_bbox=dict(type='SmoothL1Loss', beta=1.0, loss_weight=1.0))
+
+
+@pytest.fixture(scope='module')
+def table_files(tmp_path_factory):
+    d = tmp_path_factory.mktemp('tables')
+    return save_reference_files(synthetic_tables(1231, seed=0), str(d))
+
+
+@pytest.mark.parametrize('attr_style', [False, True])
+def test_builds_from_reference_config_block(table_files, attr_style):
+    head = registry.build_head(bags_cfg(table_files, attr_style))
+    assert isinstance(head, GSBBoxHeadWith0)
+    assert head.fc_cls.in_features == 1024 and head.fc_cls.out_features == 1236
+    assert head.fc_reg.out_features == 4 * 1231
+    assert head.num_classes == 1231 and head.fp16_enabled is False and head.reg_class_agnostic is False
+    assert head.others_sample_ratio == 8.0 and len(head.loss_bins) == 5
+    sd = head.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == {
+        'shared_fcs.0.weight': (1024, 12544), 'shared_fcs.0.bias': (1024,),
+        'shared_fcs.1.weight': (1024, 1024), 'shared_fcs.1.bias': (1024,),
+        'fc_cls.weight': (1236, 1024), 'fc_cls.bias': (1236,),
+        'fc_reg.weight': (4924, 1024), 'fc_reg.bias': (4924,)}
+    assert all(v.dtype == torch.float32 for v in sd.values())
+    # tables are plain attributes, not in the state dict (gs_bbox_head_with0.py:37-49)
+    assert head.label2binlabel.dtype == torch.int64 and len(head.fg_splits) == 4
+
+
+def test_registry_contract():
+    assert registry.HEADS.get('GSBBoxHeadWith0') is GSBBoxHeadWith0
+    assert registry.HEADS.get('GSBBoxHead') is GSBBoxHead
+    assert registry.HEADS.get('SharedFCBBoxHead') is not None
+    assert registry.LOSSES.get('CrossEntropyLoss') is CrossEntropyLoss
+    with pytest.raises(KeyError):
+        registry.build_from_cfg(dict(type='Nope'), registry.HEADS)
+    with pytest.raises(TypeError):
+        registry.build_from_cfg(dict(type=3), registry.HEADS)
+    r = registry.Registry('x')
+
+    @r.register_module
+    class A(object):
+        pass
+
+    assert r.get('A') is A
+    with pytest.raises(KeyError):
+        r.register_module(A)
+    obj = registry.build_from_cfg(dict(type='SmoothL1Loss'), registry.LOSSES, default_args=dict(beta=0.5))
+    assert isinstance(obj, SmoothL1Loss) and obj.beta == 0.5
+
+
+def test_init_weights_like_reference():
+    t = synthetic_tables()
+    head = GSBBoxHeadWith0(num_fcs=2, in_channels=8, fc_out_channels=64, roi_feat_size=2, num_classes=1231,
+                           gs_config=dict(tables=t, others_sample_ratio=8.0, num_bins=5,
+                                          loss_bin=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0)))
+    torch.manual_seed(0)
+    head.init_weights()
+    assert abs(head.fc_cls.weight.std().item() - 0.01) < 1e-3 and head.fc_cls.bias.abs().sum().item() == 0
+    assert abs(head.fc_reg.weight.std().item() - 0.001) < 1e-4
+
+
+def test_training_forward_returns_lazy_handle_and_cpu_loss_raises():
+    from balancedgroupsoftmax_b200._native import BagsNativeError
+    t = synthetic_tables()
+    head = GSBBoxHeadWith0(num_fcs=2, in_channels=4, fc_out_channels=64, roi_feat_size=2, num_classes=1231,
+                           gs_config=dict(tables=t, others_sample_ratio=8.0, num_bins=5,
+                                          loss_bin=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0)))
+    head.train()
+    cls_score, bbox_pred = head(torch.randn(10, 4, 2, 2))
+    assert isinstance(cls_score, ClsScoreHandle)
+    assert tuple(cls_score.shape) == (10, 1236) and cls_score.size(1) == 1236 and cls_score.dim() == 2
+    assert tuple(bbox_pred.shape) == (10, 4 * 1231)
+    labels = torch.zeros(10, dtype=torch.long)
+    with pytest.raises(BagsNativeError):          # no CPU fallback for the hot path
+        head.loss(cls_score, None, labels, None, None, None)
+    with pytest.raises(BagsNativeError):
+        head.eval()(torch.randn(10, 4, 2, 2))
+
+
+def test_bbox_loss_branch_matches_reference_formula():
+    t = synthetic_tables()
+    head = GSBBoxHeadWith0(num_fcs=1, in_channels=4, fc_out_channels=32, roi_feat_size=1, num_classes=1231,
+                           reg_class_agnostic=True,
+                           gs_config=dict(tables=t, others_sample_ratio=8.0, num_bins=5,
+                                          loss_bin=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0)))
+    labels = torch.tensor([3, 0, 7, 0])
+    bbox_pred = torch.tensor([[0.1, 0.2, 2.0, -3.0]] * 4)
+    targets = torch.zeros(4, 4)
+    weights = torch.ones(4, 4)
+    out = head.loss(None, bbox_pred, labels, None, targets, weights)
+    # smooth-l1(beta=1): 0.005 + 0.02 + 1.5 + 2.5 per positive row, 2 positives, avg_factor = 4 rows
+    assert abs(out['loss_bbox'].item() - 2 * (0.005 + 0.02 + 1.5 + 2.5) / 4) < 1e-6
+    assert list(out.keys()) == ['loss_bbox']
+
+
+def test_fp16_decorators():
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fp16_enabled = False
+
+        @force_fp32(apply_to=('a', ))
+        def f(self, a, b):
+            return a.dtype, b.dtype
+
+        @force_fp32(apply_to=('cls_score'))     # bare string: substring membership, as the reference relies on
+        def g(self, cls_score, other):
+            return cls_score.dtype, other.dtype
+
+        @auto_fp16(apply_to=('a', ), out_fp32=True)
+        def h(self, a):
+            return a
+
+    m = M()
+    h, f = torch.zeros(2).half(), torch.zeros(2)
+    assert m.f(h, h) == (torch.float16, torch.float16)          # disabled -> untouched
+    m.fp16_enabled = True
+    assert m.f(h, h) == (torch.float32, torch.float16)
+    assert m.f(a=h, b=h) == (torch.float32, torch.float16)
+    assert m.g(h, h) == (torch.float32, torch.float16)
+    assert m.h(f).dtype == torch.float32
+    with pytest.raises(TypeError):
+        force_fp32()(lambda x: x)(3)
+
+
+def test_delta2bbox_doctest_values():
+    """mmdet/core/bbox/transforms.py:63-76 known answers."""
+    rois = torch.Tensor([[0., 0., 1., 1.], [0., 0., 1., 1.], [0., 0., 1., 1.], [5., 5., 5., 5.]])
+    deltas = torch.Tensor([[0., 0., 0., 0.], [1., 1., 1., 1.], [0., 0., 2., -1.], [0.7, -1.9, -0.5, 0.3]])
+    out = delta2bbox(rois, deltas, max_shape=(32, 32))
+    exp = torch.tensor([[0.0000, 0.0000, 1.0000, 1.0000], [0.2817, 0.2817, 4.7183, 4.7183],
+                        [0.0000, 0.6321, 7.3891, 0.3679], [5.8967, 2.9251, 5.5033, 3.2749]])
+    assert torch.allclose(out, exp, atol=1e-4)
+
+
+def test_loss_modules_semantics():
+    ce = CrossEntropyLoss(loss_weight=2.0)
+    z = torch.tensor([[2.0, 0.0], [0.0, 0.0]])
+    y = torch.tensor([0, 1])
+    w = torch.tensor([1, 0])
+    per = torch.nn.functional.cross_entropy(z, y, reduction='none')
+    assert torch.allclose(ce(z, y, w, avg_factor=4.0), 2.0 * (per * w.float()).sum() / 4.0)
+    assert torch.allclose(ce(z, y, reduction_override='none'), 2.0 * per)
+    with pytest.raises(ValueError):
+        ce(z, y, w, avg_factor=2.0, reduction_override='sum')

@@ -1,0 +1,90 @@
+"""CPU, build container only: the oracle (and the host-side mirror of the head) against the reference's
+OWN source executed in place through oracle/ref_shim.py.  Skipped where no checkout is reachable
+(e.g. the GPU box) -- the committed fixtures in tests/golden/ carry the pinning there."""
+import numpy as np
+import pytest
+import torch
+
+from balancedgroupsoftmax_b200.tables import synthetic_tables, build_group_tables, synthetic_instance_counts
+from oracle import bags_oracle as O
+from oracle import ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason='reference checkout not reachable')
+
+
+@pytest.fixture(scope='module')
+def ref():
+    t = synthetic_tables(1231, seed=0)
+    head = ref_shim.build_reference_head(t, fc_out_channels=128)
+    head.init_weights()
+    return t, head
+
+
+@pytest.mark.parametrize('N,npos,seed', [(1, 1, 0), (1, 0, 1), (64, 16, 2), (300, 75, 3), (512, 128, 4), (40, 40, 5)])
+def test_loss_and_grads_match_reference(ref, N, npos, seed):
+    t, head = ref
+    l2b, ps = torch.from_numpy(t.label2binlabel), torch.from_numpy(t.pred_slice)
+    torch.manual_seed(seed)
+    with torch.no_grad():
+        head.fc_cls.weight.normal_(0, 0.2)
+        head.fc_cls.bias.normal_(0, 0.1)
+    x = torch.relu(torch.randn(N, 128))
+    labels = torch.zeros(N, dtype=torch.long)
+    labels[:npos] = torch.randint(1, 1231, (npos,))
+    np.random.seed(seed)
+    xr = x.clone().requires_grad_(True)
+    head.zero_grad()
+    z = head.fc_cls(xr)
+    losses = head.loss(z, None, labels, None, None, None)
+    sum(losses.values()).backward()
+    assert set(losses.keys()) == {'loss_cls_bin%d' % g for g in range(5)}
+    W, b = head.fc_cls.weight.detach(), head.fc_cls.bias.detach()
+    np.random.seed(seed)   # same numpy state => identical sampled masks
+    lo, dW, db, dX = O.head_step(x, W, b, labels, l2b, ps, 8.0)
+    for k in losses:
+        assert abs(lo[k].item() - losses[k].item()) <= 1e-6 * max(1.0, abs(losses[k].item())), k
+    assert ((dW - head.fc_cls.weight.grad).norm() / head.fc_cls.weight.grad.norm().clamp_min(1e-20)).item() < 1e-6
+    assert ((db - head.fc_cls.bias.grad).norm() / head.fc_cls.bias.grad.norm().clamp_min(1e-20)).item() < 1e-6
+    assert ((dX - xr.grad).norm() / xr.grad.norm().clamp_min(1e-20)).item() < 1e-6
+
+
+def test_merge_score_matches_reference(ref):
+    t, head = ref
+    ps = torch.from_numpy(t.pred_slice)
+    torch.manual_seed(7)
+    for _ in range(3):
+        z = torch.randn(200, t.num_logits) * 3
+        a = head._merge_score(z)
+        b = O.merge_score(z, ps, [torch.from_numpy(s) for s in t.fg_splits], t.num_classes)
+        assert (a - b).abs().max().item() == 0.0
+        assert torch.equal(a.argmax(1), b.argmax(1))
+
+
+def test_tables_load_into_reference_head(ref):
+    """Files written by tables.save_reference_files are what the reference's constructor reads
+    (gs_bbox_head_with0.py:37-49): shapes/dtypes/keys survive the round trip."""
+    t, head = ref
+    assert head.label2binlabel.dtype == torch.int64 and tuple(head.label2binlabel.shape) == (5, 1231)
+    assert torch.equal(head.label2binlabel, torch.from_numpy(t.label2binlabel))
+    assert torch.equal(head.pred_slice, torch.from_numpy(t.pred_slice))
+    assert len(head.fg_splits) == 4
+    for a, b in zip(head.fg_splits, t.fg_splits):
+        assert torch.equal(a, torch.from_numpy(b))
+    assert head.fc_cls.out_features == 1236
+
+
+def test_host_mirror_numpy_sampler_is_the_reference_sampler(ref):
+    """GSBBoxHeadWith0(sampler='numpy')._sample_others_numpy draws the same masks as the reference."""
+    from balancedgroupsoftmax_b200.head import GSBBoxHeadWith0
+    t, head = ref
+    mine = GSBBoxHeadWith0(num_fcs=2, in_channels=4, fc_out_channels=128, roi_feat_size=2, num_classes=1231,
+                           gs_config=dict(tables=t, others_sample_ratio=8.0, num_bins=5, sampler='numpy',
+                                          loss_bin=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0)))
+    labels = torch.zeros(400, dtype=torch.long)
+    labels[:90] = torch.randint(1, 1231, (90,), generator=torch.Generator().manual_seed(3))
+    np.random.seed(11)
+    _, ref_w, ref_avg = head._remap_labels(labels)
+    np.random.seed(11)
+    for g in range(1, 5):
+        w = mine._sample_others_numpy(mine.label2binlabel[g][labels])
+        assert torch.equal(w, ref_w[g])
