@@ -36,5 +36,8 @@ def bags_head_loss(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.T
         wmask, avg = ops.sample_others(labels, dt, others_sample_ratio, seed)
     elif avg is None:
         avg = ops.mask_avg(wmask)
-    loss, logits = ops.GroupSoftmaxFunction.apply(x, weight, bias, labels, dt, wmask, avg, compute_dtype, None)
+    logits = None
+    if return_logits:
+        logits = torch.empty((x.shape[0], weight.shape[0]), dtype=torch.float32, device=x.device)
+    loss = ops.GroupSoftmaxFunction.apply(x, weight, bias, labels, dt, wmask, avg, compute_dtype, logits)
     return (loss, logits) if return_logits else loss

@@ -12,6 +12,7 @@
 
 #include "../../include/bags_b200.h"
 #include "bags_gemm.cuh"
+#include "bags_fused_fwd.cuh"
 #include "bags_kernels.cuh"
 
 using namespace bags;
@@ -58,6 +59,13 @@ static std::mutex g_mutex;
 static DeviceInfo g_dev[64];
 static bool g_dev_ok[64] = {false};
 
+// test hook: device buffer [ctas][8] int64 that the next launches stamp with %globaltimer values
+static long long* g_timing = nullptr;
+extern "C" int bags_debug_set_timing(void* dev_ptr) {
+  g_timing = reinterpret_cast<long long*>(dev_ptr);
+  return BAGS_OK;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -93,20 +101,20 @@ static int device_info(DeviceInfo& out) {
 
 // 2-D row-major tensor [outer, inner] (inner contiguous), 128B-swizzled boxes.
 static int make_tmap(CUtensorMap* tm, const void* ptr, int dtype, long long inner, long long outer,
-                     long long ld_elems, int box_inner, int box_outer, bool atom32 = false) {
+                     long long ld_elems, int box_inner, int box_outer, bool atom32 = false, bool swz64 = false) {
   const int elt = (dtype == BAGS_DTYPE_BF16) ? 2 : 4;
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0)
     return fail(BAGS_ERR_INVALID, "operand pointer %p is not 16-byte aligned", ptr);
   if (((ld_elems * elt) & 15) != 0)
     return fail(BAGS_ERR_INVALID, "operand row stride %lld bytes is not a multiple of 16", ld_elems * elt);
-  if (box_inner * elt != 128) return fail(BAGS_ERR_INVALID, "internal: box inner must span 128 bytes");
+  if (box_inner * elt != (swz64 ? 64 : 128)) return fail(BAGS_ERR_INVALID, "internal: box inner must span the swizzle width");
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
   cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld_elems * elt)};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(tm, dtype == BAGS_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                         2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        swz64 ? CU_TENSOR_MAP_SWIZZLE_64B : (atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -161,7 +169,16 @@ static int launch_gemm(const GemmArgs& ga, const DeviceInfo& di, cudaStream_t st
   else      rc = make_tmap(&tb, ga.b, ga.dtype, ga.K, ga.N, ga.ldb, Cfg::BLOCK_K, Cfg::UMMA_N);
   if (rc) return rc;
 
+  // output tensor map: [M, N] row-major, 32-row x 128-byte boxes
+  CUtensorMap tc;
+  {
+    const int out_dtype = (EPI == EPI_STORE_BF16) ? BAGS_DTYPE_BF16 : BAGS_DTYPE_F32;
+    rc = make_tmap(&tc, ga.p.out, out_dtype, ga.N, ga.M, ga.p.ldo, Cfg::EPI_COLS, 32);
+    if (rc) return rc;
+  }
+
   GemmParams p = ga.p;
+  p.timing = g_timing;
   p.M = ga.M; p.N = ga.N; p.K = ga.K;
   p.num_m_tiles = (ga.M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
   p.num_n_tiles = (ga.N + BLOCK_N - 1) / BLOCK_N;
@@ -175,7 +192,7 @@ static int launch_gemm(const GemmArgs& ga, const DeviceInfo& di, cudaStream_t st
   const int grid = units < di.num_sms ? units : di.num_sms;
 
   BAGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  kernel<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  kernel<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tc, p);
   BAGS_CUDA(cudaGetLastError());
   return BAGS_OK;
 }
@@ -213,8 +230,8 @@ extern "C" int bags_linear_fwd(const void* x, long long ldx, const void* w, long
                                const float* bias, float* out, long long ldo, int N, int K, int C,
                                int dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  BAGS_REQUIRE(x && w && out, "bags_linear_fwd: NULL operand");
   BAGS_REQUIRE(N >= 0 && K >= 1 && C >= 1, "bags_linear_fwd: bad shape N=%d K=%d C=%d", N, K, C);
+  BAGS_REQUIRE(N == 0 || (x && w && out), "bags_linear_fwd: NULL operand");
   BAGS_REQUIRE(dtype == BAGS_DTYPE_F32 || dtype == BAGS_DTYPE_BF16, "bags_linear_fwd: bad dtype %d", dtype);
   BAGS_REQUIRE(ldx >= K && ldw >= K && ldo >= C, "bags_linear_fwd: leading dimension smaller than row");
   if (N == 0) return BAGS_OK;
@@ -230,10 +247,10 @@ extern "C" int bags_linear_fwd(const void* x, long long ldx, const void* w, long
   ga.p.colsum_in = nullptr; ga.p.colsum_out = nullptr;
   const int bn = pick_fwd_block_n(N, C, di.num_sms);
   if (dtype == BAGS_DTYPE_BF16) {
-    return bn == 320 ? launch_gemm<320, false, false, EPI_STORE_F32, false, 4>(ga, di, stream)
+    return bn == 320 ? launch_gemm<320, false, false, EPI_STORE_F32, false, 3>(ga, di, stream)
                      : launch_gemm<256, false, false, EPI_STORE_F32, false, 4>(ga, di, stream);
   }
-  return bn == 320 ? launch_gemm<320, false, false, EPI_STORE_F32, true, 4>(ga, di, stream)
+  return bn == 320 ? launch_gemm<320, false, false, EPI_STORE_F32, true, 3>(ga, di, stream)
                    : launch_gemm<256, false, false, EPI_STORE_F32, true, 4>(ga, di, stream);
 }
 
@@ -244,9 +261,11 @@ extern "C" int bags_sample_others(const int64_t* labels, const int32_t* label2bi
   BAGS_REQUIRE(labels && label2bin && wmask && avg, "bags_sample_others: NULL argument");
   BAGS_REQUIRE(G >= 1 && G <= kMaxG && classes >= 1 && N >= 0, "bags_sample_others: bad shape");
   BAGS_REQUIRE(ratio >= 0.0, "bags_sample_others: negative ratio");
-  sample_others_kernel<<<G, 1024, 0, stream>>>(reinterpret_cast<const long long*>(labels), label2bin,
-                                               classes, G, N, ratio, static_cast<unsigned long long>(seed),
-                                               wmask, avg);
+  const long long* lab = reinterpret_cast<const long long*>(labels);
+  const unsigned long long sd = static_cast<unsigned long long>(seed);
+  if (N <= 4096)       sample_others_kernel<4><<<G, 1024, 0, stream>>>(lab, label2bin, classes, G, N, ratio, sd, wmask, avg);
+  else if (N <= 16384) sample_others_kernel<16><<<G, 1024, 0, stream>>>(lab, label2bin, classes, G, N, ratio, sd, wmask, avg);
+  else                 sample_others_kernel<0><<<G, 1024, 0, stream>>>(lab, label2bin, classes, G, N, ratio, sd, wmask, avg);
   BAGS_CUDA(cudaGetLastError());
   return BAGS_OK;
 }
@@ -267,8 +286,10 @@ static int launch_group_ce(const float* logits, long long ldz, const int64_t* la
                            void* dz, long long ldd, int dz_dtype, float* colsum, void* workspace,
                            int num_sms, cudaStream_t stream) {
   const int smem = 8 * NV * 128 * (int)sizeof(float);
+  // persistent CTAs (2 per SM: 126 regs x 256 threads): every CTA walks several row octets so the
+  // bias-gradient column sums are reduced in registers/smem and hit global atomics once per CTA
   int per_sm = (200 * 1024) / (smem + 2048);
-  if (per_sm > 6) per_sm = 6;
+  if (per_sm > 2) per_sm = 2;
   if (per_sm < 1) per_sm = 1;
   int grid = (N + 7) / 8;
   if (grid > num_sms * per_sm) grid = num_sms * per_sm;
@@ -299,12 +320,13 @@ extern "C" int bags_group_ce(const float* logits, long long ldz, const int64_t* 
                              int dz_dtype, float* colsum, void* workspace, size_t workspace_bytes,
                              void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  BAGS_REQUIRE(logits && labels && label2bin && loss && workspace, "bags_group_ce: NULL argument");
+  BAGS_REQUIRE(label2bin && loss && workspace && (N == 0 || (logits && labels)), "bags_group_ce: NULL argument");
   BAGS_REQUIRE(workspace_bytes >= bags_workspace_bytes(), "bags_group_ce: workspace too small (%zu < %zu)",
                workspace_bytes, bags_workspace_bytes());
   BAGS_REQUIRE(N >= 0 && C >= 4 && (C % 4) == 0 && C <= 4096, "bags_group_ce: C=%d must be a multiple of 4 in [4,4096]", C);
   BAGS_REQUIRE((ldz % 4) == 0 && ldz >= C, "bags_group_ce: ldz=%lld must be a multiple of 4 and >= C", ldz);
   BAGS_REQUIRE((reinterpret_cast<uintptr_t>(logits) & 15) == 0, "bags_group_ce: logits not 16-byte aligned");
+  if (N == 0) dz = nullptr;
   BAGS_REQUIRE(dz_dtype == BAGS_DTYPE_F32 || dz_dtype == BAGS_DTYPE_BF16, "bags_group_ce: bad dz dtype");
   if (dz != nullptr) {
     BAGS_REQUIRE(ldd >= C && (ldd % 8) == 0, "bags_group_ce: ldd=%lld must be a multiple of 8 and >= C", ldd);
@@ -332,30 +354,139 @@ extern "C" int bags_group_ce(const float* logits, long long ldz, const int64_t* 
                              dz_dtype, colsum, workspace, di.num_sms, stream);
 }
 
+
+// ----------------------------------------------------------------------------
+// fused forward (GEMM + grouped softmax-CE in one kernel)
+// ----------------------------------------------------------------------------
+static bool fused_eligible(const int32_t* slices_host, int G, int C) {
+  if (slices_host == nullptr || G < 1 || G > FusedCfg<false>::MAXG || C > 4 * FusedCfg<false>::BLOCK_N || (C % 4) != 0)
+    return false;
+  int end = 0;
+  for (int g = 0; g < G; ++g) {   // bins must tile [0, C) contiguously
+    if (slices_host[2 * g] != end || slices_host[2 * g + 1] < 1) return false;
+    end += slices_host[2 * g + 1];
+  }
+  if (end != C) return false;
+  for (int c0 = 0; c0 < C; c0 += 32) {   // at most two bins per 32-column chunk
+    int cnt = 0;
+    for (int g = 0; g < G; ++g) {
+      const int s = slices_host[2 * g], e = s + slices_host[2 * g + 1];
+      if (s < c0 + 32 && e > c0) ++cnt;
+    }
+    if (cnt > 2) return false;
+  }
+  const char* v = getenv("BAGS_FUSED");
+  if (v && *v == '0') return false;
+  return true;
+}
+
+extern "C" int bags_fused_eligible(const int32_t* slices_host, int G, int C) {
+  return fused_eligible(slices_host, G, C) ? 1 : 0;
+}
+
+template <bool TF32>
+static int launch_fused_fwd(const void* x, long long ldx, const void* w, long long ldw, const FusedFwdParams& p0,
+                            void* dz, long long ldd, const DeviceInfo& di, cudaStream_t stream) {
+  using Cfg = FusedCfg<TF32>;
+  const int dtype = TF32 ? BAGS_DTYPE_F32 : BAGS_DTYPE_BF16;
+  CUtensorMap tx, tw, td;
+  int rc = make_tmap(&tx, x, dtype, p0.K, p0.N, ldx, Cfg::BLOCK_K, Cfg::BLOCK_M);
+  if (rc) return rc;
+  rc = make_tmap(&tw, w, dtype, p0.K, p0.C, ldw, Cfg::BLOCK_K, Cfg::UMMA_N);
+  if (rc) return rc;
+  if (dz != nullptr) {
+    rc = TF32 ? make_tmap(&td, dz, dtype, p0.C, p0.N, ldd, 32, 32)
+              : make_tmap(&td, dz, dtype, p0.C, p0.N, ldd, 32, 32, false, true);
+    if (rc) return rc;
+  } else {
+    td = tx;  // never dereferenced (want_dz == 0)
+  }
+  FusedFwdParams p = p0;
+  p.kblocks = (p.K + Cfg::BLOCK_K - 1) / Cfg::BLOCK_K;
+  p.want_dz = dz != nullptr ? 1 : 0;
+  p.timing = g_timing;
+  auto kernel = bags_fwd_fused_kernel<TF32>;
+  BAGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  const int grid = Cfg::CLUSTER * ((p.N + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M);
+  (void)di;
+  kernel<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tx, tw, td, p);
+  BAGS_CUDA(cudaGetLastError());
+  return BAGS_OK;
+}
+
 extern "C" int bags_fwd(const void* x, long long ldx, const void* w, long long ldw,
                         const float* bias, const int64_t* labels, const int32_t* label2bin,
                         const int32_t* slices_host, const uint8_t* wmask, const float* avg, int N,
                         int K, int C, int G, int classes, int dtype, float* logits, long long ldz,
                         float* loss, float* lse, void* dz, long long ldd, float* colsum,
-                        void* workspace, size_t workspace_bytes, void* stream) {
-  if (int rc = bags_linear_fwd(x, ldx, w, ldw, bias, logits, ldz, N, K, C, dtype, stream)) return rc;
-  return bags_group_ce(logits, ldz, labels, label2bin, slices_host, wmask, avg, N, C, G, classes, loss,
-                       lse, dz, ldd, dtype, colsum, workspace, workspace_bytes, stream);
+                        void* workspace, size_t workspace_bytes, void* stream_) {
+  if (logits != nullptr) {
+    // caller wants materialised logits: GEMM with fp32 store, then the stand-alone grouped CE
+    if (int rc = bags_linear_fwd(x, ldx, w, ldw, bias, logits, ldz, N, K, C, dtype, stream_)) return rc;
+    return bags_group_ce(logits, ldz, labels, label2bin, slices_host, wmask, avg, N, C, G, classes, loss,
+                         lse, dz, ldd, dtype, colsum, workspace, workspace_bytes, stream_);
+  }
+  // fused path: logits stay in TMEM
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BAGS_REQUIRE(fused_eligible(slices_host, G, C),
+               "bags_fwd: logits == NULL requests the fused kernel, but this bin table / C=%d / G=%d is not eligible "
+               "(see bags_fused_eligible); pass a logits workspace", C, G);
+  BAGS_REQUIRE(dtype == BAGS_DTYPE_F32 || dtype == BAGS_DTYPE_BF16, "bags_fwd: bad dtype %d", dtype);
+  BAGS_REQUIRE(label2bin && loss && workspace && (N == 0 || (x && w && labels)), "bags_fwd: NULL argument");
+  BAGS_REQUIRE(workspace_bytes >= bags_workspace_bytes(), "bags_fwd: workspace too small");
+  BAGS_REQUIRE(N >= 0 && K >= 1, "bags_fwd: bad shape");
+  if (dz != nullptr) BAGS_REQUIRE(ldd >= C && (ldd % 8) == 0, "bags_fwd: ldd=%lld must be a multiple of 8 and >= C", ldd);
+  GroupTable gt;
+  if (int rc = make_group_table(gt, slices_host, G, C)) return rc;
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  if (colsum != nullptr) BAGS_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * C, stream));
+  if (N == 0) {
+    BAGS_CUDA(cudaMemsetAsync(loss, 0, sizeof(float) * G, stream));
+    return BAGS_OK;
+  }
+  const int grid = 4 * ((N + 127) / 128);
+  BAGS_REQUIRE(grid <= 4096, "bags_fwd: N=%d too large for the fused path's loss workspace", N);
+  FusedFwdParams p{};
+  p.N = N; p.C = C; p.K = K; p.gt = gt; p.bias = bias;
+  p.labels = reinterpret_cast<const long long*>(labels);
+  p.l2b = label2bin; p.classes = classes; p.wmask = wmask; p.avg = avg;
+  p.loss = loss; p.lse = lse; p.colsum = colsum;
+  p.counter = reinterpret_cast<unsigned int*>(workspace);
+  p.part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
+  if (N == 0) dz = nullptr;
+  return dtype == BAGS_DTYPE_BF16 ? launch_fused_fwd<false>(x, ldx, w, ldw, p, dz, ldd, di, stream)
+                                  : launch_fused_fwd<true>(x, ldx, w, ldw, p, dz, ldd, di, stream);
 }
 
-// dst[r, :] = src[r, :] * gout[bin(r)]   (rows = logit columns)
+// dst[r, :] = src[r, :] * gout[bin(r)]   (rows = logit columns); 16-byte vectors, one CTA per row
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 scale_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, long long ld, int rows, int cols,
-                  GroupTable gt, const float* __restrict__ gout) {
-  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
-    float s = 0.f;
-    for (int g = 0; g < gt.G; ++g)
-      if (r >= gt.start[g] && r < gt.start[g] + gt.len[g]) s = __ldg(gout + g);
-    for (int c = threadIdx.x; c < cols; c += 256) {
-      const float v = static_cast<float>(src[(long long)r * ld + c]) * s;
-      dst[(long long)r * ld + c] = static_cast<T>(v);
+                  const GroupTable gt, const float* __restrict__ gout) {
+  constexpr int V = 16 / sizeof(T);
+  const int r = blockIdx.x;
+  float s = 0.f;
+#pragma unroll
+  for (int g = 0; g < kMaxG; ++g)
+    if (g < gt.G && r >= gt.start[g] && r < gt.start[g] + gt.len[g]) s = __ldg(gout + g);
+  for (int c = threadIdx.x * V; c < cols; c += 128 * V) {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src + (long long)r * ld + c));
+    uint4 out;
+    if (sizeof(T) == 2) {
+      const uint32_t in[4] = {raw.x, raw.y, raw.z, raw.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float lo = __uint_as_float(in[q] << 16), hi = __uint_as_float(in[q] & 0xffff0000u);
+        o[q] = pack_bf16x2(lo * s, hi * s);
+      }
+      out = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+      out = make_uint4(__float_as_uint(__uint_as_float(raw.x) * s), __float_as_uint(__uint_as_float(raw.y) * s),
+                       __float_as_uint(__uint_as_float(raw.z) * s), __float_as_uint(__uint_as_float(raw.w) * s));
     }
+    *reinterpret_cast<uint4*>(dst + (long long)r * ld + c) = out;
   }
 }
 
@@ -377,7 +508,7 @@ extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long 
                         long long lddx, void* wscratch, int N, int K, int C, int G, int dtype,
                         void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  BAGS_REQUIRE(dz != nullptr, "bags_bwd: dz is NULL");
+  BAGS_REQUIRE(dz != nullptr || N == 0, "bags_bwd: dz is NULL");
   BAGS_REQUIRE(dtype == BAGS_DTYPE_F32 || dtype == BAGS_DTYPE_BF16, "bags_bwd: bad dtype %d", dtype);
   BAGS_REQUIRE(N >= 0 && K >= 1 && C >= 1, "bags_bwd: bad shape");
   GroupTable gt;
@@ -387,7 +518,7 @@ extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long 
   if (db != nullptr) BAGS_REQUIRE(colsum != nullptr, "bags_bwd: db requested but colsum is NULL");
 
   if (dW != nullptr) {
-    BAGS_REQUIRE(x != nullptr, "bags_bwd: x is NULL but dW requested");
+    BAGS_REQUIRE(x != nullptr || N == 0, "bags_bwd: x is NULL but dW requested");
     BAGS_REQUIRE(lddw >= K && (lddw % 4) == 0 && (reinterpret_cast<uintptr_t>(dW) & 15) == 0,
                  "bags_bwd: dW must be 16-byte aligned with lddw %% 4 == 0");
     BAGS_CUDA(cudaMemset2DAsync(dW, lddw * sizeof(float), 0, K * sizeof(float), C, stream));
@@ -421,12 +552,16 @@ extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long 
     const void* wb = w;
     if (gout != nullptr) {
       BAGS_REQUIRE(wscratch != nullptr, "bags_bwd: wscratch is required when dX and gout are both given");
-      const int grid = C < 2 * di.num_sms ? C : 2 * di.num_sms;
+      const int vecw = (dtype == BAGS_DTYPE_BF16) ? 8 : 4;
+      BAGS_REQUIRE((K % vecw) == 0 && (ldw % vecw) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(wscratch) & 15) == 0,
+                   "bags_bwd: w / wscratch must be 16-byte aligned with K and ldw multiples of %d", vecw);
+      const int grid = C;
       if (dtype == BAGS_DTYPE_BF16)
-        scale_rows_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
+        scale_rows_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(
             reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<__nv_bfloat16*>(wscratch), ldw, C, K, gt, gout);
       else
-        scale_rows_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(w),
+        scale_rows_kernel<float><<<grid, 128, 0, stream>>>(reinterpret_cast<const float*>(w),
                                                            reinterpret_cast<float*>(wscratch), ldw, C, K, gt, gout);
       BAGS_CUDA(cudaGetLastError());
       wb = wscratch;
@@ -450,7 +585,7 @@ extern "C" int bags_merge_scores(const float* logits, long long ldz, const int32
                                  const int32_t* cls2col, int N, int C, int G, int classes,
                                  float* scores, long long lds, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  BAGS_REQUIRE(logits && cls2col && scores, "bags_merge_scores: NULL argument");
+  BAGS_REQUIRE(cls2col && (N == 0 || (logits && scores)), "bags_merge_scores: NULL argument");
   BAGS_REQUIRE(N >= 0 && C >= 4 && (C % 4) == 0 && C <= 4096, "bags_merge_scores: C=%d must be a multiple of 4 in [4,4096]", C);
   BAGS_REQUIRE((ldz % 4) == 0 && ldz >= C && lds >= classes, "bags_merge_scores: bad leading dimension");
   BAGS_REQUIRE((reinterpret_cast<uintptr_t>(logits) & 15) == 0, "bags_merge_scores: logits not 16-byte aligned");
@@ -509,8 +644,8 @@ extern "C" int bags_gemm_probe(const void* a, long long lda, int a_mn, const voi
   BAGS_REQUIRE(bf || dtype == BAGS_DTYPE_F32, "bags_gemm_probe: bad dtype");
   // the instantiations the product uses
   if (!a_mn && !b_mn && epi == 0 && block_n == 320)
-    return bf ? launch_gemm<320, false, false, EPI_STORE_F32, false, 4>(ga, di, stream)
-              : launch_gemm<320, false, false, EPI_STORE_F32, true, 4>(ga, di, stream);
+    return bf ? launch_gemm<320, false, false, EPI_STORE_F32, false, 3>(ga, di, stream)
+              : launch_gemm<320, false, false, EPI_STORE_F32, true, 3>(ga, di, stream);
   if (!a_mn && !b_mn && epi == 0 && block_n == 256)
     return bf ? launch_gemm<256, false, false, EPI_STORE_F32, false, 4>(ga, di, stream)
               : launch_gemm<256, false, false, EPI_STORE_F32, true, 4>(ga, di, stream);

@@ -1,0 +1,528 @@
+// Fused BAGS forward for sm_100a:  fc_cls GEMM  ->  grouped softmax-CE  ->  dz~  in ONE kernel.
+//
+//   z = x W^T + b  is accumulated in TMEM and never written to HBM.
+//
+// A cluster of 4 CTAs owns one 128-row tile of RoIs; CTA r holds logit columns [320r, 320r+320)
+// of those rows in its TMEM (128 lanes x 320 fp32 columns).  The epilogue maps ONE THREAD TO ONE
+// ROW (TMEM lane), so walking the columns of a bin is a plain sequential loop: no masks, no
+// shuffles, bin boundaries are warp-uniform.  Bins usually span several CTAs, so each
+// (CTA, column-half) publishes its per-row partial (max, sum-exp) for every bin to all four CTAs
+// through distributed shared memory; after one cluster barrier every thread combines the eight
+// partials into the bin's log-sum-exp and makes a second pass over its TMEM columns:
+//
+//   pass A  (after the mainloop):  per bin segment, online (max, sum exp(z - max))
+//   exchange + barrier.cluster
+//   pass C:  p = exp(z - lse_bin) ; dz~ = w/avg * (p - onehot)  -> bf16/fp32 -> swizzled smem
+//            -> TMA tensor store ;  column sums of dz~ (bias gradient) from the staged tile ;
+//            loss_bin += w/avg * -log p[target]
+//
+// reference semantics: gs_bbox_head_with0.py:91-112 (labels/weights), :134-171 (slices + CE),
+// cross_entropy_loss.py:9-19, losses/utils.py:26-53 (sum / avg_factor).
+//
+// Preconditions (checked on the host, otherwise the unfused path runs): C <= 1280, G <= 6, bins
+// tile [0, C) contiguously, and no 32-column chunk intersects more than two bins.
+#pragma once
+#include "bags_kernels.cuh"
+#include "bags_ptx.cuh"
+
+namespace bags {
+
+struct FusedFwdParams {
+  int N, C, K, kblocks;
+  GroupTable gt;
+  const float* bias;        // [C] or nullptr
+  const long long* labels;  // [N]
+  const int* l2b;           // [G, classes]
+  int classes;
+  const uint8_t* wmask;     // [G, N] or nullptr (all ones)
+  const float* avg;         // [G] or nullptr (N)
+  float* loss;              // [G]
+  float* lse;               // [N, G] or nullptr
+  float* colsum;            // [C] (+=, caller zeroes) or nullptr
+  float* part;              // [gridDim.x, kMaxG]
+  unsigned int* counter;
+  int want_dz;
+  long long* timing;        // debug timeline [grid][8] or nullptr
+};
+
+template <bool TF32>
+struct FusedCfg {
+  static constexpr int BLOCK_M = 128;
+  static constexpr int BLOCK_N = 320;
+  static constexpr int UMMA_N = 160;
+  static constexpr int STAGES = 3;
+  static constexpr int ELT = TF32 ? 4 : 2;
+  static constexpr int BLOCK_K = 128 / ELT;
+  static constexpr int UMMA_K = 32 / ELT;
+  static constexpr int K_STEPS = BLOCK_K / UMMA_K;
+  static constexpr int A_BYTES = BLOCK_M * 128;
+  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int CLUSTER = 4;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int HALF_COLS = BLOCK_N / 2;       // 160 columns per epilogue warp
+  static constexpr int CHUNKS = HALF_COLS / 32;       // 5
+  static constexpr int MAXG = 6;
+  static constexpr int NSRC = CLUSTER * 2;            // (cta rank, column half)
+  static constexpr int XCH_BYTES = NSRC * MAXG * BLOCK_M * 8;   // float2 (max, sum)
+  static constexpr int DZ_ROW_BYTES = 32 * (TF32 ? 4 : 2);     // 32 columns per staged row
+  static constexpr int DZ_BUF_BYTES = 32 * DZ_ROW_BYTES;
+  static constexpr int MISC_BYTES = BLOCK_N * 4 /*bias*/ + 2 * MAXG * BLOCK_M * 4 /*tcol, coef*/ +
+                                    BLOCK_N * 4 /*colsum*/ + 64 /*loss*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + XCH_BYTES + MISC_BYTES + 1024;
+  static_assert(SMEM_BYTES <= 232448, "fused forward exceeds shared memory");
+  static_assert(EPI_WARPS * 2 * DZ_BUF_BYTES <= STAGES * STAGE_BYTES, "staging must fit in the idle pipeline buffers");
+};
+
+__device__ __forceinline__ void cluster_arrive_wait() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f2(uint32_t local_smem_addr, uint32_t rank, float a, float b) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_smem_addr), "r"(rank));
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(raddr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <bool TF32>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FusedCfg<TF32>::NUM_THREADS, 1)
+bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                      const __grid_constant__ CUtensorMap tmap_dz, const FusedFwdParams p) {
+  using Cfg = FusedCfg<TF32>;
+  constexpr int BLOCK_M = Cfg::BLOCK_M, BLOCK_N = Cfg::BLOCK_N, BLOCK_K = Cfg::BLOCK_K, STAGES = Cfg::STAGES;
+  constexpr int MAXG = Cfg::MAXG;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+  float2* xch = reinterpret_cast<float2*>(smem + STAGES * Cfg::STAGE_BYTES);   // [NSRC][MAXG][128]
+  float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(xch) + Cfg::XCH_BYTES);  // [320]
+  int* s_tcol = reinterpret_cast<int*>(s_bias + BLOCK_N);      // [MAXG][128] absolute target column
+  float* s_coef = reinterpret_cast<float*>(s_tcol + MAXG * BLOCK_M);  // [MAXG][128] w / avg
+  float* s_colsum = s_coef + MAXG * BLOCK_M;                   // [320]
+  float* s_loss = s_colsum + BLOCK_N;                          // [8]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_loss + 16);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  __shared__ bool s_last;
+  __shared__ int s_gs[kMaxG], s_ge[kMaxG];   // bin start / end, for runtime-indexed access
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int row_tile = blockIdx.x / Cfg::CLUSTER;
+  const int m0 = row_tile * BLOCK_M;
+  const int n0 = static_cast<int>(rank) * BLOCK_N;   // first logit column of this CTA
+  const int G = p.gt.G;
+  if (threadIdx.x == 0) { stamp(p.timing, 0); if (p.timing) p.timing[blockIdx.x * 8 + 7] = sm_id(); }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_dz);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tfull_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_holder, 512); tmem_relinquish(); }
+  if (threadIdx.x < 8) s_loss[threadIdx.x] = 0.f;
+  if (threadIdx.x < kMaxG) {
+    int gs = 0, ge = 0;
+#pragma unroll
+    for (int i = 0; i < kMaxG; ++i)
+      if (i == static_cast<int>(threadIdx.x)) { gs = p.gt.start[i]; ge = p.gt.start[i] + p.gt.len[i]; }
+    s_gs[threadIdx.x] = gs;
+    s_ge[threadIdx.x] = ge;
+  }
+  for (int c = threadIdx.x; c < BLOCK_N; c += Cfg::NUM_THREADS) {
+    s_colsum[c] = 0.f;
+    s_bias[c] = (p.bias != nullptr && n0 + c < p.C) ? __ldg(p.bias + n0 + c) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster_arrive_wait();   // every CTA of the cluster is running before anyone touches remote smem
+  const uint32_t tmem_base = *tmem_holder;
+  if (threadIdx.x == 0) stamp(p.timing, 1);   // setup + first cluster barrier done
+
+  // warp-uniform helpers over the bin table -----------------------------------------------------
+  auto bin_of = [&](int col) -> int {   // -1 : not a logit column
+    int g = -1;
+#pragma unroll
+    for (int i = 0; i < MAXG; ++i)
+      if (i < G && col >= p.gt.start[i] && col < p.gt.start[i] + p.gt.len[i]) g = i;
+    return g;
+  };
+  auto bin_end = [&](int g) -> int {
+    int e = 0;
+#pragma unroll
+    for (int i = 0; i < MAXG; ++i)
+      if (i == g) e = p.gt.start[i] + p.gt.len[i];
+    return e;
+  };
+
+  const int ew = warp - 2;                 // epilogue warp index 0..7 (valid when warp >= 2)
+  const int quarter = warp & 3;            // TMEM lane quarter
+  const int half = (ew >= 0) ? (ew >> 2) : 0;
+  const int row_l = quarter * 32 + lane;   // row inside the tile == TMEM lane
+  const int row = m0 + row_l;
+  const int c_half = half * Cfg::HALF_COLS;   // first TMEM column of this warp's range
+  const int src = static_cast<int>(rank) * 2 + half;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+        const int k0 = kb * BLOCK_K;
+        uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
+        uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
+        tma_load_2d(sa, &tmap_x, &full_bar[stage], k0, m0);
+        tma_load_2d(sb, &tmap_w, &full_bar[stage], k0, n0);
+        tma_load_2d(sb + Cfg::UMMA_N * 128, &tmap_w, &full_bar[stage], k0, n0 + Cfg::UMMA_N);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== UMMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_instr_desc(TF32 ? 2u : 1u, false, false, BLOCK_M, Cfg::UMMA_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (kb == 0) stamp(p.timing, 2);   // first operands landed
+        const uint32_t sa = smem_u32(smem_a + stage * Cfg::A_BYTES);
+        const uint32_t sb = smem_u32(smem_b + stage * Cfg::B_BYTES);
+#pragma unroll
+        for (int k = 0; k < Cfg::K_STEPS; ++k) {
+          const uint64_t adesc = make_smem_desc(sa + k * 32, 16, 1024);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint64_t bdesc = make_smem_desc(sb + h * Cfg::UMMA_N * 128 + k * 32, 16, 1024);
+            const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+            if (TF32) umma_tf32(tmem_base + h * Cfg::UMMA_N, adesc, bdesc, idesc, accum);
+            else      umma_bf16(tmem_base + h * Cfg::UMMA_N, adesc, bdesc, idesc, accum);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tfull_bar);
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue, part 1: row info (overlaps the mainloop) + pass A ==========
+    if (half == 0) {
+      long long lab = 0;
+      if (row < p.N) lab = __ldg(p.labels + row);
+      const bool lab_ok = (row < p.N) && lab >= 0 && lab < p.classes;
+      for (int g = 0; g < G; ++g) {
+        int t = lab_ok ? __ldg(p.l2b + g * p.classes + static_cast<int>(lab)) : 0;
+        t = (t >= 0 && t < s_ge[g] - s_gs[g]) ? t : 0;
+        float w = 0.f;
+        if (row < p.N) w = (p.wmask != nullptr) ? static_cast<float>(__ldg(p.wmask + static_cast<long long>(g) * p.N + row)) : 1.0f;
+        const float inv_avg = 1.0f / (p.avg != nullptr ? __ldg(p.avg + g) : fmaxf(static_cast<float>(p.N), 1.0f));
+        s_tcol[g * BLOCK_M + row_l] = s_gs[g] + t;
+        s_coef[g * BLOCK_M + row_l] = w * inv_avg;
+      }
+    }
+    named_bar_sync(1, 32 * Cfg::EPI_WARPS);
+
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    if (warp == 2 && lane == 0) stamp(p.timing, 3);   // accumulators complete
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c_half;
+
+    // bins this warp does not touch publish the identity (-inf, 0); touched ones are overwritten below
+    for (int g = 0; g < G; ++g) {
+      const int s = s_gs[g], e = s_ge[g];
+      const int lo = n0 + c_half, hi = lo + Cfg::HALF_COLS;
+      if (e <= lo || s >= hi) {
+        const uint32_t addr = smem_u32(&xch[(src * MAXG + g) * BLOCK_M + row_l]);
+#pragma unroll
+        for (uint32_t r = 0; r < 4; ++r) st_cluster_f2(addr, r, -INFINITY, 0.f);
+      }
+    }
+    {
+      int g_cur = -2;
+      float m_cur = -INFINITY, s_cur = 0.f;
+      auto flush = [&]() {
+        if (g_cur >= 0) {
+          const uint32_t addr = smem_u32(&xch[(src * MAXG + g_cur) * BLOCK_M + row_l]);
+#pragma unroll
+          for (uint32_t r = 0; r < 4; ++r) st_cluster_f2(addr, r, m_cur, s_cur);
+        }
+      };
+      // online update of (m_cur, s_cur) with elements j in [lo, hi) of z[32]
+      auto accum = [&](const float (&z)[32], int lo, int hi) {
+        float cm = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) cm = fmaxf(cm, (j >= lo && j < hi) ? z[j] : -INFINITY);
+        const float m_new = fmaxf(m_cur, cm);
+        const float mb = m_new * kLog2e;
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float e = exp2f(fmaf(z[j], kLog2e, -mb));
+          acc += (j >= lo && j < hi) ? e : 0.f;
+        }
+        const float resc = (m_cur == -INFINITY) ? 0.f : exp2f((m_cur - m_new) * kLog2e);
+        s_cur = s_cur * resc + acc;
+        m_cur = m_new;
+      };
+#pragma unroll 1
+      for (int ci = 0; ci < Cfg::CHUNKS; ++ci) {
+        const int col0 = n0 + c_half + ci * 32;
+        if (col0 >= p.C) break;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_row + ci * 32, v);
+        tmem_ld_wait();
+        float z[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c_half + ci * 32 + j]);
+          z[j + 0] = __uint_as_float(v[j + 0]) + b4.x; z[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+          z[j + 2] = __uint_as_float(v[j + 2]) + b4.z; z[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+        }
+        const int gA = bin_of(col0);
+        const int endA = bin_end(gA);
+        const int bpos = (endA - col0 < 32) ? (endA - col0) : 32;   // columns [0,bpos) belong to gA
+        if (gA != g_cur) { flush(); g_cur = gA; m_cur = -INFINITY; s_cur = 0.f; }
+        if (bpos >= 32) {
+          // fast path: the whole chunk is one bin
+          float cm = z[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) cm = fmaxf(cm, z[j]);
+          const float m_new = fmaxf(m_cur, cm);
+          const float mb = m_new * kLog2e;
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc += exp2f(fmaf(z[j], kLog2e, -mb));
+          const float resc = (m_cur == -INFINITY) ? 0.f : exp2f((m_cur - m_new) * kLog2e);
+          s_cur = s_cur * resc + acc;
+          m_cur = m_new;
+        } else {
+          accum(z, 0, bpos);
+          const int gB = bin_of(col0 + bpos);     // -1 beyond the last logit column
+          flush();
+          g_cur = gB; m_cur = -INFINITY; s_cur = 0.f;
+          if (gB >= 0) {
+            const int endB = bin_end(gB);
+            const int hiB = (endB - col0 < 32) ? (endB - col0) : 32;
+            accum(z, bpos, hiB);
+          }
+        }
+      }
+      flush();
+    }
+  }
+
+  // all partials of all four CTAs are in place after this barrier (release/acquire at cluster scope)
+  if (warp == 2 && lane == 0) stamp(p.timing, 4);   // pass A done
+  cluster_arrive_wait();
+  if (warp == 2 && lane == 0) stamp(p.timing, 5);   // exchange barrier passed
+
+  if (warp >= 2) {
+    // ===================== epilogue, part 2: combine + pass C =====================================
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c_half;
+    uint8_t* my_bufs = smem + (ew * 2) * Cfg::DZ_BUF_BYTES;   // aliases the (now idle) pipeline stages
+    uint32_t chunk_ctr = 0;
+    float* colsum_dst = s_colsum + c_half;
+
+    int g_cur = -2;
+    float lb_cur = 0.f, coef_cur = 0.f, pt_cur = 1.0f;
+    int tcol_cur = -1;
+    bool own_cur = false;
+    auto finish_bin = [&]() {   // loss term of the bin whose target column lies in this warp's range
+      if (g_cur >= 0 && own_cur) atomicAdd(&s_loss[g_cur], coef_cur * (-logf(pt_cur)));
+    };
+    auto start_bin = [&](int g) {
+      g_cur = g;
+      pt_cur = 1.0f;
+      own_cur = false;
+      if (g < 0) { lb_cur = 0.f; coef_cur = 0.f; tcol_cur = -1; return; }
+      float M = -INFINITY;
+#pragma unroll
+      for (int s = 0; s < Cfg::NSRC; ++s) M = fmaxf(M, xch[(s * MAXG + g) * BLOCK_M + row_l].x);
+      float S = 0.f;
+#pragma unroll
+      for (int s = 0; s < Cfg::NSRC; ++s) {
+        const float2 ms = xch[(s * MAXG + g) * BLOCK_M + row_l];
+        S += ms.y * exp2f((ms.x - M) * kLog2e);
+      }
+      const float lse_v = M + logf(S);
+      lb_cur = lse_v * kLog2e;
+      coef_cur = s_coef[g * BLOCK_M + row_l];
+      tcol_cur = s_tcol[g * BLOCK_M + row_l];
+      const int lo = n0 + c_half, hi = lo + Cfg::HALF_COLS;
+      own_cur = (tcol_cur >= lo && tcol_cur < hi);
+      if (p.lse != nullptr && row < p.N && s_gs[g] >= lo && s_gs[g] < hi)
+        p.lse[static_cast<long long>(row) * G + g] = lse_v;
+    };
+
+#pragma unroll 1
+    for (int ci = 0; ci < Cfg::CHUNKS; ++ci) {
+      const int col0 = n0 + c_half + ci * 32;
+      if (col0 >= p.C) break;
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(t_row + ci * 32, v);
+      tmem_ld_wait();
+      float d[32];
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c_half + ci * 32 + j]);
+        d[j + 0] = __uint_as_float(v[j + 0]) + b4.x; d[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+        d[j + 2] = __uint_as_float(v[j + 2]) + b4.z; d[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+      }
+      const int gA = bin_of(col0);
+      const int endA = bin_end(gA);
+      const int bpos = (endA - col0 < 32) ? (endA - col0) : 32;
+      if (gA != g_cur) { finish_bin(); start_bin(gA); }
+      if (bpos >= 32) {
+        const int tq = tcol_cur - col0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float pj = exp2f(fmaf(d[j], kLog2e, -lb_cur));
+          float dj = coef_cur * pj;
+          if (j == tq) { pt_cur = pj; dj -= coef_cur; }
+          d[j] = dj;
+        }
+      } else {
+        {
+          const int tq = tcol_cur - col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < bpos) {
+              const float pj = exp2f(fmaf(d[j], kLog2e, -lb_cur));
+              float dj = coef_cur * pj;
+              if (j == tq) { pt_cur = pj; dj -= coef_cur; }
+              d[j] = dj;
+            }
+          }
+        }
+        const int gB = bin_of(col0 + bpos);
+        finish_bin();
+        start_bin(gB);
+        const int endB = (gB >= 0) ? bin_end(gB) : 0;
+        const int hiB = (gB >= 0) ? ((endB - col0 < 32) ? (endB - col0) : 32) : 0;
+        const int tq = tcol_cur - col0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j >= bpos) {
+            float dj = 0.f;
+            if (j < hiB) {
+              const float pj = exp2f(fmaf(d[j], kLog2e, -lb_cur));
+              dj = coef_cur * pj;
+              if (j == tq) { pt_cur = pj; dj -= coef_cur; }
+            }
+            d[j] = dj;
+          }
+        }
+      }
+      if (p.want_dz) {
+        uint8_t* buf = my_bufs + (chunk_ctr & 1u) * Cfg::DZ_BUF_BYTES;
+        ++chunk_ctr;
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        if (TF32) {
+          uint4* rowp = reinterpret_cast<uint4*>(buf + lane * 128);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 r = make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
+            rowp[j ^ (lane & 7)] = *reinterpret_cast<uint4*>(&r);
+          }
+        } else {
+          uint4* rowp = reinterpret_cast<uint4*>(buf + lane * 64);   // 64-byte rows, 64B swizzle
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 r;
+            r.x = pack_bf16x2(d[8 * j + 0], d[8 * j + 1]); r.y = pack_bf16x2(d[8 * j + 2], d[8 * j + 3]);
+            r.z = pack_bf16x2(d[8 * j + 4], d[8 * j + 5]); r.w = pack_bf16x2(d[8 * j + 6], d[8 * j + 7]);
+            rowp[j ^ ((lane >> 1) & 3)] = r;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmap_dz, buf, col0, m0 + quarter * 32);
+          tma_store_commit();
+        }
+        // bias-gradient column sums from the staged tile: lane l owns column l of the chunk
+        if (p.colsum != nullptr) {
+          float cs = 0.f;
+          if (TF32) {
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              const int chunk16 = (lane >> 2) ^ (r & 7);
+              cs += *reinterpret_cast<const float*>(buf + r * 128 + chunk16 * 16 + (lane & 3) * 4);
+            }
+          } else {
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              const int chunk16 = (lane >> 3) ^ ((r >> 1) & 3);
+              const unsigned short h = *reinterpret_cast<const unsigned short*>(buf + r * 64 + chunk16 * 16 + (lane & 7) * 2);
+              cs += __uint_as_float(static_cast<uint32_t>(h) << 16);
+            }
+          }
+          atomicAdd(&colsum_dst[ci * 32 + lane], cs);   // 4 quarters share a column
+        }
+      }
+    }
+    finish_bin();
+    if (lane == 0) tma_store_wait_all();
+    if (warp == 2 && lane == 0) stamp(p.timing, 6);   // pass C done
+    named_bar_sync(1, 32 * Cfg::EPI_WARPS);
+
+    // ---- CTA results -> global ----
+    const int et = threadIdx.x - 64;   // 0..255
+    if (p.colsum != nullptr && p.want_dz) {
+      for (int c = et; c < BLOCK_N; c += 32 * Cfg::EPI_WARPS)
+        if (n0 + c < p.C) red_add_f32(p.colsum + n0 + c, s_colsum[c]);
+    }
+    if (et < kMaxG) p.part[blockIdx.x * kMaxG + et] = (et < G) ? s_loss[et] : 0.f;
+    __threadfence();
+    named_bar_sync(1, 32 * Cfg::EPI_WARPS);
+    if (et == 0) {
+      const unsigned int done = atomicAdd(p.counter, 1u);
+      s_last = (done == gridDim.x - 1);
+    }
+    named_bar_sync(1, 32 * Cfg::EPI_WARPS);
+    if (s_last) {
+      __threadfence();
+      if (ew < G) {
+        float s = 0.f;
+        for (int b = lane; b < static_cast<int>(gridDim.x); b += 32) s += __ldcg(p.part + b * kMaxG + ew);
+        s = warp_sum(s);
+        if (lane == 0) p.loss[ew] = s;   // already divided by avg (coef = w/avg)
+      }
+      if (et == 0) *p.counter = 0u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace bags

@@ -44,6 +44,7 @@ struct GemmParams {
   int glen[kMaxGroups];
   const float* colsum_in;  // optional [M]: db_out[m] = rowscale(m) * colsum_in[m]
   float* colsum_out;       // written by the (n_tile==0, split==0) unit
+  long long* timing;       // debug timeline [grid][8] (ns, %globaltimer) or nullptr
 };
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool TF32, int STAGES>
@@ -67,7 +68,13 @@ struct GemmCfg {
   static constexpr int A_BOX_BYTES = A_BYTES / A_BOXES;
   static constexpr int B_BOXES = B_MN ? BLOCK_N / SLAB : N_MMA;
   static constexpr int B_BOX_BYTES = B_BYTES / B_BOXES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // epilogue staging: per epilogue warp two 32-row x 128-byte swizzled buffers feeding TMA stores
+  static constexpr int EPI_BUF_BYTES = 32 * 128;
+  static constexpr int EPI_STAGING_BYTES = 4 * 2 * EPI_BUF_BYTES;   // 32 KB
+  static constexpr int EPI_COLS = (EPI == EPI_STORE_BF16) ? 64 : 32;  // output columns per 128-byte row
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
+  static_assert(BLOCK_N % EPI_COLS == 0, "tile width must be a multiple of the epilogue chunk");
   static constexpr int NUM_THREADS = 192;
   static_assert(UMMA_N % 16 == 0 && UMMA_N >= 16 && UMMA_N <= 256, "invalid UMMA N");
   static_assert(!B_MN || (BLOCK_N % SLAB == 0 && N_MMA == 1), "MN-major B needs slab-aligned single MMA");
@@ -88,7 +95,7 @@ __device__ __forceinline__ float row_group_scale(const GemmParams& p, int m) {
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool TF32, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 bags_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N, A_MN, B_MN, EPI, TF32, STAGES>;
   constexpr int BLOCK_M = Cfg::BLOCK_M;
   constexpr int BLOCK_K = Cfg::BLOCK_K;
@@ -98,7 +105,8 @@ bags_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* smem_epi = smem + STAGES * Cfg::STAGE_BYTES;  // 1024-byte aligned (all tile sizes are multiples of 1024)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::EPI_STAGING_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
@@ -107,10 +115,12 @@ bags_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { stamp(p.timing, 0); if (p.timing) p.timing[blockIdx.x * 8 + 7] = sm_id(); }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_out);
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -131,6 +141,7 @@ bags_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  if (threadIdx.x == 0) stamp(p.timing, 1);   // setup done
 
   const int units_per_split = p.num_m_tiles * p.num_n_tiles;
   const int num_units = units_per_split * p.num_splits;
@@ -204,6 +215,7 @@ bags_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (local == 0 && kb == kb0) stamp(p.timing, 2);   // first operands landed
           const uint32_t sa = smem_u32(smem_a + stage * Cfg::A_BYTES);
           const uint32_t sb = smem_u32(smem_b + stage * Cfg::B_BYTES);
 #pragma unroll
@@ -221,22 +233,27 @@ bags_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
+        if (local == 0) stamp(p.timing, 3);   // all MMAs of the first tile issued
       }
     }
   } else {
     // ===================== epilogue warps =====================
+    // TMEM -> registers (thread = accumulator row) -> bias / row scale / bf16 pack -> 128B-swizzled smem
+    // staging -> TMA tensor store (or TMA reduce-add for split-K).  The TMA unit writes full 128-byte
+    // rows and clips everything outside [M, N], so there are no per-element bounds checks.
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    uint8_t* my_bufs = smem_epi + quarter * 2 * Cfg::EPI_BUF_BYTES;
+    uint32_t chunk_ctr = 0;
     int local = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++local) {
       const int split = u / units_per_split;
       const int t = u - split * units_per_split;
       const int m_tile = t / p.num_n_tiles, n_tile = t - m_tile * p.num_n_tiles;
-      const int m = m_tile * BLOCK_M + quarter * 32 + lane;
+      const int m_warp = m_tile * BLOCK_M + quarter * 32;
+      const int m = m_warp + lane;
       const int n0 = n_tile * BLOCK_N;
       const int acc = local % Cfg::ACC_STAGES;
       const uint32_t acc_phase = (local / Cfg::ACC_STAGES) & 1u;
-      int kb0, kb1;
-      split_range(split, kb0, kb1);
 
       float scale = 1.0f;
       if (EPI == EPI_RED_F32) {
@@ -247,78 +264,69 @@ bags_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (local == 0 && warp == 2 && lane == 0) stamp(p.timing, 4);   // first accumulator complete
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
-      const bool row_ok = (m < p.M) && (kb1 > kb0);
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
+      for (int c = 0; c < BLOCK_N; c += Cfg::EPI_COLS) {
+        const int n = n0 + c;
+        if (n >= p.N) break;  // warp-uniform: nothing of this chunk is inside the output
+        uint8_t* buf = my_bufs + (chunk_ctr & 1u) * Cfg::EPI_BUF_BYTES;
+        ++chunk_ctr;
         uint32_t v[32];
         tmem_ld_32x32b_x32(t_row + c, v);
+        uint32_t v2[32];
+        if (EPI == EPI_STORE_BF16) tmem_ld_32x32b_x32(t_row + c + 32, v2);
         tmem_ld_wait();
-        const int n = n0 + c;
-        if (row_ok && n < p.N) {
-          if (EPI == EPI_STORE_F32) {
-            float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(m) * p.ldo + n;
-            const bool vec_ok = ((p.ldo & 3) == 0) && (n + 32 <= p.N);
-            if (vec_ok) {
+        // the TMA store that last read this buffer (two chunks ago) must have drained it
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        uint4* rowp = reinterpret_cast<uint4*>(buf + lane * 128);
+        if (EPI == EPI_STORE_BF16) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 r;
-                r.x = __uint_as_float(v[j + 0]); r.y = __uint_as_float(v[j + 1]);
-                r.z = __uint_as_float(v[j + 2]); r.w = __uint_as_float(v[j + 3]);
-                if (p.bias != nullptr) {
-                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-                  r.x += b.x; r.y += b.y; r.z += b.z; r.w += b.w;
-                }
-                *reinterpret_cast<float4*>(o + j) = r;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (n + j < p.N) {
-                  float r = __uint_as_float(v[j]);
-                  if (p.bias != nullptr) r += __ldg(p.bias + n + j);
-                  o[j] = r;
-                }
-              }
-            }
-          } else if (EPI == EPI_STORE_BF16) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(m) * p.ldo + n;
-            const bool vec_ok = ((p.ldo & 7) == 0) && (n + 32 <= p.N);
-            if (vec_ok) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 r;
-                r.x = pack_bf16x2(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
-                r.y = pack_bf16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                r.z = pack_bf16x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
-                r.w = pack_bf16x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
-                *reinterpret_cast<uint4*>(o + j) = r;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n + j < p.N) o[j] = __float2bfloat16_rn(__uint_as_float(v[j]));
-            }
-          } else {  // EPI_RED_F32
-            float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(m) * p.ldo + n;
-            const bool vec_ok = ((p.ldo & 3) == 0) && (n + 32 <= p.N);
-            if (vec_ok) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                red_add_v4_f32(o + j, scale * __uint_as_float(v[j + 0]), scale * __uint_as_float(v[j + 1]),
-                               scale * __uint_as_float(v[j + 2]), scale * __uint_as_float(v[j + 3]));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n + j < p.N) red_add_f32(o + j, scale * __uint_as_float(v[j]));
-            }
+          for (int j = 0; j < 8; ++j) {  // 16-byte chunk j = 8 bf16 = columns 8j..8j+7
+            const uint32_t* src = (j < 4) ? (v + 8 * j) : (v2 + 8 * (j - 4));
+            uint4 r;
+            r.x = pack_bf16x2(__uint_as_float(src[0]), __uint_as_float(src[1]));
+            r.y = pack_bf16x2(__uint_as_float(src[2]), __uint_as_float(src[3]));
+            r.z = pack_bf16x2(__uint_as_float(src[4]), __uint_as_float(src[5]));
+            r.w = pack_bf16x2(__uint_as_float(src[6]), __uint_as_float(src[7]));
+            rowp[j ^ (lane & 7)] = r;
           }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {  // 16-byte chunk j = 4 fp32 = columns 4j..4j+3
+            float4 r;
+            r.x = __uint_as_float(v[4 * j + 0]); r.y = __uint_as_float(v[4 * j + 1]);
+            r.z = __uint_as_float(v[4 * j + 2]); r.w = __uint_as_float(v[4 * j + 3]);
+            if (EPI == EPI_STORE_F32) {
+              if (p.bias != nullptr && n + 4 * j + 3 < p.N) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4 * j));
+                r.x += b.x; r.y += b.y; r.z += b.z; r.w += b.w;
+              } else if (p.bias != nullptr) {
+                if (n + 4 * j + 0 < p.N) r.x += __ldg(p.bias + n + 4 * j + 0);
+                if (n + 4 * j + 1 < p.N) r.y += __ldg(p.bias + n + 4 * j + 1);
+                if (n + 4 * j + 2 < p.N) r.z += __ldg(p.bias + n + 4 * j + 2);
+              }
+            } else {
+              r.x *= scale; r.y *= scale; r.z *= scale; r.w *= scale;
+            }
+            rowp[j ^ (lane & 7)] = *reinterpret_cast<uint4*>(&r);
+          }
+        }
+        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          if (EPI == EPI_RED_F32) tma_reduce_add_2d(&tmap_out, buf, n, m_warp);
+          else                    tma_store_2d(&tmap_out, buf, n, m_warp);
+          tma_store_commit();
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    if (lane == 0) tma_store_wait_all();  // smem must outlive the last bulk reads
+    if (warp == 2 && lane == 0) stamp(p.timing, 5);   // epilogue done
   }
 
   tc_fence_before();
@@ -328,6 +336,7 @@ bags_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
+  if (threadIdx.x == 0) stamp(p.timing, 6);
 }
 
 }  // namespace bags

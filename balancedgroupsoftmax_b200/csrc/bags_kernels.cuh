@@ -115,6 +115,7 @@ group_ce_kernel(const float* __restrict__ z, long long ldz, const long long* __r
       const float w = (wmask != nullptr) ? (float)__ldg(wmask + (long long)g * N + n) : 1.0f;
       // pass 1: max
       float m = -INFINITY;
+#pragma unroll 4
       for (int i = lane; i < len; i += 32) m = fmaxf(m, row[s + i]);
       m = warp_max(m);
       const float zt = row[s + t];  // broadcast read, before pass 2 overwrites
@@ -122,6 +123,7 @@ group_ce_kernel(const float* __restrict__ z, long long ldz, const long long* __r
       // pass 2: e = exp(v - m) kept in smem, sum
       const float mb = m * kLog2e;
       float sum = 0.f;
+#pragma unroll 4
       for (int i = lane; i < len; i += 32) {
         const float e = exp2f(fmaf(row[s + i], kLog2e, -mb));
         row[s + i] = e;
@@ -187,12 +189,26 @@ group_ce_kernel(const float* __restrict__ z, long long ldz, const long long* __r
     __syncwarp();
   }
 
-  // ---- bias-gradient column sums: warp registers -> global atomics ----
+  // ---- bias-gradient column sums: warp registers -> CTA reduction in smem (the row staging
+  //      buffers are free now) -> ONE global reduction per column per CTA ----
   if (colsum != nullptr) {
+    __syncthreads();
+    float* red = smem_rows;  // [8][NV*128] : warp w owns its slice, no conflicts
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int c = lane + 32 * j;
-      if (c < nchunks) red_add_v4_f32(colsum + 4 * c, csum[j][0], csum[j][1], csum[j][2], csum[j][3]);
+      if (c < nchunks)
+        reinterpret_cast<float4*>(red + warp * (NV * 128))[c] = make_float4(csum[j][0], csum[j][1], csum[j][2], csum[j][3]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < nchunks; c += 256) {
+      float4 a = reinterpret_cast<const float4*>(red)[c];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) {
+        const float4 b = reinterpret_cast<const float4*>(red + w * (NV * 128))[c];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      red_add_v4_f32(colsum + 4 * c, a.x, a.y, a.z, a.w);
     }
   }
 
@@ -244,6 +260,9 @@ __device__ __forceinline__ uint32_t sample_key(unsigned long long seed, int g, i
 //   F == 0 -> w = 0 ; k >= O -> w = 1 ; else in-bin rows + the k "others" rows with
 //   the smallest (random key, row index) pairs  (a uniform k-subset).
 //   avg_g = max(sum w, 1).
+// Rows are read from global memory ONCE: thread t keeps rows t, t+1024, ... (EPT of them) in
+// registers as (is_other, key); N > 1024*EPT uses the EPT = 0 instantiation, which re-reads.
+template <int EPT>
 __global__ void __launch_bounds__(1024)
 sample_others_kernel(const long long* __restrict__ labels, const int* __restrict__ l2b, int classes,
                      int G, int N, double ratio, unsigned long long seed,
@@ -264,42 +283,55 @@ sample_others_kernel(const long long* __restrict__ labels, const int* __restrict
     return;
   }
   const int* map = l2b + g * classes;
-  // ---- count in-bin rows ----
+  auto in_bin = [&](int n) -> bool {
+    const long long lab = __ldg(labels + n);
+    return (lab >= 0 && lab < classes) ? (__ldg(map + lab) > 0) : false;
+  };
+  constexpr int R = EPT > 0 ? EPT : 1;
+  bool r_fg[R];
+  uint32_t r_key[R];
+  // ---- count in-bin rows (and cache them) ----
   int cnt = 0;
-  for (int n = tid; n < N; n += 1024) {
-    const long long lab = labels[n];
-    const int t = (lab >= 0 && lab < classes) ? map[lab] : 0;
-    cnt += (t > 0);
+  if (EPT > 0) {
+#pragma unroll
+    for (int e = 0; e < R; ++e) {
+      const int n = tid + e * 1024;
+      r_fg[e] = (n < N) ? in_bin(n) : true;  // out-of-range slots behave like kept rows: never sampled
+      r_key[e] = sample_key(seed, g, n);
+      cnt += (n < N && r_fg[e]) ? 1 : 0;
+    }
+  } else {
+    for (int n = tid; n < N; n += 1024) cnt += in_bin(n) ? 1 : 0;
   }
   cnt = __reduce_add_sync(0xffffffffu, cnt);
   if ((tid & 31) == 0) s_warp[tid >> 5] = cnt;
   __syncthreads();
-  if (tid == 0) {
-    int F = 0;
-    for (int i = 0; i < 32; ++i) F += s_warp[i];
-    s_F = F;
+  if (tid < 32) {
+    int v = s_warp[tid];
+    v = __reduce_add_sync(0xffffffffu, v);
+    if (tid == 0) s_F = v;
   }
   __syncthreads();
   const int F = s_F;
   const int O = N - F;
   const long long k_ll = (long long)((double)F * ratio);  // Python int(): truncation
-  if (F == 0) {
-    for (int n = tid; n < N; n += 1024) w[n] = 0;
-    if (tid == 0) avg[g] = 1.0f;
-    return;
-  }
-  if (k_ll >= (long long)O) {
-    for (int n = tid; n < N; n += 1024) w[n] = 1;
-    if (tid == 0) avg[g] = fmaxf((float)N, 1.0f);
-    return;
-  }
-  const int k = (int)k_ll;  // 0 <= k < O
-  if (tid == 0) avg[g] = fmaxf((float)(F + k), 1.0f);
-  if (k == 0) {
-    for (int n = tid; n < N; n += 1024) {
-      const long long lab = labels[n];
-      const int t = (lab >= 0 && lab < classes) ? map[lab] : 0;
-      w[n] = (t > 0) ? 1 : 0;
+  int mode;  // 0: zeros, 1: ones, 2: in-bin only, 3: sample
+  if (F == 0) mode = 0;
+  else if (k_ll >= (long long)O) mode = 1;
+  else if (k_ll == 0) mode = 2;
+  else mode = 3;
+  const int k = (int)(k_ll < (long long)O ? k_ll : 0);
+  if (tid == 0)
+    avg[g] = (mode == 0) ? 1.0f : (mode == 1) ? fmaxf((float)N, 1.0f) : fmaxf((float)(F + k), 1.0f);
+  if (mode != 3) {
+    if (EPT > 0) {
+#pragma unroll
+      for (int e = 0; e < R; ++e) {
+        const int n = tid + e * 1024;
+        if (n < N) w[n] = (mode == 1) ? 1 : (mode == 0) ? 0 : (r_fg[e] ? 1 : 0);
+      }
+    } else {
+      for (int n = tid; n < N; n += 1024) w[n] = (mode == 1) ? 1 : (mode == 0) ? 0 : (in_bin(n) ? 1 : 0);
     }
     return;
   }
@@ -310,51 +342,78 @@ sample_others_kernel(const long long* __restrict__ labels, const int* __restrict
   for (int shift = 24; shift >= 0; shift -= 8) {
     if (tid < 256) s_hist[tid] = 0;
     __syncthreads();
-    for (int n = tid; n < N; n += 1024) {
-      const long long lab = labels[n];
-      const int t = (lab >= 0 && lab < classes) ? map[lab] : 0;
-      if (t == 0) {
-        const uint32_t key = sample_key(seed, g, n);
-        if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1);
+    if (EPT > 0) {
+#pragma unroll
+      for (int e = 0; e < R; ++e)
+        if (!r_fg[e] && (r_key[e] & mask) == prefix) atomicAdd(&s_hist[(r_key[e] >> shift) & 255u], 1);
+    } else {
+      for (int n = tid; n < N; n += 1024) {
+        if (!in_bin(n)) {
+          const uint32_t key = sample_key(seed, g, n);
+          if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1);
+        }
       }
     }
     __syncthreads();
-    if (tid == 0) {
-      int acc = 0, d = 0;
-      for (; d < 256; ++d) {
-        if (acc + s_hist[d] >= need) break;
-        acc += s_hist[d];
+    if (tid < 32) {
+      // 256 bins -> 32 lanes x 8 bins: lane-local sums, warp inclusive scan, then the owning lane
+      // walks its 8 bins.  Finds digit d with  count(< d) < need <= count(<= d).
+      int c[8];
+      int ls = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { c[i] = s_hist[tid * 8 + i]; ls += c[i]; }
+      int incl = ls;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (tid >= o) incl += t;
       }
-      s_prefix = prefix | (static_cast<uint32_t>(d) << shift);
-      s_need = need - acc;
+      const int excl = incl - ls;
+      if (excl < need && need <= incl) {
+        int acc = excl, d = tid * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (acc + c[i] >= need) { d = tid * 8 + i; break; }
+          acc += c[i];
+        }
+        s_prefix = prefix | (static_cast<uint32_t>(d) << shift);
+        s_need = need - acc;
+      }
     }
     __syncthreads();
     prefix = s_prefix;
     need = s_need;
     mask |= (0xFFu << shift);
-    __syncthreads();
   }
   // ---- write weights; ties on the threshold key broken by ascending row index ----
   if (tid == 0) s_base = 0;
   __syncthreads();
-  for (int n0 = 0; n0 < N; n0 += 1024) {
-    const int n = n0 + tid;
+  const int rounds = (N + 1023) / 1024;
+  for (int e = 0; e < rounds; ++e) {
+    const int n = e * 1024 + tid;
     bool other = false, tie = false;
     uint32_t key = 0;
-    int t = 0;
     if (n < N) {
-      const long long lab = labels[n];
-      t = (lab >= 0 && lab < classes) ? map[lab] : 0;
-      other = (t == 0);
-      if (other) { key = sample_key(seed, g, n); tie = (key == prefix); }
+      bool fg = true;
+      if (EPT > 0) {
+#pragma unroll
+        for (int q = 0; q < R; ++q)
+          if (q == e) { fg = r_fg[q]; key = r_key[q]; }
+      } else {
+        fg = in_bin(n);
+        key = sample_key(seed, g, n);
+      }
+      other = !fg;
+      tie = other && (key == prefix);
     }
     // block-wide exclusive rank of `tie` in row order
     const unsigned bal = __ballot_sync(0xffffffffu, tie);
     const int wrank = __popc(bal & ((1u << (tid & 31)) - 1u));
     if ((tid & 31) == 0) s_warp[tid >> 5] = __popc(bal);
     __syncthreads();
-    int woff = 0;
-    for (int i = 0; i < (tid >> 5); ++i) woff += s_warp[i];
+    const int cw = s_warp[tid & 31];
+    const int woff = __reduce_add_sync(0xffffffffu, ((tid & 31) < (tid >> 5)) ? cw : 0);  // warps before mine
+    const int tot = __reduce_add_sync(0xffffffffu, cw);
     const int rank = s_base + woff + wrank;
     if (n < N) {
       uint8_t wv;
@@ -365,11 +424,7 @@ sample_others_kernel(const long long* __restrict__ labels, const int* __restrict
       w[n] = wv;
     }
     __syncthreads();
-    if (tid == 0) {
-      int tot = 0;
-      for (int i = 0; i < 32; ++i) tot += s_warp[i];
-      s_base += tot;
-    }
+    if (tid == 0) s_base += tot;
     __syncthreads();
   }
 }

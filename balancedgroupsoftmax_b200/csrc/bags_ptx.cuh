@@ -31,6 +31,21 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+__device__ __forceinline__ long long global_timer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ int sm_id() {
+  int r;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+  return r;
+}
+// Debug timeline (test hook): slot layout per CTA is 8 x int64; a null pointer disables it.
+__device__ __forceinline__ void stamp(long long* timing, int slot) {
+  if (timing != nullptr) timing[blockIdx.x * 8 + slot] = global_timer_ns();
+}
+
 // ----------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------
@@ -97,6 +112,27 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
         "r"(c_inner), "r"(c_outer)
       : "memory");
 }
+
+// 2-D tiled store shared::cta -> global (bulk async group); out-of-bounds parts of the box are clipped.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int32_t c_inner,
+                                             int32_t c_outer) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c_inner), "r"(c_outer)
+               : "memory");
+}
+// same, but global += smem (fp32 add performed by the TMA unit at L2)
+__device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, const void* smem_src, int32_t c_inner,
+                                                  int32_t c_outer) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c_inner), "r"(c_outer)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------
 // tcgen05 : TMEM allocation

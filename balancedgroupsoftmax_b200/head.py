@@ -495,7 +495,7 @@ class GSBBoxHeadWith0(SharedFCBBoxHead):
                         reduction_override=reduction_override)
             else:
                 if isinstance(cls_score, ClsScoreHandle) and cls_score._logits is None:
-                    loss_vec, _ = ops.GroupSoftmaxFunction.apply(
+                    loss_vec = ops.GroupSoftmaxFunction.apply(
                         cls_score.x_cls, self.fc_cls.weight, self.fc_cls.bias, labels, dt, wmask, avg,
                         self.compute_dtype, None)
                 else:

@@ -174,9 +174,18 @@ def group_ce(logits: torch.Tensor, labels: torch.Tensor, dt: DeviceTables,
     return loss, lse, dz, colsum
 
 
+def fused_eligible(dt: DeviceTables) -> bool:
+    """True when bags_fwd can keep the logits in tensor memory (fused GEMM + grouped CE kernel)."""
+    return bool(nat.lib().bags_fused_eligible(dt.slices_host, dt.G, dt.num_logits))
+
+
 def fused_fwd(x, w, bias, labels, dt: DeviceTables, wmask, avg, logits: Optional[torch.Tensor] = None,
-              want_dz: bool = True, want_lse: bool = False):
-    """bags_fwd: fc_cls + grouped CE in one ABI call.  Returns (loss, logits, lse, dz, colsum)."""
+              want_dz: bool = True, want_lse: bool = False, materialize: Optional[bool] = None):
+    """bags_fwd: fc_cls + grouped CE in one ABI call.  Returns (loss, logits | None, lse, dz, colsum).
+
+    By default (``logits is None`` and the bin table is eligible) the fused kernel runs and no logits
+    exist in HBM; pass a ``logits`` buffer or ``materialize=True`` for the GEMM -> fp32 logits -> CE route.
+    """
     _require_cuda(x, w, bias, labels, wmask, avg)
     x, w = _row_major(x), _row_major(w)
     if x.dtype != w.dtype:
@@ -185,8 +194,12 @@ def fused_fwd(x, w, bias, labels, dt: DeviceTables, wmask, avg, logits: Optional
     N, K = x.shape
     Cc = w.shape[0]
     dev = x.device
-    if logits is None:
+    if materialize is None:
+        materialize = (logits is not None) or not fused_eligible(dt)
+    if materialize and logits is None:
         logits = torch.empty((N, Cc), dtype=torch.float32, device=dev)
+    if not materialize:
+        logits = None
     loss = torch.empty((dt.G,), dtype=torch.float32, device=dev)
     lse = torch.empty((N, dt.G), dtype=torch.float32, device=dev) if want_lse else None
     dz = colsum = None
@@ -199,8 +212,8 @@ def fused_fwd(x, w, bias, labels, dt: DeviceTables, wmask, avg, logits: Optional
     nat.check(nat.lib().bags_fwd(
         x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), nat.ptr(bias), labels.data_ptr(),
         dt.label2bin.data_ptr(), dt.slices_host, nat.ptr(wmask), nat.ptr(avg), N, K, Cc, dt.G, dt.num_classes,
-        _dtype_code(x.dtype), logits.data_ptr(), logits.stride(0), loss.data_ptr(), nat.ptr(lse), nat.ptr(dz), ldd,
-        nat.ptr(colsum), ws.data_ptr(), ws.numel(), _stream_ptr(dev)), 'bags_fwd')
+        _dtype_code(x.dtype), nat.ptr(logits), logits.stride(0) if logits is not None else 0, loss.data_ptr(),
+        nat.ptr(lse), nat.ptr(dz), ldd, nat.ptr(colsum), ws.data_ptr(), ws.numel(), _stream_ptr(dev)), 'bags_fwd')
     return loss, logits, lse, dz, colsum
 
 
@@ -256,7 +269,7 @@ def gemm_probe(a, a_mn: bool, b, b_mn: bool, M: int, N: int, K: int, block_n: in
     dev = a.device
     if out is None:
         out_dtype = torch.bfloat16 if epi == 1 else torch.float32
-        out = torch.zeros((M, N), dtype=out_dtype, device=dev)
+        out = torch.zeros((M, (N + 7) // 8 * 8), dtype=out_dtype, device=dev)[:, :N]  # 16-byte aligned rows
     nat.check(nat.lib().bags_gemm_probe(a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0), int(b_mn),
                                         out.data_ptr(), out.stride(0), M, N, K, _dtype_code(a.dtype), block_n,
                                         splits, epi, _stream_ptr(dev)), 'bags_gemm_probe')
@@ -267,7 +280,8 @@ def gemm_probe(a, a_mn: bool, b, b_mn: bool, M: int, N: int, K: int, block_n: in
 class GroupSoftmaxFunction(torch.autograd.Function):
     """losses[G] = BAGS(fc_cls(x)) with a fused backward.
 
-    forward : bags_fwd  (tcgen05 fc_cls GEMM -> grouped softmax-CE, saves dz~ and its column sums)
+    forward : bags_fwd  (fused kernel: tcgen05 fc_cls GEMM with the grouped softmax-CE in its epilogue;
+              logits stay in tensor memory unless a ``logits_out`` buffer is given; saves dz~ and its column sums)
     backward: bags_bwd  (dW = dz^T x, db, dX = dz W on tcgen05; per-bin upstream gradients applied
               in the GEMM epilogue / on a scaled copy of W)
 
@@ -292,8 +306,8 @@ class GroupSoftmaxFunction(torch.autograd.Function):
             raise nat.BagsNativeError('compute_dtype must be torch.bfloat16 or torch.float32')
         b32 = None if bias is None else bias.detach().float().contiguous()
         need_grad = any(ctx.needs_input_grad[:3])
-        loss, logits, _, dz, colsum = fused_fwd(xc, wc, b32, labels, dt, wmask, avg, logits=logits_out,
-                                                want_dz=need_grad)
+        loss, _, _, dz, colsum = fused_fwd(xc, wc, b32, labels, dt, wmask, avg, logits=logits_out,
+                                           want_dz=need_grad)
         ctx.dt = dt
         ctx.x_dtype = x.dtype
         ctx.w_dtype = weight.dtype
@@ -301,12 +315,11 @@ class GroupSoftmaxFunction(torch.autograd.Function):
         ctx.bias_dtype = None if bias is None else bias.dtype
         if need_grad:
             ctx.save_for_backward(xc, wc, dz, colsum)
-        ctx.mark_non_differentiable(logits)
-        return loss, logits
+        return loss
 
     @staticmethod
     @torch.autograd.function.once_differentiable
-    def backward(ctx, grad_loss, _grad_logits):
+    def backward(ctx, grad_loss):
         xc, wc, dz, colsum = ctx.saved_tensors
         need_dx, need_dw, need_db = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         gout = grad_loss.detach().to(torch.float32).contiguous()

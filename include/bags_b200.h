@@ -93,7 +93,14 @@ int bags_group_ce(const float* logits, long long ldz, const int64_t* labels,
                   void* dz, long long ldd, int dz_dtype, float* colsum, void* workspace,
                   size_t workspace_bytes, void* stream);
 
-/* bags_linear_fwd into `logits` followed by bags_group_ce (same arguments). */
+/* 1 if bags_fwd can run its fused kernel (logits == NULL) for this bin table: C <= 1280, G <= 6, C % 4 == 0,
+ * bins tile [0, C) contiguously and no 32-column chunk intersects more than two bins. */
+int bags_fused_eligible(const int32_t* slices_host, int G, int C);
+
+/* fc_cls + grouped softmax-CE (+ dz, colsum) in one call.
+ *   logits == NULL : fused kernel -- the logits stay in tensor memory and never reach HBM
+ *                    (requires bags_fused_eligible); ldz is ignored.
+ *   logits != NULL : bags_linear_fwd into `logits` followed by bags_group_ce (same arguments). */
 int bags_fwd(const void* x, long long ldx, const void* w, long long ldw, const float* bias,
              const int64_t* labels, const int32_t* label2bin, const int32_t* slices_host,
              const uint8_t* wmask, const float* avg, int N, int K, int C, int G, int classes,
@@ -127,6 +134,11 @@ int bags_cast_bf16(const float* src, long long lds, void* dst, long long ldd, in
 int bags_gemm_probe(const void* a, long long lda, int a_mn, const void* b, long long ldb, int b_mn,
                     void* out, long long ldo, int M, int N, int K, int dtype, int block_n,
                     int splits, int epi, void* stream);
+
+/* Test hook: point the tcgen05 kernels at a device buffer of [ctas][8] int64 that they stamp with
+ * %globaltimer values (0 start, 1 setup done, 2 first operands landed, 3..6 phase ends, 7 SM id).
+ * NULL (the default) disables it.  Not thread-safe; for profiling only. */
+int bags_debug_set_timing(void* dev_ptr);
 
 #ifdef __cplusplus
 }

@@ -178,7 +178,7 @@ def case_fused(name):
         wmask = torch.stack([w.to(torch.uint8) for w in remapped[1]]).cuda()
         avg = ops.mask_avg(wmask)
         xc, wc = x.cuda().to(cdt), W.cuda().to(cdt)
-        loss, logits, _, dz, colsum = ops.fused_fwd(xc, wc, b.cuda(), labels.cuda(), dt, wmask, avg)
+        loss, logits, _, dz, colsum = ops.fused_fwd(xc, wc, b.cuda(), labels.cuda(), dt, wmask, avg, materialize=True)
         dW, db, dX = ops.fused_bwd(dz, xc, wc, torch.tensor(gout, device='cuda'), dt, colsum)
         torch.cuda.synchronize()
         lr = max(abs(loss[g].item() - ref['loss_cls_bin%d' % g].item()) / abs(ref['loss_cls_bin%d' % g].item())
@@ -191,6 +191,96 @@ def case_fused(name):
         for k_, v in res.items():
             assert v < tol[k_], (k_, v, tol[k_])
     return out
+
+
+
+def case_fusedk(name):
+    """fused forward kernel (logits stay in TMEM) vs the oracle, incl. ragged N and lse output"""
+    np, torch, ops, _, O = _setup()
+    _, dts = name.split('.')
+    cdt = torch.bfloat16 if dts == 'bf16' else torch.float32
+    out = {}
+    for N in (1, 77, 128, 512, 1000, 4096):
+        t, x, W, b, labels, l2b, ps, remapped = _problem(N, seed=N)
+        if cdt == torch.bfloat16:
+            xo, Wo = x.bfloat16().float(), W.bfloat16().float()
+        else:
+            xo, Wo = x, W
+        z = O.fc_cls(xo, Wo, b)
+        ref = O.bags_loss(z, labels, l2b, ps, remapped=remapped)
+        dz_ref, dW_ref, db_ref, dX_ref = O.closed_form_grads(xo, Wo, b, labels, l2b, ps, remapped)
+        dt = ops.DeviceTables.from_tables(t, 'cuda')
+        assert ops.fused_eligible(dt)
+        wmask = torch.stack([w.to(torch.uint8) for w in remapped[1]]).cuda()
+        avg = ops.mask_avg(wmask)
+        xc, wc = x.cuda().to(cdt), W.cuda().to(cdt)
+        loss, logits, lse, dz, colsum = ops.fused_fwd(xc, wc, b.cuda(), labels.cuda(), dt, wmask, avg, want_lse=True)
+        assert logits is None
+        torch.cuda.synchronize()
+        lr = max(abs(loss[g].item() - ref['loss_cls_bin%d' % g].item()) / max(abs(ref['loss_cls_bin%d' % g].item()), 1e-2)
+                 for g in range(dt.G))
+        lse_ref = torch.stack([torch.logsumexp(z[:, int(ps[g, 0]):int(ps[g, 0]) + int(ps[g, 1])], 1) for g in range(5)], 1)
+        res = dict(loss=lr, lse=rel(lse.cpu(), lse_ref), dz=rel(dz[:, :t.num_logits].float().cpu(), dz_ref),
+                   colsum=rel(colsum.cpu(), db_ref) if db_ref.norm() > 0 else 0.0)
+        dW, db, dX = ops.fused_bwd(dz, xc, wc, None, dt, colsum)
+        torch.cuda.synchronize()
+        res['dW'] = rel(dW.cpu(), dW_ref)
+        out['N%d' % N] = res
+        tol = dict(loss=1e-4, lse=1e-5, dz=4e-3, colsum=2e-3, dW=3e-3) if cdt == torch.bfloat16 else \
+            dict(loss=1e-3, lse=1e-3, dz=2e-3, colsum=1e-3, dW=1e-3)
+        for k_, v in res.items():
+            assert v < tol[k_], (N, k_, v, tol[k_])
+    return out
+
+
+def case_timeline(name):
+    """per-CTA %globaltimer stamps of the tcgen05 kernels at the benchmark shape"""
+    np, torch, ops, _, O = _setup()
+    from balancedgroupsoftmax_b200 import _native as nat
+    N = 4096
+    t, x, W, b, labels, l2b, ps, remapped = _problem(N)
+    dt = ops.DeviceTables.from_tables(t, 'cuda')
+    xc, wc = x.cuda().bfloat16(), W.cuda().bfloat16()
+    bc, lc = b.cuda(), labels.cuda()
+    wmask, avg = ops.sample_others(lc, dt, 8.0, 1)
+    logits = torch.empty(N, t.num_logits, device='cuda')
+    tbuf = torch.zeros(4096, 8, dtype=torch.int64, device='cuda')
+    res = {}
+
+    def run(label, fn, nctas):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        tbuf.zero_()
+        nat.check(nat.lib().bags_debug_set_timing(tbuf.data_ptr()), 'set_timing')
+        fn()
+        torch.cuda.synchronize()
+        nat.check(nat.lib().bags_debug_set_timing(None), 'set_timing')
+        tb = tbuf[:nctas].cpu().double()
+        t0 = tb[:, 0].min()
+        end = tb[:, 6].max()
+        d = {}
+        d['kernel_span_us'] = float((end - t0) / 1e3)
+        d['cta_start_skew_us'] = float((tb[:, 0].max() - t0) / 1e3)
+        names = ['start', 'setup', 'first_data', 's3', 's4', 's5', 'end']
+        for i in range(1, 7):
+            seg = (tb[:, i] - tb[:, i - 1]) / 1e3
+            d['%s->%s_us(mean,max)' % (names[i - 1], names[i])] = [round(float(seg.mean()), 2), round(float(seg.max()), 2)]
+        d['cta_life_us(mean,max)'] = [round(float(((tb[:, 6] - tb[:, 0]) / 1e3).mean()), 2),
+                                      round(float(((tb[:, 6] - tb[:, 0]) / 1e3).max()), 2)]
+        d['distinct_sms'] = int(tb[:, 7].unique().numel())
+        res[label] = d
+
+    run('gemm_fwd_320 (s3=mma issued, s4=acc done, s5=epi done)',
+        lambda: ops.linear_fwd(xc, wc, bc, out=logits), 128)
+    loss, _, _, dz, colsum = ops.fused_fwd(xc, wc, bc, lc, dt, wmask, avg, logits=logits)
+    dW = torch.empty(t.num_logits, 1024, device='cuda')
+    dX = torch.empty(N, 1024, device='cuda', dtype=torch.bfloat16)
+    run('gemm_dX_256', lambda: ops.fused_bwd(dz, xc, wc, None, dt, colsum, need_dw=False, need_db=False, dX=dX), 128)
+    run('gemm_dW_256_split3', lambda: ops.fused_bwd(dz, xc, wc, None, dt, colsum, need_dx=False, dW=dW), 120)
+    run('fused_fwd (s3=acc done, s4=passA, s5=xchg barrier, end=passC...)',
+        lambda: ops.fused_fwd(xc, wc, bc, lc, dt, wmask, avg), 128)
+    return res
 
 
 def case_timing(name):
@@ -228,7 +318,8 @@ def case_timing(name):
     res['bwd_all_us'] = timeit(lambda: ops.fused_bwd(dz, xc, wc, gout, dt, colsum, dW=dW, dX=dX, wscratch=ws))
     res['bwd_dw_only_us'] = timeit(lambda: ops.fused_bwd(dz, xc, wc, gout, dt, colsum, need_dx=False, dW=dW))
     res['bwd_dx_only_us'] = timeit(lambda: ops.fused_bwd(dz, xc, wc, None, dt, colsum, need_dw=False, need_db=False, dX=dX))
-    res['fwd_all_us'] = timeit(lambda: ops.fused_fwd(xc, wc, bc, lc, dt, wmask, avg, logits=logits))
+    res['fwd_unfused_us'] = timeit(lambda: ops.fused_fwd(xc, wc, bc, lc, dt, wmask, avg, logits=logits))
+    res['fwd_fused_us'] = timeit(lambda: ops.fused_fwd(xc, wc, bc, lc, dt, wmask, avg))
     # torch reference pieces on the same device for scale
     res['torch_matmul_bf16_us'] = timeit(lambda: torch.matmul(xc, wc.t()))
     return res
@@ -239,7 +330,8 @@ CASES = {
     'gemm.kk256.bf16': case_gemm, 'gemm.kk320.bf16': case_gemm, 'gemm.kmn.bf16': case_gemm,
     'gemm.mnmn.bf16': case_gemm,
     'gemm.kk256.f32': case_gemm, 'gemm.kk320.f32': case_gemm, 'gemm.kmn.f32': case_gemm, 'gemm.mnmn.f32': case_gemm,
-    'fused.bf16': case_fused, 'fused.f32': case_fused, 'timing': case_timing,
+    'fused.bf16': case_fused, 'fused.f32': case_fused, 'fusedk.bf16': case_fusedk, 'fusedk.f32': case_fusedk,
+    'timeline': case_timeline, 'timing': case_timing,
 }
 
 
