@@ -61,8 +61,11 @@ static bool g_dev_ok[64] = {false};
 
 // test hook: device buffer [ctas][8] int64 that the next launches stamp with %globaltimer values
 static long long* g_timing = nullptr;
+static int g_dbg = 0;
 extern "C" int bags_debug_set_timing(void* dev_ptr) {
   g_timing = reinterpret_cast<long long*>(dev_ptr);
+  const char* v = getenv("BAGS_DBG");
+  g_dbg = (v && *v) ? atoi(v) : 0;
   return BAGS_OK;
 }
 
@@ -169,16 +172,9 @@ static int launch_gemm(const GemmArgs& ga, const DeviceInfo& di, cudaStream_t st
   else      rc = make_tmap(&tb, ga.b, ga.dtype, ga.K, ga.N, ga.ldb, Cfg::BLOCK_K, Cfg::UMMA_N);
   if (rc) return rc;
 
-  // output tensor map: [M, N] row-major, 32-row x 128-byte boxes
-  CUtensorMap tc;
-  {
-    const int out_dtype = (EPI == EPI_STORE_BF16) ? BAGS_DTYPE_BF16 : BAGS_DTYPE_F32;
-    rc = make_tmap(&tc, ga.p.out, out_dtype, ga.N, ga.M, ga.p.ldo, Cfg::EPI_COLS, 32);
-    if (rc) return rc;
-  }
-
   GemmParams p = ga.p;
   p.timing = g_timing;
+  p.dbg = g_timing ? g_dbg : 0;
   p.M = ga.M; p.N = ga.N; p.K = ga.K;
   p.num_m_tiles = (ga.M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
   p.num_n_tiles = (ga.N + BLOCK_N - 1) / BLOCK_N;
@@ -192,7 +188,7 @@ static int launch_gemm(const GemmArgs& ga, const DeviceInfo& di, cudaStream_t st
   const int grid = units < di.num_sms ? units : di.num_sms;
 
   BAGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  kernel<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tc, p);
+  kernel<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
   BAGS_CUDA(cudaGetLastError());
   return BAGS_OK;
 }
@@ -389,28 +385,35 @@ static int launch_fused_fwd(const void* x, long long ldx, const void* w, long lo
                             void* dz, long long ldd, const DeviceInfo& di, cudaStream_t stream) {
   using Cfg = FusedCfg<TF32>;
   const int dtype = TF32 ? BAGS_DTYPE_F32 : BAGS_DTYPE_BF16;
-  CUtensorMap tx, tw, td;
+  CUtensorMap tx, tw;
   int rc = make_tmap(&tx, x, dtype, p0.K, p0.N, ldx, Cfg::BLOCK_K, Cfg::BLOCK_M);
   if (rc) return rc;
   rc = make_tmap(&tw, w, dtype, p0.K, p0.C, ldw, Cfg::BLOCK_K, Cfg::UMMA_N);
   if (rc) return rc;
-  if (dz != nullptr) {
-    rc = TF32 ? make_tmap(&td, dz, dtype, p0.C, p0.N, ldd, 32, 32)
-              : make_tmap(&td, dz, dtype, p0.C, p0.N, ldd, 32, 32, false, true);
-    if (rc) return rc;
-  } else {
-    td = tx;  // never dereferenced (want_dz == 0)
-  }
+  if (dz != nullptr && (reinterpret_cast<uintptr_t>(dz) & 15) != 0)
+    return fail(BAGS_ERR_INVALID, "bags_fwd: dz must be 16-byte aligned");
   FusedFwdParams p = p0;
+  p.dz = dz;
+  p.ldd = ldd;
   p.kblocks = (p.K + Cfg::BLOCK_K - 1) / Cfg::BLOCK_K;
   p.want_dz = dz != nullptr ? 1 : 0;
   p.timing = g_timing;
+  p.dbg = g_timing ? g_dbg : 0;
   auto kernel = bags_fwd_fused_kernel<TF32>;
   BAGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int grid = Cfg::CLUSTER * ((p.N + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M);
   (void)di;
-  kernel<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tx, tw, td, p);
-  BAGS_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(Cfg::NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // overlap with the sampler (pdl_wait in-kernel)
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = env_int("BAGS_PDL", 1) ? 1 : 0;
+  BAGS_CUDA(cudaLaunchKernelEx(&cfg, kernel, tx, tw, p));
   return BAGS_OK;
 }
 
@@ -419,9 +422,15 @@ extern "C" int bags_fwd(const void* x, long long ldx, const void* w, long long l
                         const int32_t* slices_host, const uint8_t* wmask, const float* avg, int N,
                         int K, int C, int G, int classes, int dtype, float* logits, long long ldz,
                         float* loss, float* lse, void* dz, long long ldd, float* colsum,
-                        void* workspace, size_t workspace_bytes, void* stream_) {
+                        int colsum_tiles, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (colsum != nullptr)
+    BAGS_REQUIRE(colsum_tiles >= 1 && (logits != nullptr || colsum_tiles == (N + 127) / 128 || N == 0),
+                 "bags_fwd: colsum must hold ceil(N/128) = %d row tiles of C floats (got %d)", (N + 127) / 128, colsum_tiles);
   if (logits != nullptr) {
-    // caller wants materialised logits: GEMM with fp32 store, then the stand-alone grouped CE
+    // caller wants materialised logits: GEMM with fp32 store, then the stand-alone grouped CE (tile 0 holds
+    // the column sums, the other tiles are zero)
+    if (colsum != nullptr && colsum_tiles > 1)
+      BAGS_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * C * colsum_tiles, static_cast<cudaStream_t>(stream_)));
     if (int rc = bags_linear_fwd(x, ldx, w, ldw, bias, logits, ldz, N, K, C, dtype, stream_)) return rc;
     return bags_group_ce(logits, ldz, labels, label2bin, slices_host, wmask, avg, N, C, G, classes, loss,
                          lse, dz, ldd, dtype, colsum, workspace, workspace_bytes, stream_);
@@ -440,9 +449,9 @@ extern "C" int bags_fwd(const void* x, long long ldx, const void* w, long long l
   if (int rc = make_group_table(gt, slices_host, G, C)) return rc;
   DeviceInfo di;
   if (int rc = device_info(di)) return rc;
-  if (colsum != nullptr) BAGS_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * C, stream));
   if (N == 0) {
     BAGS_CUDA(cudaMemsetAsync(loss, 0, sizeof(float) * G, stream));
+    if (colsum != nullptr) BAGS_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * C * colsum_tiles, stream));
     return BAGS_OK;
   }
   const int grid = 4 * ((N + 127) / 128);
@@ -491,7 +500,7 @@ scale_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, long long ld, 
 }
 
 __global__ void __launch_bounds__(256)
-scale_colsum_kernel(const float* __restrict__ colsum, float* __restrict__ db, int C, GroupTable gt,
+scale_colsum_kernel(const float* __restrict__ colsum, int tiles, float* __restrict__ db, int C, GroupTable gt,
                     const float* __restrict__ gout) {
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c >= C) return;
@@ -499,12 +508,14 @@ scale_colsum_kernel(const float* __restrict__ colsum, float* __restrict__ db, in
   if (gout != nullptr)
     for (int g = 0; g < gt.G; ++g)
       if (c >= gt.start[g] && c < gt.start[g] + gt.len[g]) s = __ldg(gout + g);
-  db[c] = s * colsum[c];
+  float cs = 0.f;
+  for (int t = 0; t < tiles; ++t) cs += colsum[(long long)t * C + c];
+  db[c] = s * cs;
 }
 
 extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long ldx, const void* w,
                         long long ldw, const float* gout, const int32_t* slices_host,
-                        const float* colsum, float* dW, long long lddw, float* db, void* dX,
+                        const float* colsum, int colsum_tiles, float* dW, long long lddw, float* db, void* dX,
                         long long lddx, void* wscratch, int N, int K, int C, int G, int dtype,
                         void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -515,7 +526,7 @@ extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long 
   if (int rc = make_group_table(gt, slices_host, G, C)) return rc;
   DeviceInfo di;
   if (int rc = device_info(di)) return rc;
-  if (db != nullptr) BAGS_REQUIRE(colsum != nullptr, "bags_bwd: db requested but colsum is NULL");
+  if (db != nullptr) BAGS_REQUIRE(colsum != nullptr && colsum_tiles >= 1, "bags_bwd: db requested but colsum is NULL");
 
   if (dW != nullptr) {
     BAGS_REQUIRE(x != nullptr || N == 0, "bags_bwd: x is NULL but dW requested");
@@ -535,6 +546,7 @@ extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long 
       for (int g = 0; g < kMaxGroups; ++g) { ga.p.gstart[g] = gt.start[g]; ga.p.glen[g] = gt.len[g]; }
       if (gout == nullptr) { ga.p.G = 0; }
       ga.p.colsum_in = (db != nullptr) ? colsum : nullptr;
+      ga.p.colsum_tiles = colsum_tiles;
       ga.p.colsum_out = (db != nullptr && colsum != nullptr) ? db : nullptr;
       int rc = (dtype == BAGS_DTYPE_BF16)
                    ? launch_gemm<256, true, true, EPI_RED_F32, false, 4>(ga, di, stream)
@@ -543,7 +555,7 @@ extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long 
     }
   }
   if (db != nullptr && (dW == nullptr || N == 0)) {
-    scale_colsum_kernel<<<(C + 255) / 256, 256, 0, stream>>>(colsum, db, C, gt, gout);
+    scale_colsum_kernel<<<(C + 255) / 256, 256, 0, stream>>>(colsum, colsum_tiles, db, C, gt, gout);
     BAGS_CUDA(cudaGetLastError());
   }
 

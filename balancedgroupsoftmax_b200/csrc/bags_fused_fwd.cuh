@@ -13,7 +13,8 @@
 //   pass A  (after the mainloop):  per bin segment, online (max, sum exp(z - max))
 //   exchange + barrier.cluster
 //   pass C:  p = exp(z - lse_bin) ; dz~ = w/avg * (p - onehot)  -> bf16/fp32 -> swizzled smem
-//            -> TMA tensor store ;  column sums of dz~ (bias gradient) from the staged tile ;
+//            -> transposed, fully coalesced 16-byte stores ; column sums of dz~ (bias gradient) from the
+//            staged tile ;
 //            loss_bin += w/avg * -log p[target]
 //
 // reference semantics: gs_bbox_head_with0.py:91-112 (labels/weights), :134-171 (slices + CE),
@@ -38,11 +39,14 @@ struct FusedFwdParams {
   const float* avg;         // [G] or nullptr (N)
   float* loss;              // [G]
   float* lse;               // [N, G] or nullptr
-  float* colsum;            // [C] (+=, caller zeroes) or nullptr
+  float* colsum;            // [row tiles, C] per-row-tile column sums of dz (plain stores) or nullptr
   float* part;              // [gridDim.x, kMaxG]
   unsigned int* counter;
+  void* dz;                 // [N, ldd] operand dtype, or nullptr (loss only)
+  long long ldd;
   int want_dz;
   long long* timing;        // debug timeline [grid][8] or nullptr
+  int dbg;                  // test hook: bit0 skip dz stores, bit2 skip column sums
 };
 
 template <bool TF32>
@@ -88,6 +92,12 @@ __device__ __forceinline__ void st_cluster_f2(uint32_t local_smem_addr, uint32_t
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_smem_addr), "r"(rank));
   asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(raddr), "f"(a), "f"(b) : "memory");
 }
+// single-MUFU 2^x (ex2.approx.ftz, ~2 ulp): the inputs are <= 0 after max subtraction
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -95,7 +105,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 template <bool TF32>
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FusedCfg<TF32>::NUM_THREADS, 1)
 bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                      const __grid_constant__ CUtensorMap tmap_dz, const FusedFwdParams p) {
+                      const FusedFwdParams p) {
   using Cfg = FusedCfg<TF32>;
   constexpr int BLOCK_M = Cfg::BLOCK_M, BLOCK_N = Cfg::BLOCK_N, BLOCK_K = Cfg::BLOCK_K, STAGES = Cfg::STAGES;
   constexpr int MAXG = Cfg::MAXG;
@@ -129,7 +139,6 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
-    tma_prefetch_desc(&tmap_dz);
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(tfull_bar, 1);
@@ -229,6 +238,7 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     __syncwarp();
   } else {
     // ===================== epilogue, part 1: row info (overlaps the mainloop) + pass A ==========
+    pdl_wait();   // masks / avg come from the preceding sampler kernel (programmatic dependent launch)
     if (half == 0) {
       long long lab = 0;
       if (row < p.N) lab = __ldg(p.labels + row);
@@ -280,19 +290,19 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         float acc = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float e = exp2f(fmaf(z[j], kLog2e, -mb));
+          const float e = fast_exp2(fmaf(z[j], kLog2e, -mb));
           acc += (j >= lo && j < hi) ? e : 0.f;
         }
-        const float resc = (m_cur == -INFINITY) ? 0.f : exp2f((m_cur - m_new) * kLog2e);
+        const float resc = (m_cur == -INFINITY) ? 0.f : fast_exp2((m_cur - m_new) * kLog2e);
         s_cur = s_cur * resc + acc;
         m_cur = m_new;
       };
-#pragma unroll 1
+      uint32_t v[32];
+      if (n0 + c_half < p.C) tmem_ld_32x32b_x32(t_row, v);   // software pipeline: chunk ci+1 is in flight
+#pragma unroll 1                                                // while chunk ci is reduced
       for (int ci = 0; ci < Cfg::CHUNKS; ++ci) {
         const int col0 = n0 + c_half + ci * 32;
         if (col0 >= p.C) break;
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_row + ci * 32, v);
         tmem_ld_wait();
         float z[32];
 #pragma unroll
@@ -301,21 +311,24 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           z[j + 0] = __uint_as_float(v[j + 0]) + b4.x; z[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
           z[j + 2] = __uint_as_float(v[j + 2]) + b4.z; z[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
         }
+        if (ci + 1 < Cfg::CHUNKS && col0 + 32 < p.C) tmem_ld_32x32b_x32(t_row + (ci + 1) * 32, v);
         const int gA = bin_of(col0);
         const int endA = bin_end(gA);
         const int bpos = (endA - col0 < 32) ? (endA - col0) : 32;   // columns [0,bpos) belong to gA
         if (gA != g_cur) { flush(); g_cur = gA; m_cur = -INFINITY; s_cur = 0.f; }
         if (bpos >= 32) {
           // fast path: the whole chunk is one bin
-          float cm = z[0];
+          float c4[4] = {z[0], z[1], z[2], z[3]};
 #pragma unroll
-          for (int j = 1; j < 32; ++j) cm = fmaxf(cm, z[j]);
+          for (int j = 4; j < 32; ++j) c4[j & 3] = fmaxf(c4[j & 3], z[j]);
+          const float cm = fmaxf(fmaxf(c4[0], c4[1]), fmaxf(c4[2], c4[3]));
           const float m_new = fmaxf(m_cur, cm);
           const float mb = m_new * kLog2e;
-          float acc = 0.f;
+          float a4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc += exp2f(fmaf(z[j], kLog2e, -mb));
-          const float resc = (m_cur == -INFINITY) ? 0.f : exp2f((m_cur - m_new) * kLog2e);
+          for (int j = 0; j < 32; ++j) a4[j & 3] += fast_exp2(fmaf(z[j], kLog2e, -mb));
+          const float acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+          const float resc = (m_cur == -INFINITY) ? 0.f : fast_exp2((m_cur - m_new) * kLog2e);
           s_cur = s_cur * resc + acc;
           m_cur = m_new;
         } else {
@@ -350,8 +363,12 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     float lb_cur = 0.f, coef_cur = 0.f, pt_cur = 1.0f;
     int tcol_cur = -1;
     bool own_cur = false;
-    auto finish_bin = [&]() {   // loss term of the bin whose target column lies in this warp's range
-      if (g_cur >= 0 && own_cur) atomicAdd(&s_loss[g_cur], coef_cur * (-logf(pt_cur)));
+    auto finish_bin = [&]() {   // loss terms of the bin: rows whose target column lies in this warp's range
+      if (g_cur >= 0) {           // warp-uniform
+        float term = own_cur ? coef_cur * (-__logf(pt_cur)) : 0.f;
+        term = warp_sum(term);    // one shared-memory atomic per warp instead of 32 contending CAS loops
+        if (lane == 0) atomicAdd(&s_loss[g_cur], term);
+      }
     };
     auto start_bin = [&](int g) {
       g_cur = g;
@@ -365,7 +382,7 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 #pragma unroll
       for (int s = 0; s < Cfg::NSRC; ++s) {
         const float2 ms = xch[(s * MAXG + g) * BLOCK_M + row_l];
-        S += ms.y * exp2f((ms.x - M) * kLog2e);
+        S += ms.y * fast_exp2((ms.x - M) * kLog2e);
       }
       const float lse_v = M + logf(S);
       lb_cur = lse_v * kLog2e;
@@ -377,12 +394,12 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         p.lse[static_cast<long long>(row) * G + g] = lse_v;
     };
 
+    uint32_t v[32];
+    if (n0 + c_half < p.C) tmem_ld_32x32b_x32(t_row, v);
 #pragma unroll 1
     for (int ci = 0; ci < Cfg::CHUNKS; ++ci) {
       const int col0 = n0 + c_half + ci * 32;
       if (col0 >= p.C) break;
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(t_row + ci * 32, v);
       tmem_ld_wait();
       float d[32];
 #pragma unroll
@@ -391,6 +408,8 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         d[j + 0] = __uint_as_float(v[j + 0]) + b4.x; d[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
         d[j + 2] = __uint_as_float(v[j + 2]) + b4.z; d[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
       }
+      // next chunk's TMEM load overlaps the exp / pack / store phases of this one
+      if (ci + 1 < Cfg::CHUNKS && col0 + 32 < p.C) tmem_ld_32x32b_x32(t_row + (ci + 1) * 32, v);
       const int gA = bin_of(col0);
       const int endA = bin_end(gA);
       const int bpos = (endA - col0 < 32) ? (endA - col0) : 32;
@@ -399,7 +418,7 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         const int tq = tcol_cur - col0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float pj = exp2f(fmaf(d[j], kLog2e, -lb_cur));
+          const float pj = fast_exp2(fmaf(d[j], kLog2e, -lb_cur));
           float dj = coef_cur * pj;
           if (j == tq) { pt_cur = pj; dj -= coef_cur; }
           d[j] = dj;
@@ -410,7 +429,7 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             if (j < bpos) {
-              const float pj = exp2f(fmaf(d[j], kLog2e, -lb_cur));
+              const float pj = fast_exp2(fmaf(d[j], kLog2e, -lb_cur));
               float dj = coef_cur * pj;
               if (j == tq) { pt_cur = pj; dj -= coef_cur; }
               d[j] = dj;
@@ -428,7 +447,7 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           if (j >= bpos) {
             float dj = 0.f;
             if (j < hiB) {
-              const float pj = exp2f(fmaf(d[j], kLog2e, -lb_cur));
+              const float pj = fast_exp2(fmaf(d[j], kLog2e, -lb_cur));
               dj = coef_cur * pj;
               if (j == tq) { pt_cur = pj; dj -= coef_cur; }
             }
@@ -439,8 +458,7 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       if (p.want_dz) {
         uint8_t* buf = my_bufs + (chunk_ctr & 1u) * Cfg::DZ_BUF_BYTES;
         ++chunk_ctr;
-        if (lane == 0) tma_store_wait_read<1>();
-        __syncwarp();
+        const int m_warp = m0 + quarter * 32;
         if (TF32) {
           uint4* rowp = reinterpret_cast<uint4*>(buf + lane * 128);
 #pragma unroll
@@ -448,8 +466,17 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             float4 r = make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
             rowp[j ^ (lane & 7)] = *reinterpret_cast<uint4*>(&r);
           }
+          __syncwarp();
+          // transposed read-back: each warp-wide 16-byte store covers 4 complete 128-byte rows
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + (lane >> 3), ch = lane & 7;
+            const uint4 val = *reinterpret_cast<const uint4*>(buf + r * 128 + ((ch ^ (r & 7)) << 4));
+            if (m_warp + r < p.N && !(p.dbg & 1))
+              *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.dz) + static_cast<long long>(m_warp + r) * p.ldd + col0 + ch * 4) = val;
+          }
         } else {
-          uint4* rowp = reinterpret_cast<uint4*>(buf + lane * 64);   // 64-byte rows, 64B swizzle
+          uint4* rowp = reinterpret_cast<uint4*>(buf + lane * 64);   // 64-byte rows, 64B-style swizzle
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 r;
@@ -457,36 +484,38 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             r.z = pack_bf16x2(d[8 * j + 4], d[8 * j + 5]); r.w = pack_bf16x2(d[8 * j + 6], d[8 * j + 7]);
             rowp[j ^ ((lane >> 1) & 3)] = r;
           }
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&tmap_dz, buf, col0, m0 + quarter * 32);
-          tma_store_commit();
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {   // 8 rows x 64 bytes per warp-wide store
+            const int r = it * 8 + (lane >> 2), ch = lane & 3;
+            const uint4 val = *reinterpret_cast<const uint4*>(buf + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4));
+            if (m_warp + r < p.N && !(p.dbg & 1))
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.dz) + static_cast<long long>(m_warp + r) * p.ldd + col0 + ch * 8) = val;
+          }
         }
         // bias-gradient column sums from the staged tile: lane l owns column l of the chunk
-        if (p.colsum != nullptr) {
-          float cs = 0.f;
+        if (p.colsum != nullptr && !(p.dbg & 4)) {
+          float cs4[4] = {0.f, 0.f, 0.f, 0.f};
           if (TF32) {
-#pragma unroll 8
+#pragma unroll
             for (int r = 0; r < 32; ++r) {
               const int chunk16 = (lane >> 2) ^ (r & 7);
-              cs += *reinterpret_cast<const float*>(buf + r * 128 + chunk16 * 16 + (lane & 3) * 4);
+              cs4[r & 3] += *reinterpret_cast<const float*>(buf + r * 128 + chunk16 * 16 + (lane & 3) * 4);
             }
           } else {
-#pragma unroll 8
+#pragma unroll
             for (int r = 0; r < 32; ++r) {
               const int chunk16 = (lane >> 3) ^ ((r >> 1) & 3);
               const unsigned short h = *reinterpret_cast<const unsigned short*>(buf + r * 64 + chunk16 * 16 + (lane & 7) * 2);
-              cs += __uint_as_float(static_cast<uint32_t>(h) << 16);
+              cs4[r & 3] += __uint_as_float(static_cast<uint32_t>(h) << 16);
             }
           }
-          atomicAdd(&colsum_dst[ci * 32 + lane], cs);   // 4 quarters share a column
+          atomicAdd(&colsum_dst[ci * 32 + lane], (cs4[0] + cs4[1]) + (cs4[2] + cs4[3]));   // 4 quarters share a column
         }
+        __syncwarp();
       }
     }
     finish_bin();
-    if (lane == 0) tma_store_wait_all();
     if (warp == 2 && lane == 0) stamp(p.timing, 6);   // pass C done
     named_bar_sync(1, 32 * Cfg::EPI_WARPS);
 
@@ -494,7 +523,7 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     const int et = threadIdx.x - 64;   // 0..255
     if (p.colsum != nullptr && p.want_dz) {
       for (int c = et; c < BLOCK_N; c += 32 * Cfg::EPI_WARPS)
-        if (n0 + c < p.C) red_add_f32(p.colsum + n0 + c, s_colsum[c]);
+        if (n0 + c < p.C) p.colsum[static_cast<long long>(row_tile) * p.C + n0 + c] = s_colsum[c];
     }
     if (et < kMaxG) p.part[blockIdx.x * kMaxG + et] = (et < G) ? s_loss[et] : 0.f;
     __threadfence();

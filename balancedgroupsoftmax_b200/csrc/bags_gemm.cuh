@@ -11,10 +11,11 @@
 //   backward dX = dz W    : A = dz  [N_roi,C]  K-major , B = W   [C,K]      MN-major
 //   backward dW = dz^T X  : A = dz  [N_roi,C]  MN-major, B = X   [N_roi,K]  MN-major
 //
-// Pipeline (one CTA per SM, 192 threads):
+// Pipeline (one CTA per SM, 320 threads):
 //   warp 0      : TMA producer   (cp.async.bulk.tensor, 128B swizzle, mbarrier tx)
 //   warp 1      : UMMA issuer    (one thread; tcgen05.mma cta_group::1, M=128)
-//   warps 2..5  : epilogue       (tcgen05.ld 32x32b -> registers -> global)
+//   warps 2..9  : epilogue       (tcgen05.ld 32x32b -> registers -> swizzled smem transpose -> coalesced
+//                                 16-byte st.global / red.global)
 // smem ring of kStages {A tile, B tile}; TMEM holds kAccStages accumulators so
 // the epilogue of tile i overlaps the mainloop of tile i+1.
 #pragma once
@@ -42,9 +43,11 @@ struct GemmParams {
   int G;
   int gstart[kMaxGroups];
   int glen[kMaxGroups];
-  const float* colsum_in;  // optional [M]: db_out[m] = rowscale(m) * colsum_in[m]
+  const float* colsum_in;  // optional [colsum_tiles, M]: db_out[m] = rowscale(m) * sum_t colsum_in[t, m]
+  int colsum_tiles;
   float* colsum_out;       // written by the (n_tile==0, split==0) unit
   long long* timing;       // debug timeline [grid][8] (ns, %globaltimer) or nullptr
+  int dbg;                 // test hook: bit0 skip global stores, bit1 skip TMEM loads
 };
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool TF32, int STAGES>
@@ -68,14 +71,18 @@ struct GemmCfg {
   static constexpr int A_BOX_BYTES = A_BYTES / A_BOXES;
   static constexpr int B_BOXES = B_MN ? BLOCK_N / SLAB : N_MMA;
   static constexpr int B_BOX_BYTES = B_BYTES / B_BOXES;
-  // epilogue staging: per epilogue warp two 32-row x 128-byte swizzled buffers feeding TMA stores
+  // epilogue: 8 warps (two per TMEM lane quarter, each owning half of the tile's columns) so that every
+  // SM sub-partition has two warps to interleave -- a lone warp per scheduler is issue-latency bound.
+  // Each warp has one 32-row x 128-byte swizzled transpose buffer.
+  static constexpr int EPI_WARPS = 8;
   static constexpr int EPI_BUF_BYTES = 32 * 128;
-  static constexpr int EPI_STAGING_BYTES = 4 * 2 * EPI_BUF_BYTES;   // 32 KB
+  static constexpr int EPI_STAGING_BYTES = EPI_WARPS * EPI_BUF_BYTES;   // 32 KB
+  static constexpr int HALF_N = BLOCK_N / 2;
   static constexpr int EPI_COLS = (EPI == EPI_STORE_BF16) ? 64 : 32;  // output columns per 128-byte row
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
-  static_assert(BLOCK_N % EPI_COLS == 0, "tile width must be a multiple of the epilogue chunk");
-  static constexpr int NUM_THREADS = 192;
+  static_assert(HALF_N % EPI_COLS == 0, "half tile width must be a multiple of the epilogue chunk");
+  static constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
   static_assert(UMMA_N % 16 == 0 && UMMA_N >= 16 && UMMA_N <= 256, "invalid UMMA N");
   static_assert(!B_MN || (BLOCK_N % SLAB == 0 && N_MMA == 1), "MN-major B needs slab-aligned single MMA");
   static_assert((UMMA_N * 128) % 1024 == 0, "B half offset must keep 1024B swizzle alignment");
@@ -93,9 +100,9 @@ __device__ __forceinline__ float row_group_scale(const GemmParams& p, int m) {
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool TF32, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(64 + 32 * 8, 1)
 bags_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
+                 const GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N, A_MN, B_MN, EPI, TF32, STAGES>;
   constexpr int BLOCK_M = Cfg::BLOCK_M;
   constexpr int BLOCK_K = Cfg::BLOCK_K;
@@ -120,7 +127,6 @@ bags_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    tma_prefetch_desc(&tmap_out);
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -129,7 +135,7 @@ bags_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
     for (int a = 0; a < Cfg::ACC_STAGES; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], Cfg::EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -239,11 +245,14 @@ bags_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else {
     // ===================== epilogue warps =====================
     // TMEM -> registers (thread = accumulator row) -> bias / row scale / bf16 pack -> 128B-swizzled smem
-    // staging -> TMA tensor store (or TMA reduce-add for split-K).  The TMA unit writes full 128-byte
-    // rows and clips everything outside [M, N], so there are no per-element bounds checks.
+    // tile (conflict-free 16 B writes) -> read back transposed so that every warp-wide 16 B store /
+    // reduction covers 4 complete 128-byte output rows (fully coalesced).
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    uint8_t* my_bufs = smem_epi + quarter * 2 * Cfg::EPI_BUF_BYTES;
-    uint32_t chunk_ctr = 0;
+    const int half = (warp - 2) >> 2;   // which half of the tile's columns
+    uint8_t* buf = smem_epi + (warp - 2) * Cfg::EPI_BUF_BYTES;
+    constexpr int OUT_ELT = (EPI == EPI_STORE_BF16) ? 2 : 4;
+    constexpr int VEC = 16 / OUT_ELT;  // output elements per 16-byte vector
+    const bool vec_ok = ((p.ldo * OUT_ELT) % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
     int local = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++local) {
       const int split = u / units_per_split;
@@ -258,8 +267,11 @@ bags_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       float scale = 1.0f;
       if (EPI == EPI_RED_F32) {
         scale = (m < p.M) ? row_group_scale(p, m) : 0.0f;
-        if (p.colsum_out != nullptr && n_tile == 0 && split == 0 && m < p.M)
-          p.colsum_out[m] = scale * __ldg(p.colsum_in + m);
+        if (p.colsum_out != nullptr && n_tile == 0 && split == 0 && half == 0 && m < p.M) {
+          float cs = 0.f;
+          for (int tt = 0; tt < p.colsum_tiles; ++tt) cs += __ldg(p.colsum_in + static_cast<long long>(tt) * p.M + m);
+          p.colsum_out[m] = scale * cs;
+        }
       }
 
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -267,19 +279,19 @@ bags_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (local == 0 && warp == 2 && lane == 0) stamp(p.timing, 4);   // first accumulator complete
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += Cfg::EPI_COLS) {
+      for (int c = half * Cfg::HALF_N; c < (half + 1) * Cfg::HALF_N; c += Cfg::EPI_COLS) {
         const int n = n0 + c;
         if (n >= p.N) break;  // warp-uniform: nothing of this chunk is inside the output
-        uint8_t* buf = my_bufs + (chunk_ctr & 1u) * Cfg::EPI_BUF_BYTES;
-        ++chunk_ctr;
         uint32_t v[32];
-        tmem_ld_32x32b_x32(t_row + c, v);
         uint32_t v2[32];
-        if (EPI == EPI_STORE_BF16) tmem_ld_32x32b_x32(t_row + c + 32, v2);
-        tmem_ld_wait();
-        // the TMA store that last read this buffer (two chunks ago) must have drained it
-        if (lane == 0) tma_store_wait_read<1>();
-        __syncwarp();
+        if (!(p.dbg & 2)) {
+          tmem_ld_32x32b_x32(t_row + c, v);
+          if (EPI == EPI_STORE_BF16) tmem_ld_32x32b_x32(t_row + c + 32, v2);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { v[j] = c + j; v2[j] = lane + j; }
+        }
         uint4* rowp = reinterpret_cast<uint4*>(buf + lane * 128);
         if (EPI == EPI_STORE_BF16) {
 #pragma unroll
@@ -313,19 +325,47 @@ bags_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             rowp[j ^ (lane & 7)] = *reinterpret_cast<uint4*>(&r);
           }
         }
-        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
         __syncwarp();
-        if (lane == 0) {
-          if (EPI == EPI_RED_F32) tma_reduce_add_2d(&tmap_out, buf, n, m_warp);
-          else                    tma_store_2d(&tmap_out, buf, n, m_warp);
-          tma_store_commit();
+        // read back: iteration it covers tile rows 4*it .. 4*it+3, lane -> (row, 16-byte chunk)
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + (lane >> 3);
+          const int ch = lane & 7;
+          const uint4 val = *reinterpret_cast<const uint4*>(buf + r * 128 + ((ch ^ (r & 7)) << 4));
+          const int gm = m_warp + r;
+          const int gn = n + ch * VEC;
+          if (gm < p.M && gn < p.N && !(p.dbg & 1)) {
+            uint8_t* gp = reinterpret_cast<uint8_t*>(p.out) + (static_cast<long long>(gm) * p.ldo + gn) * OUT_ELT;
+            if (vec_ok && gn + VEC <= p.N) {
+              if (EPI == EPI_RED_F32)
+                red_add_v4_f32(reinterpret_cast<float*>(gp), __uint_as_float(val.x), __uint_as_float(val.y),
+                               __uint_as_float(val.z), __uint_as_float(val.w));
+              else
+                *reinterpret_cast<uint4*>(gp) = val;
+            } else {
+              const uint32_t w4[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+              for (int e = 0; e < VEC; ++e) {
+                if (gn + e < p.N) {
+                  if (EPI == EPI_STORE_BF16) {
+                    const uint32_t word = w4[e >> 1];
+                    reinterpret_cast<unsigned short*>(gp)[e] = static_cast<unsigned short>((e & 1) ? (word >> 16) : (word & 0xffffu));
+                  } else if (EPI == EPI_RED_F32) {
+                    red_add_f32(reinterpret_cast<float*>(gp) + e, __uint_as_float(w4[e]));
+                  } else {
+                    reinterpret_cast<float*>(gp)[e] = __uint_as_float(w4[e]);
+                  }
+                }
+              }
+            }
+          }
         }
+        __syncwarp();   // buffer is rewritten by the next chunk
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
-    if (lane == 0) tma_store_wait_all();  // smem must outlive the last bulk reads
     if (warp == 2 && lane == 0) stamp(p.timing, 5);   // epilogue done
   }
 

@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(1024)
 sample_others_kernel(const long long* __restrict__ labels, const int* __restrict__ l2b, int classes,
                      int G, int N, double ratio, unsigned long long seed,
                      uint8_t* __restrict__ wmask, float* __restrict__ avg) {
+  pdl_trigger();   // the fused forward's GEMM mainloop does not depend on the masks: let it start now
   const int g = blockIdx.x;
   const int tid = threadIdx.x;
   __shared__ int s_hist[256];
@@ -432,6 +433,7 @@ sample_others_kernel(const long long* __restrict__ labels, const int* __restrict
 // avg_g = max(sum_n w_g[n], 1) for caller-provided masks (parity mode)
 __global__ void __launch_bounds__(256)
 mask_avg_kernel(const uint8_t* __restrict__ wmask, int N, float* __restrict__ avg) {
+  pdl_trigger();
   const int g = blockIdx.x;
   __shared__ int s_w[8];
   int c = 0;

@@ -31,6 +31,12 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor is still running; pdl_wait() blocks until the predecessor grid has completed and
+// its writes are visible.  pdl_trigger() in the predecessor lets dependents start launching early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ long long global_timer_ns() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

@@ -147,7 +147,7 @@ class FcClsFunction(torch.autograd.Function):
         ldd = ops.pad_cols(Cc)
         dz = torch.zeros((N, ldd), dtype=xc.dtype, device=xc.device)
         dz[:, :Cc] = grad_out
-        colsum = grad_out.float().sum(0)
+        colsum = grad_out.float().sum(0, keepdim=True)
         head_dt = ops.DeviceTables(1, 1, Cc, torch.zeros(1, 1, dtype=torch.int32, device=xc.device),
                                    torch.zeros(1, dtype=torch.int32, device=xc.device),
                                    ops.nat.int32_array([0, Cc]), np.array([[0, Cc]], dtype=np.int64))

@@ -152,7 +152,7 @@ def mask_avg(wmask: torch.Tensor) -> torch.Tensor:
 def group_ce(logits: torch.Tensor, labels: torch.Tensor, dt: DeviceTables,
              wmask: Optional[torch.Tensor], avg: Optional[torch.Tensor], want_dz: bool = True,
              dz_dtype: torch.dtype = torch.bfloat16, want_lse: bool = False):
-    """(loss[G], lse[N,G] | None, dz[N, ldd] | None, colsum[C] | None)   (a5-a7 + grad-in-forward)."""
+    """(loss[G], lse[N,G] | None, dz[N, ldd] | None, colsum[1,C] | None)   (a5-a7 + grad-in-forward)."""
     _require_cuda(logits, labels, wmask, avg)
     assert logits.dtype == torch.float32 and logits.dim() == 2 and logits.stride(1) == 1
     labels = labels.contiguous()
@@ -165,7 +165,7 @@ def group_ce(logits: torch.Tensor, labels: torch.Tensor, dt: DeviceTables,
     if want_dz:
         ldd = pad_cols(Cc)
         dz = torch.empty((N, ldd), dtype=dz_dtype, device=dev)
-        colsum = torch.empty((Cc,), dtype=torch.float32, device=dev)
+        colsum = torch.empty((1, Cc), dtype=torch.float32, device=dev)
     ws = _workspace(dev)
     nat.check(nat.lib().bags_group_ce(
         logits.data_ptr(), logits.stride(0), labels.data_ptr(), dt.label2bin.data_ptr(), dt.slices_host,
@@ -207,13 +207,14 @@ def fused_fwd(x, w, bias, labels, dt: DeviceTables, wmask, avg, logits: Optional
     if want_dz:
         ldd = pad_cols(Cc)
         dz = torch.empty((N, ldd), dtype=x.dtype, device=dev)
-        colsum = torch.empty((Cc,), dtype=torch.float32, device=dev)
+        colsum = torch.empty((max((N + 127) // 128, 1), Cc), dtype=torch.float32, device=dev)   # per-row-tile partials
     ws = _workspace(dev)
     nat.check(nat.lib().bags_fwd(
         x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), nat.ptr(bias), labels.data_ptr(),
         dt.label2bin.data_ptr(), dt.slices_host, nat.ptr(wmask), nat.ptr(avg), N, K, Cc, dt.G, dt.num_classes,
         _dtype_code(x.dtype), nat.ptr(logits), logits.stride(0) if logits is not None else 0, loss.data_ptr(),
-        nat.ptr(lse), nat.ptr(dz), ldd, nat.ptr(colsum), ws.data_ptr(), ws.numel(), _stream_ptr(dev)), 'bags_fwd')
+        nat.ptr(lse), nat.ptr(dz), ldd, nat.ptr(colsum), colsum.shape[0] if colsum is not None else 0, ws.data_ptr(),
+        ws.numel(), _stream_ptr(dev)), 'bags_fwd')
     return loss, logits, lse, dz, colsum
 
 
@@ -241,7 +242,8 @@ def fused_bwd(dz, x, w, gout, dt: DeviceTables, colsum, need_dw=True, need_db=Tr
         assert gout.dtype == torch.float32 and gout.numel() == dt.G
     nat.check(nat.lib().bags_bwd(
         dz.data_ptr(), dz.stride(0), x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), nat.ptr(gout),
-        dt.slices_host, nat.ptr(colsum), nat.ptr(dW) if need_dw else None, dW.stride(0) if need_dw else 0,
+        dt.slices_host, nat.ptr(colsum), (colsum.shape[0] if colsum.dim() == 2 else 1) if colsum is not None else 0,
+        nat.ptr(dW) if need_dw else None, dW.stride(0) if need_dw else 0,
         nat.ptr(db), nat.ptr(dX) if need_dx else None, dX.stride(0) if need_dx else 0,
         nat.ptr(wscratch) if (need_dx and gout is not None) else None, N, K, Cc, dt.G, _dtype_code(x.dtype),
         _stream_ptr(dev)), 'bags_bwd')

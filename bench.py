@@ -250,7 +250,7 @@ def run_ours(args):
         seed_ctr[0] += 1
         wmask, avg = ops.sample_others(s['labels'], dt, RATIO, seed_ctr[0])
         loss, _, _, dz, colsum = ops.fused_fwd(s['x'], s['w'], s['bias'], s['labels'], dt, wmask, avg,
-                                               logits=s['logits'])
+                                               logits=(s['logits'] if args.unfused else None))
         ops.fused_bwd(dz, s['x'], s['w'], gout, dt, colsum, dW=s['dW'], dX=s['dX'], wscratch=s['wscratch'],
                       db=s['db'])
         if world > 1:
@@ -258,7 +258,8 @@ def run_ours(args):
         last['loss'] = loss
         return loss
 
-    kernels_per_step = 6  # sampler, fwd GEMM, grouped CE, W row-scale, dW GEMM, dX GEMM (+2 memset nodes)
+    # sampler, fused fwd (or GEMM + grouped CE), W row-scale, dW GEMM, dX GEMM (+2 memset nodes)
+    kernels_per_step = 6 if args.unfused else 5
 
     stream = torch.cuda.Stream(device=dev)
     use_graph = not args.no_graph
@@ -332,26 +333,57 @@ def run_ours(args):
         loss_host = torch.empty(dt.G, dtype=torch.float32).pin_memory()
         e2e_steps = max(10, min(args.steps, 200))
 
-        def e2e_step():
-            xd = x_host.to(dev, non_blocking=True).requires_grad_(True)
-            ld = lab_host.to(dev, non_blocking=True)
+        # double-buffered pipeline: the H2D copy of step i+1 (copy stream) overlaps the compute of step i; every
+        # step still pays its own H2D of features+labels and its own D2H read of the five losses
+        copy_stream = torch.cuda.Stream(device=dev)
+        comp_stream = torch.cuda.current_stream(dev)
+        xd = [torch.empty(n, K_FEAT, device=dev, dtype=dtype) for _ in range(2)]
+        ld = [torch.empty(n, device=dev, dtype=torch.int64) for _ in range(2)]
+        loss_hosts = [torch.empty(dt.G, dtype=torch.float32).pin_memory() for _ in range(2)]
+        ev_copied = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+        ev_loss = [torch.cuda.Event() for _ in range(2)]
+
+        def stage(i):
+            b_ = i & 1
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_free[b_])
+                xd[b_].copy_(x_host, non_blocking=True)
+                ld[b_].copy_(lab_host, non_blocking=True)
+                ev_copied[b_].record(copy_stream)
+
+        def compute(i):
+            b_ = i & 1
+            comp_stream.wait_event(ev_copied[b_])
+            xin = xd[b_].detach().requires_grad_(True)
             w_param.grad = None
             b_param.grad = None
-            losses = bags_head_loss(xd, w_param, b_param, ld, dt, RATIO, compute_dtype=dtype)
+            losses = bags_head_loss(xin, w_param, b_param, ld[b_], dt, RATIO, compute_dtype=dtype)
             losses.sum().backward()
             if world > 1:
                 dist.all_reduce(w_param.grad, op=dist.ReduceOp.AVG)
-            loss_host.copy_(losses.detach(), non_blocking=True)
-            torch.cuda.current_stream().synchronize()   # the step's result is on the host
+            ev_free[b_].record(comp_stream)
+            loss_hosts[b_].copy_(losses.detach(), non_blocking=True)
+            ev_loss[b_].record(comp_stream)
 
-        for _ in range(3):
-            e2e_step()
+        def run_e2e(k):
+            for b_ in range(2):
+                ev_free[b_].record(comp_stream)
+            stage(0)
+            for i in range(k):
+                if i + 1 < k:
+                    stage(i + 1)
+                compute(i)
+                if i >= 1:
+                    ev_loss[(i - 1) & 1].synchronize()   # the previous step's losses are on the host
+            ev_loss[(k - 1) & 1].synchronize()
+
+        run_e2e(6)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
+        run_e2e(e2e_steps)
         torch.cuda.synchronize()
         e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
         if world > 1:
@@ -360,7 +392,8 @@ def run_ours(args):
             e2e_ms = float(t.item())
         e2e = {'value': world * n / (e2e_ms * 1e-3), 'unit': 'RoIs/s',
                'h2d_bytes_per_step': int(x_host.numel() * x_host.element_size() + lab_host.numel() * 8),
-               'd2h_bytes_per_step': int(loss_host.numel() * 4), 'ms_per_step': e2e_ms, 'steps': e2e_steps}
+               'd2h_bytes_per_step': int(loss_host.numel() * 4), 'ms_per_step': e2e_ms, 'steps': e2e_steps,
+               'pipeline': 'H2D of step i+1 overlaps compute of step i (2 buffers); losses read back every step'}
     except Exception as ex:  # pragma: no cover
         log('e2e arm failed: %r' % (ex,))
 
@@ -390,7 +423,7 @@ def run_ours(args):
         with torch.cuda.stream(stream):
             wmask, avg = ops.sample_others(sets[0]['labels'], dt, RATIO, 1)
             _, _, _, dz0, colsum0 = ops.fused_fwd(sets[0]['x'], sets[0]['w'], sets[0]['bias'], sets[0]['labels'], dt,
-                                                  wmask, avg, logits=sets[0]['logits'])
+                                                  wmask, avg)
             dzs = [torch.empty_like(dz0).copy_(dz0) for _ in sets]
             stream.synchronize()
 
@@ -416,9 +449,13 @@ def run_ours(args):
 
         idx = {id(s): i for i, s in enumerate(sets)}
         try:
-            kernel_us['fc_cls_gemm'] = graphed(lambda s: ops.linear_fwd(s['x'], s['w'], s['bias'], out=s['logits']))
-            kernel_us['group_ce'] = graphed(lambda s: ops.group_ce(s['logits'], s['labels'], dt, wmask, avg,
-                                                                   dz_dtype=dtype))
+            if args.unfused:
+                kernel_us['fc_cls_gemm'] = graphed(lambda s: ops.linear_fwd(s['x'], s['w'], s['bias'], out=s['logits']))
+                kernel_us['group_ce'] = graphed(lambda s: ops.group_ce(s['logits'], s['labels'], dt, wmask, avg,
+                                                                       dz_dtype=dtype))
+            else:
+                kernel_us['fused_fwd'] = graphed(lambda s: ops.fused_fwd(s['x'], s['w'], s['bias'], s['labels'], dt,
+                                                                         wmask, avg))
             kernel_us['dW_gemm'] = graphed(lambda s: ops.fused_bwd(dzs[idx[id(s)]], s['x'], s['w'], gout, dt, colsum0,
                                                                    need_dx=False, dW=s['dW']))
             kernel_us['dX_gemm'] = graphed(lambda s: ops.fused_bwd(dzs[idx[id(s)]], s['x'], s['w'], None, dt, colsum0,
@@ -426,7 +463,8 @@ def run_ours(args):
             kernel_us['sample_others'] = graphed(lambda s: ops.sample_others(s['labels'], dt, RATIO, 7))
         except Exception as ex:  # pragma: no cover
             log('per-kernel timing failed: %r' % (ex,))
-        flops = {'fc_cls_gemm': 2.0 * n * K_FEAT * C, 'dW_gemm': 2.0 * n * K_FEAT * C, 'dX_gemm': 2.0 * n * K_FEAT * C}
+        flops = {'fc_cls_gemm': 2.0 * n * K_FEAT * C, 'fused_fwd': 2.0 * n * K_FEAT * C, 'dW_gemm': 2.0 * n * K_FEAT * C,
+                 'dX_gemm': 2.0 * n * K_FEAT * C}
         bytes_ce = n * C * 4 + n * C * elt + n * 8 + dt.G * n   # read fp32 logits, write dz, labels, masks
         if kernel_us:
             dom = max(kernel_us, key=lambda k_: kernel_us[k_])
@@ -456,7 +494,8 @@ def run_ours(args):
             'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
             'config': {
                 'workload': 'BASELINE.json configs[1]: fused BAGS fwd+bwd, %d RoIs/GPU x %d feat x %d cls (%d logits), '
-                            '5 bins, %s operands, dW+db+dX, device sampler' % (n, K_FEAT, NUM_CLASSES, C, args.dtype),
+                            '5 bins, %s operands, dW+db+dX, device sampler, %s forward' % (n, K_FEAT, NUM_CLASSES, C, args.dtype,
+                                                                                    'unfused' if args.unfused else 'fused'),
                 'rois_per_gpu': n, 'parallelism': 'dp%d' % world,
                 'l2': 'rotating pool of %d buffer sets (%.0f MB > 126 MB L2); no step re-reads cached inputs'
                       % (pool, pool * per_set / 1e6),
@@ -490,6 +529,7 @@ def main():
     ap.add_argument('--rois', type=int, default=N_ROIS)
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--unfused', action='store_true', help='GEMM -> fp32 logits -> grouped CE instead of the fused kernel')
     ap.add_argument('--profile', action='store_true', help='timed loop only (for ncu): skip e2e / cpu / per-kernel legs')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -100,22 +100,28 @@ int bags_fused_eligible(const int32_t* slices_host, int G, int C);
 /* fc_cls + grouped softmax-CE (+ dz, colsum) in one call.
  *   logits == NULL : fused kernel -- the logits stay in tensor memory and never reach HBM
  *                    (requires bags_fused_eligible); ldz is ignored.
- *   logits != NULL : bags_linear_fwd into `logits` followed by bags_group_ce (same arguments). */
+ *   logits != NULL : bags_linear_fwd into `logits` followed by bags_group_ce (same arguments).
+ * colsum (optional) is [colsum_tiles, C] with colsum_tiles = ceil(N/128): per-128-row-tile partial column sums
+ * of dz (written with plain stores, no pre-zeroing needed); their sum over tiles is sum_n dz[n, :].
+ * The fused kernel is launched with programmatic dependent launch: when the preceding kernel in the stream is
+ * bags_sample_others / bags_mask_avg, its GEMM mainloop overlaps them and only the epilogue waits. */
 int bags_fwd(const void* x, long long ldx, const void* w, long long ldw, const float* bias,
              const int64_t* labels, const int32_t* label2bin, const int32_t* slices_host,
              const uint8_t* wmask, const float* avg, int N, int K, int C, int G, int classes,
              int dtype, float* logits, long long ldz, float* loss, float* lse, void* dz,
-             long long ldd, float* colsum, void* workspace, size_t workspace_bytes, void* stream);
+             long long ldd, float* colsum, int colsum_tiles, void* workspace, size_t workspace_bytes,
+             void* stream);
 
-/* Backward of bags_fwd given dz (and colsum) saved by the forward and gout[G] = dL/dloss_g (NULL => 1):
+/* Backward of bags_fwd given dz (and colsum[colsum_tiles, C]) saved by the forward and gout[G] = dL/dloss_g
+ * (NULL => 1):
  *   dW[C,K]  = (gout ⊙ dz)^T x      fp32, overwritten         (NULL to skip)
- *   db[C]    = gout ⊙ colsum         fp32                      (NULL to skip)
+ *   db[C]    = gout ⊙ sum_t colsum   fp32                      (NULL to skip)
  *   dX[N,K]  = (gout ⊙ dz) w         dtype elements            (NULL to skip)
  * wscratch: [C, ldw] dtype elements, required when dX != NULL and gout != NULL. */
 int bags_bwd(const void* dz, long long ldd, const void* x, long long ldx, const void* w,
              long long ldw, const float* gout, const int32_t* slices_host, const float* colsum,
-             float* dW, long long lddw, float* db, void* dX, long long lddx, void* wscratch, int N,
-             int K, int C, int G, int dtype, void* stream);
+             int colsum_tiles, float* dW, long long lddw, float* db, void* dX, long long lddx,
+             void* wscratch, int N, int K, int C, int G, int dtype, void* stream);
 
 /* scores[N,classes]: scores[:,0] = softmax(z[:,slice_0])[:,0];
  * scores[:,c] = softmax(z[:,slice_0])[:,1] * softmax(z[:,slice_g])[:,j] where cls2col[c] = start_g + j.

@@ -103,7 +103,7 @@ def case_group_ce(name):
             lr = max(abs(loss[g].item() - ref['loss_cls_bin%d' % g].item()) /
                      max(abs(ref['loss_cls_bin%d' % g].item()), 1e-3) for g in range(dt.G))
             dr = rel(dz[:, :t.num_logits].float().cpu(), dz_ref)
-            cr = rel(colsum.cpu(), db_ref)
+            cr = rel(colsum.sum(0).cpu(), db_ref)
             out['N%d.%s' % (N, str(dzt)[6:])] = dict(loss=lr, dz=dr, colsum=cr)
             assert lr < 1e-5, lr
             assert dr < (1e-5 if dzt == torch.float32 else 4e-3), dr
@@ -221,13 +221,13 @@ def case_fusedk(name):
                  for g in range(dt.G))
         lse_ref = torch.stack([torch.logsumexp(z[:, int(ps[g, 0]):int(ps[g, 0]) + int(ps[g, 1])], 1) for g in range(5)], 1)
         res = dict(loss=lr, lse=rel(lse.cpu(), lse_ref), dz=rel(dz[:, :t.num_logits].float().cpu(), dz_ref),
-                   colsum=rel(colsum.cpu(), db_ref) if db_ref.norm() > 0 else 0.0)
+                   colsum=rel(colsum.sum(0).cpu(), db_ref) if db_ref.norm() > 0 else 0.0)
         dW, db, dX = ops.fused_bwd(dz, xc, wc, None, dt, colsum)
         torch.cuda.synchronize()
         res['dW'] = rel(dW.cpu(), dW_ref)
         out['N%d' % N] = res
         tol = dict(loss=1e-4, lse=1e-5, dz=4e-3, colsum=2e-3, dW=3e-3) if cdt == torch.bfloat16 else \
-            dict(loss=1e-3, lse=1e-3, dz=2e-3, colsum=1e-3, dW=1e-3)
+            dict(loss=1e-3, lse=1e-3, dz=2e-3, colsum=1e-3, dW=1e-3 if N >= 64 else 2e-3)
         for k_, v in res.items():
             assert v < tol[k_], (N, k_, v, tol[k_])
     return out
@@ -269,6 +269,12 @@ def case_timeline(name):
         d['cta_life_us(mean,max)'] = [round(float(((tb[:, 6] - tb[:, 0]) / 1e3).mean()), 2),
                                       round(float(((tb[:, 6] - tb[:, 0]) / 1e3).max()), 2)]
         d['distinct_sms'] = int(tb[:, 7].unique().numel())
+        if 'fused' in label:   # per cluster-rank means of pass A / barrier / pass C
+            for r in range(4):
+                sub = tb[r::4]
+                d['rank%d(passA,bar,passC)' % r] = [round(float(((sub[:, 4] - sub[:, 3]) / 1e3).mean()), 2),
+                                                    round(float(((sub[:, 5] - sub[:, 4]) / 1e3).mean()), 2),
+                                                    round(float(((sub[:, 6] - sub[:, 5]) / 1e3).mean()), 2)]
         res[label] = d
 
     run('gemm_fwd_320 (s3=mma issued, s4=acc done, s5=epi done)',

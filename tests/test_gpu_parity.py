@@ -149,7 +149,8 @@ def test_fused_fwd_bwd_vs_oracle(env, N, mode, materialize):
 
 def test_bf16_matches_oracle_on_rounded_operands_tightly(env):
     """With the oracle fed the same bf16-rounded x/W the only differences left are accumulation
-    order and the bf16 rounding of dz: loss <= 1e-5, dW <= 2e-3 (documented in DESIGN.md)."""
+    order and the bf16 rounding of dz: loss <= 1e-5, dW <= 2e-3; db <= 2e-3 on the fused route (its
+    column sums are taken from the bf16-rounded dz tile) and <= 1e-5 on the materialised route."""
     ops, t, dt, l2b, ps = env
     x, W, b, labels, remapped = _problem(768, seed=5)
     xo, Wo = x.bfloat16().float(), W.bfloat16().float()
@@ -157,12 +158,14 @@ def test_bf16_matches_oracle_on_rounded_operands_tightly(env):
     _, dW_ref, db_ref, dX_ref = O.closed_form_grads(xo, Wo, b, labels, l2b, ps, remapped)
     wmask = torch.stack([w.to(torch.uint8) for w in remapped[1]]).cuda()
     avg = ops.mask_avg(wmask)
-    loss, _, _, dz, colsum = ops.fused_fwd(x.cuda().bfloat16(), W.cuda().bfloat16(), b.cuda(), labels.cuda(), dt, wmask, avg)
-    dW, db, dX = ops.fused_bwd(dz, x.cuda().bfloat16(), W.cuda().bfloat16(), None, dt, colsum)
-    for g in range(5):
-        r = ref['loss_cls_bin%d' % g].item()
-        assert abs(loss[g].item() - r) <= 1e-5 * max(abs(r), 1.0)
-    assert rel(dW, dW_ref) <= 2e-3 and rel(db, db_ref) <= 1e-5 and rel(dX.float(), dX_ref) <= 4e-3
+    for materialize, db_tol in ((False, 2e-3), (True, 1e-5)):
+        loss, _, _, dz, colsum = ops.fused_fwd(x.cuda().bfloat16(), W.cuda().bfloat16(), b.cuda(), labels.cuda(), dt,
+                                               wmask, avg, materialize=materialize)
+        dW, db, dX = ops.fused_bwd(dz, x.cuda().bfloat16(), W.cuda().bfloat16(), None, dt, colsum)
+        for g in range(5):
+            r = ref['loss_cls_bin%d' % g].item()
+            assert abs(loss[g].item() - r) <= 1e-5 * max(abs(r), 1.0)
+        assert rel(dW, dW_ref) <= 2e-3 and rel(db, db_ref) <= db_tol and rel(dX.float(), dX_ref) <= 4e-3
 
 
 def test_group_assignment_is_bit_exact(env):
@@ -272,7 +275,7 @@ def test_full_size_properties_4096(env):
     assert none_logits is None
     assert rel(loss_f, loss) < 1e-5 and rel(lse_f, lse) < 1e-6
     assert rel(dz_f[:, :t.num_logits].float(), dz[:, :t.num_logits].float()) < 4e-3
-    assert rel(colsum_f, colsum) < 2e-3
+    assert rel(colsum_f.sum(0), colsum.sum(0)) < 2e-3 and colsum_f.shape[0] == 32
     assert (loss >= 0).all()
     dzf = dz[:, :t.num_logits].float()
     for g in range(5):
@@ -280,7 +283,7 @@ def test_full_size_properties_4096(env):
         assert dzf[:, s:s + l].sum(1).abs().max().item() < 2e-5       # bf16 rounding of ~1e-4-sized terms
         # lse really is logsumexp of the slice
         assert torch.allclose(lse[:, g], torch.logsumexp(logits[:, s:s + l], dim=1), rtol=1e-5, atol=1e-5)
-    assert rel(colsum, dzf.sum(0)) < 2e-3
+    assert rel(colsum.sum(0), dzf.sum(0)) < 2e-3
     g1 = torch.tensor([1.0, 0.0, 2.0, 0.0, 0.5], device='cuda')
     g2 = torch.tensor([0.0, 3.0, 0.0, 1.0, 0.25], device='cuda')
     r1 = ops.fused_bwd(dz, xc, wc, g1, dt, colsum)
