@@ -146,6 +146,11 @@ static int make_group_table(GroupTable& gt, const int32_t* slices_host, int G, i
   return BAGS_OK;
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
 // ----------------------------------------------------------------------------
 // GEMM launcher
 // ----------------------------------------------------------------------------
@@ -159,7 +164,7 @@ struct GemmArgs {
 };
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool TF32, int STAGES>
-static int launch_gemm(const GemmArgs& ga, const DeviceInfo& di, cudaStream_t stream) {
+static int launch_gemm(const GemmArgs& ga, const DeviceInfo& di, cudaStream_t stream, bool pdl = false) {
   using Cfg = GemmCfg<BLOCK_N, A_MN, B_MN, EPI, TF32, STAGES>;
   auto kernel = bags_gemm_kernel<BLOCK_N, A_MN, B_MN, EPI, TF32, STAGES>;
   CUtensorMap ta, tb;
@@ -188,9 +193,23 @@ static int launch_gemm(const GemmArgs& ga, const DeviceInfo& di, cudaStream_t st
   const int grid = units < di.num_sms ? units : di.num_sms;
 
   BAGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  kernel<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
-  BAGS_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(Cfg::NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && env_int("BAGS_PDL", 1)) ? 1 : 0;
+  BAGS_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tb, p));
   return BAGS_OK;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool TF32, int STAGES>
+static int launch_gemm_pdl(const GemmArgs& ga, const DeviceInfo& di, cudaStream_t stream) {
+  return launch_gemm<BLOCK_N, A_MN, B_MN, EPI, TF32, STAGES>(ga, di, stream, true);
 }
 
 static int pick_splits(int tiles, int kblocks, int num_sms) {
@@ -198,11 +217,6 @@ static int pick_splits(int tiles, int kblocks, int num_sms) {
   if (s < 1) s = 1;
   if (s > kblocks) s = kblocks;
   return s;
-}
-
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return (v && *v) ? atoi(v) : dflt;
 }
 
 // forward tile width: fewest (waves x tile width)
@@ -468,37 +482,6 @@ extern "C" int bags_fwd(const void* x, long long ldx, const void* w, long long l
                                   : launch_fused_fwd<true>(x, ldx, w, ldw, p, dz, ldd, di, stream);
 }
 
-// dst[r, :] = src[r, :] * gout[bin(r)]   (rows = logit columns); 16-byte vectors, one CTA per row
-template <typename T>
-__global__ void __launch_bounds__(128)
-scale_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, long long ld, int rows, int cols,
-                  const GroupTable gt, const float* __restrict__ gout) {
-  constexpr int V = 16 / sizeof(T);
-  const int r = blockIdx.x;
-  float s = 0.f;
-#pragma unroll
-  for (int g = 0; g < kMaxG; ++g)
-    if (g < gt.G && r >= gt.start[g] && r < gt.start[g] + gt.len[g]) s = __ldg(gout + g);
-  for (int c = threadIdx.x * V; c < cols; c += 128 * V) {
-    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src + (long long)r * ld + c));
-    uint4 out;
-    if (sizeof(T) == 2) {
-      const uint32_t in[4] = {raw.x, raw.y, raw.z, raw.w};
-      uint32_t o[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float lo = __uint_as_float(in[q] << 16), hi = __uint_as_float(in[q] & 0xffff0000u);
-        o[q] = pack_bf16x2(lo * s, hi * s);
-      }
-      out = make_uint4(o[0], o[1], o[2], o[3]);
-    } else {
-      out = make_uint4(__float_as_uint(__uint_as_float(raw.x) * s), __float_as_uint(__uint_as_float(raw.y) * s),
-                       __float_as_uint(__uint_as_float(raw.z) * s), __float_as_uint(__uint_as_float(raw.w) * s));
-    }
-    *reinterpret_cast<uint4*>(dst + (long long)r * ld + c) = out;
-  }
-}
-
 __global__ void __launch_bounds__(256)
 scale_colsum_kernel(const float* __restrict__ colsum, int tiles, float* __restrict__ db, int C, GroupTable gt,
                     const float* __restrict__ gout) {
@@ -513,11 +496,19 @@ scale_colsum_kernel(const float* __restrict__ colsum, int tiles, float* __restri
   db[c] = s * cs;
 }
 
+static constexpr int kColsumTiles = 8;   // row groups of the bias-gradient partial sums made by bwd_prep
+
+extern "C" size_t bags_bwd_scratch_bytes(int C, long long ldw, int dtype) {
+  const size_t elt = (dtype == BAGS_DTYPE_BF16) ? 2 : 4;
+  const size_t wbytes = (static_cast<size_t>(C) * static_cast<size_t>(ldw) * elt + 255) & ~static_cast<size_t>(255);
+  return wbytes + static_cast<size_t>(kColsumTiles) * C * sizeof(float);
+}
+
 extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long ldx, const void* w,
                         long long ldw, const float* gout, const int32_t* slices_host,
                         const float* colsum, int colsum_tiles, float* dW, long long lddw, float* db, void* dX,
-                        long long lddx, void* wscratch, int N, int K, int C, int G, int dtype,
-                        void* stream_) {
+                        long long lddx, void* wscratch, size_t wscratch_bytes, int N, int K, int C, int G,
+                        int dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BAGS_REQUIRE(dz != nullptr || N == 0, "bags_bwd: dz is NULL");
   BAGS_REQUIRE(dtype == BAGS_DTYPE_F32 || dtype == BAGS_DTYPE_BF16, "bags_bwd: bad dtype %d", dtype);
@@ -526,68 +517,89 @@ extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long 
   if (int rc = make_group_table(gt, slices_host, G, C)) return rc;
   DeviceInfo di;
   if (int rc = device_info(di)) return rc;
-  if (db != nullptr) BAGS_REQUIRE(colsum != nullptr && colsum_tiles >= 1, "bags_bwd: db requested but colsum is NULL");
+  const bool bf = dtype == BAGS_DTYPE_BF16;
+  const int vecw = bf ? 8 : 4;
 
-  if (dW != nullptr) {
-    BAGS_REQUIRE(x != nullptr || N == 0, "bags_bwd: x is NULL but dW requested");
-    BAGS_REQUIRE(lddw >= K && (lddw % 4) == 0 && (reinterpret_cast<uintptr_t>(dW) & 15) == 0,
-                 "bags_bwd: dW must be 16-byte aligned with lddw %% 4 == 0");
-    BAGS_CUDA(cudaMemset2DAsync(dW, lddw * sizeof(float), 0, K * sizeof(float), C, stream));
-    if (N > 0) {
-      GemmArgs ga{};
-      ga.a = dz; ga.lda = ldd; ga.a_mn = true;   // A = dz^T : [C, N_roi], stored [N_roi, C]
-      ga.b = x;  ga.ldb = ldx; ga.b_mn = true;   // B = x^T  : [K, N_roi], stored [N_roi, K]
-      ga.M = C; ga.N = K; ga.K = N; ga.dtype = dtype;
-      const int tiles = ((C + 127) / 128) * ((K + 255) / 256);
-      const int kblocks = (N + (dtype == BAGS_DTYPE_BF16 ? 63 : 31)) / (dtype == BAGS_DTYPE_BF16 ? 64 : 32);
-      ga.splits = env_int("BAGS_DW_SPLITS", pick_splits(tiles, kblocks, di.num_sms));
-      ga.p.out = dW; ga.p.ldo = lddw; ga.p.bias = nullptr;
-      ga.p.gscale = gout; ga.p.G = gt.G;
-      for (int g = 0; g < kMaxGroups; ++g) { ga.p.gstart[g] = gt.start[g]; ga.p.glen[g] = gt.len[g]; }
-      if (gout == nullptr) { ga.p.G = 0; }
-      ga.p.colsum_in = (db != nullptr) ? colsum : nullptr;
-      ga.p.colsum_tiles = colsum_tiles;
-      ga.p.colsum_out = (db != nullptr && colsum != nullptr) ? db : nullptr;
-      int rc = (dtype == BAGS_DTYPE_BF16)
-                   ? launch_gemm<256, true, true, EPI_RED_F32, false, 4>(ga, di, stream)
-                   : launch_gemm<256, true, true, EPI_RED_F32, true, 4>(ga, di, stream);
-      if (rc) return rc;
-    }
+  const bool want_scale = (dX != nullptr && N > 0 && gout != nullptr);
+  const bool want_colpart = (db != nullptr && colsum == nullptr && N > 0);
+  if (db != nullptr && colsum == nullptr && N == 0) {   // no rows: zero bias gradient
+    BAGS_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * C, stream));
+    db = nullptr;
   }
-  if (db != nullptr && (dW == nullptr || N == 0)) {
-    scale_colsum_kernel<<<(C + 255) / 256, 256, 0, stream>>>(colsum, colsum_tiles, db, C, gt, gout);
+  if (want_scale || want_colpart) {
+    BAGS_REQUIRE(wscratch != nullptr && wscratch_bytes >= bags_bwd_scratch_bytes(C, ldw, dtype),
+                 "bags_bwd: wscratch must provide bags_bwd_scratch_bytes() = %zu bytes (got %zu)",
+                 bags_bwd_scratch_bytes(C, ldw, dtype), wscratch_bytes);
+    BAGS_REQUIRE((reinterpret_cast<uintptr_t>(wscratch) & 255) == 0, "bags_bwd: wscratch must be 256-byte aligned");
+  }
+  float* colpart = nullptr;
+  if (wscratch != nullptr) {
+    const size_t elt = bf ? 2 : 4;
+    const size_t wbytes = (static_cast<size_t>(C) * static_cast<size_t>(ldw) * elt + 255) & ~static_cast<size_t>(255);
+    colpart = reinterpret_cast<float*>(reinterpret_cast<char*>(wscratch) + wbytes);
+  }
+  if (dW != nullptr)
+    BAGS_REQUIRE((x != nullptr || N == 0) && lddw >= K && (lddw % 4) == 0 && (K % 4) == 0 &&
+                     (reinterpret_cast<uintptr_t>(dW) & 15) == 0,
+                 "bags_bwd: dW must be 16-byte aligned with K and lddw multiples of 4");
+  if (want_scale)
+    BAGS_REQUIRE(w != nullptr && (K % vecw) == 0 && (ldw % vecw) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+                 "bags_bwd: w must be 16-byte aligned with K and ldw multiples of %d", vecw);
+  if (want_colpart) BAGS_REQUIRE((ldd % 2) == 0, "bags_bwd: ldd must be even");
+
+  // ---- one preparation kernel: zero dW, W' = gout-scaled W, bias-gradient partial column sums ----
+  if (dW != nullptr || want_scale || want_colpart) {
+    BwdPrepParams pp{};
+    pp.dW = dW; pp.lddw = lddw; pp.C = C; pp.K = K;
+    pp.w = w; pp.wscr = wscratch; pp.ldw = ldw; pp.gout = gout; pp.gt = gt;
+    pp.dz = dz; pp.ldd = ldd; pp.N = N; pp.colpart = colpart; pp.ctiles = kColsumTiles;
+    pp.z_ctas = (dW != nullptr) ? di.num_sms : 0;
+    pp.s_ctas = want_scale ? di.num_sms : 0;
+    pp.c_ctas = want_colpart ? ((C + 63) / 64) * kColsumTiles : 0;
+    const int grid = pp.z_ctas + pp.s_ctas + pp.c_ctas;
+    if (bf) bwd_prep_kernel<false><<<grid, 256, 0, stream>>>(pp);
+    else    bwd_prep_kernel<true><<<grid, 256, 0, stream>>>(pp);
+    BAGS_CUDA(cudaGetLastError());
+  }
+  const float* cs_in = (colsum != nullptr) ? colsum : colpart;
+  const int cs_tiles = (colsum != nullptr) ? colsum_tiles : kColsumTiles;
+  if (db != nullptr) BAGS_REQUIRE(cs_in != nullptr && cs_tiles >= 1, "bags_bwd: db requested but no column sums available");
+
+  if (dW != nullptr && N > 0) {
+    GemmArgs ga{};
+    ga.a = dz; ga.lda = ldd; ga.a_mn = true;   // A = dz^T : [C, N_roi], stored [N_roi, C]
+    ga.b = x;  ga.ldb = ldx; ga.b_mn = true;   // B = x^T  : [K, N_roi], stored [N_roi, K]
+    ga.M = C; ga.N = K; ga.K = N; ga.dtype = dtype;
+    const int tiles = ((C + 127) / 128) * ((K + 255) / 256);
+    const int kblocks = (N + (bf ? 63 : 31)) / (bf ? 64 : 32);
+    ga.splits = env_int("BAGS_DW_SPLITS", pick_splits(tiles, kblocks, di.num_sms));
+    ga.p.out = dW; ga.p.ldo = lddw; ga.p.bias = nullptr;
+    ga.p.gscale = gout; ga.p.G = (gout != nullptr) ? gt.G : 0;
+    for (int g = 0; g < kMaxGroups; ++g) { ga.p.gstart[g] = gt.start[g]; ga.p.glen[g] = gt.len[g]; }
+    ga.p.colsum_in = (db != nullptr) ? cs_in : nullptr;
+    ga.p.colsum_tiles = cs_tiles;
+    ga.p.colsum_out = (db != nullptr) ? db : nullptr;
+    ga.p.pdl_wait_epilogue = 1;   // dW zeroing + column-sum partials come from bwd_prep; the mainloop overlaps it
+    int rc = bf ? launch_gemm_pdl<256, true, true, EPI_RED_F32, false, 4>(ga, di, stream)
+                : launch_gemm_pdl<256, true, true, EPI_RED_F32, true, 4>(ga, di, stream);
+    if (rc) return rc;
+  } else if (db != nullptr) {
+    scale_colsum_kernel<<<(C + 255) / 256, 256, 0, stream>>>(cs_in, cs_tiles, db, C, gt, gout);
     BAGS_CUDA(cudaGetLastError());
   }
 
   if (dX != nullptr && N > 0) {
     BAGS_REQUIRE(w != nullptr, "bags_bwd: w is NULL but dX requested");
-    const void* wb = w;
-    if (gout != nullptr) {
-      BAGS_REQUIRE(wscratch != nullptr, "bags_bwd: wscratch is required when dX and gout are both given");
-      const int vecw = (dtype == BAGS_DTYPE_BF16) ? 8 : 4;
-      BAGS_REQUIRE((K % vecw) == 0 && (ldw % vecw) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
-                       (reinterpret_cast<uintptr_t>(wscratch) & 15) == 0,
-                   "bags_bwd: w / wscratch must be 16-byte aligned with K and ldw multiples of %d", vecw);
-      const int grid = C;
-      if (dtype == BAGS_DTYPE_BF16)
-        scale_rows_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(
-            reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<__nv_bfloat16*>(wscratch), ldw, C, K, gt, gout);
-      else
-        scale_rows_kernel<float><<<grid, 128, 0, stream>>>(reinterpret_cast<const float*>(w),
-                                                           reinterpret_cast<float*>(wscratch), ldw, C, K, gt, gout);
-      BAGS_CUDA(cudaGetLastError());
-      wb = wscratch;
-    }
+    BAGS_REQUIRE((reinterpret_cast<uintptr_t>(dX) & 15) == 0, "bags_bwd: dX not 16-byte aligned");
     GemmArgs ga{};
-    ga.a = dz; ga.lda = ldd; ga.a_mn = false;  // A = dz : [N_roi, C]
-    ga.b = wb; ga.ldb = ldw; ga.b_mn = true;   // B = W^T: [K, C], stored [C, K]
+    ga.a = dz; ga.lda = ldd; ga.a_mn = false;                 // A = dz : [N_roi, C]
+    ga.b = want_scale ? wscratch : w; ga.ldb = ldw; ga.b_mn = true;   // B = W'^T: [K, C], stored [C, K]
     ga.M = N; ga.N = K; ga.K = C; ga.dtype = dtype; ga.splits = 1;
     ga.p.out = dX; ga.p.ldo = lddx; ga.p.bias = nullptr; ga.p.gscale = nullptr; ga.p.G = 0;
     ga.p.colsum_in = nullptr; ga.p.colsum_out = nullptr;
-    BAGS_REQUIRE((reinterpret_cast<uintptr_t>(dX) & 15) == 0, "bags_bwd: dX not 16-byte aligned");
-    int rc = (dtype == BAGS_DTYPE_BF16)
-                 ? launch_gemm<256, false, true, EPI_STORE_BF16, false, 4>(ga, di, stream)
-                 : launch_gemm<256, false, true, EPI_STORE_F32, true, 4>(ga, di, stream);
+    ga.p.pdl_wait_producer = 1;   // W' is produced by bwd_prep (two kernels back; the chain of waits covers it)
+    int rc = bf ? launch_gemm_pdl<256, false, true, EPI_STORE_BF16, false, 4>(ga, di, stream)
+                : launch_gemm_pdl<256, false, true, EPI_STORE_F32, true, 4>(ga, di, stream);
     if (rc) return rc;
   }
   return BAGS_OK;

@@ -48,6 +48,8 @@ struct GemmParams {
   float* colsum_out;       // written by the (n_tile==0, split==0) unit
   long long* timing;       // debug timeline [grid][8] (ns, %globaltimer) or nullptr
   int dbg;                 // test hook: bit0 skip global stores, bit1 skip TMEM loads
+  int pdl_wait_producer;   // griddepcontrol.wait before the first operand load (B comes from the previous kernel)
+  int pdl_wait_epilogue;   // griddepcontrol.wait before the first output access (output prepared by the previous kernel)
 };
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool TF32, int STAGES>
@@ -123,6 +125,7 @@ bags_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) { stamp(p.timing, 0); if (p.timing) p.timing[blockIdx.x * 8 + 7] = sm_id(); }
+  pdl_trigger();   // a dependent kernel may begin its own prologue
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -161,6 +164,7 @@ bags_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      if (p.pdl_wait_producer) pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
@@ -250,6 +254,7 @@ bags_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;   // which half of the tile's columns
     uint8_t* buf = smem_epi + (warp - 2) * Cfg::EPI_BUF_BYTES;
+    if (p.pdl_wait_epilogue) pdl_wait();
     constexpr int OUT_ELT = (EPI == EPI_STORE_BF16) ? 2 : 4;
     constexpr int VEC = 16 / OUT_ELT;  // output elements per 16-byte vector
     const bool vec_ok = ((p.ldo * OUT_ELT) % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);

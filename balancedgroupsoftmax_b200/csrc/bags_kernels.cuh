@@ -513,6 +513,96 @@ merge_scores_kernel(const float* __restrict__ z, long long ldz, GroupTable gt,
 }
 
 // ----------------------------------------------------------------------------
+// backward preparation: everything the two backward GEMMs need that is not a GEMM, in ONE launch that the
+// dW GEMM's mainloop overlaps (programmatic dependent launch):
+//   (1) dW = 0                      (the dW GEMM reduces its split-K partials into it)
+//   (2) W' = diag(gout[bin(row)]) W  (B operand of the dX GEMM when per-bin upstream gradients are given)
+//   (3) colpart[t, c] = sum over row group t of dz[n, c]   (bias-gradient partials; the dW epilogue adds
+//       the groups and applies gout)
+// ----------------------------------------------------------------------------
+struct BwdPrepParams {
+  float* dW; long long lddw; int C, K;
+  const void* w; void* wscr; long long ldw; const float* gout; GroupTable gt;
+  const void* dz; long long ldd; int N; float* colpart; int ctiles;
+  int z_ctas, s_ctas, c_ctas;   // CTA ranges of the three jobs (0 = job disabled)
+};
+
+template <bool F32>
+__global__ void __launch_bounds__(256)
+bwd_prep_kernel(const BwdPrepParams p) {
+  pdl_trigger();   // the dW GEMM may start its mainloop right away
+  const int b = blockIdx.x;
+  if (b < p.z_ctas) {
+    // ---- (1) zero dW ----
+    const int vec_per_row = p.K >> 2;
+    const long long total = static_cast<long long>(p.C) * vec_per_row;
+    for (long long i = b * 256ll + threadIdx.x; i < total; i += p.z_ctas * 256ll) {
+      const int r = static_cast<int>(i / vec_per_row), c = static_cast<int>(i - static_cast<long long>(r) * vec_per_row);
+      reinterpret_cast<float4*>(p.dW + static_cast<long long>(r) * p.lddw)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else if (b < p.z_ctas + p.s_ctas) {
+    // ---- (2) row-scaled copy of W ----
+    constexpr int V = F32 ? 4 : 8;
+    for (int r = b - p.z_ctas; r < p.C; r += p.s_ctas) {
+      float s = 0.f;
+#pragma unroll
+      for (int g = 0; g < kMaxG; ++g)
+        if (g < p.gt.G && r >= p.gt.start[g] && r < p.gt.start[g] + p.gt.len[g]) s = __ldg(p.gout + g);
+      for (int c = threadIdx.x * V; c < p.K; c += 256 * V) {
+        if (F32) {
+          float4 v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.w) + static_cast<long long>(r) * p.ldw + c));
+          v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.wscr) + static_cast<long long>(r) * p.ldw + c) = v;
+        } else {
+          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.w) + static_cast<long long>(r) * p.ldw + c));
+          const uint32_t in[4] = {raw.x, raw.y, raw.z, raw.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            o[q] = pack_bf16x2(__uint_as_float(in[q] << 16) * s, __uint_as_float(in[q] & 0xffff0000u) * s);
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.wscr) + static_cast<long long>(r) * p.ldw + c) =
+              make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+  } else if (b < p.z_ctas + p.s_ctas + p.c_ctas) {
+    // ---- (3) column sums of dz over one row group, one 64-column strip per CTA ----
+    __shared__ float s_part[8][64];
+    const int ci = b - p.z_ctas - p.s_ctas;
+    const int nstrips = (p.C + 63) / 64;
+    const int strip = ci % nstrips, rg = ci / nstrips;
+    const int rows_per_group = (p.N + p.ctiles - 1) / p.ctiles;
+    const int r0 = rg * rows_per_group;
+    const int r1 = (r0 + rows_per_group < p.N) ? r0 + rows_per_group : p.N;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int col = strip * 64 + lane * 2;   // two columns per lane; padded columns of dz exist up to ldd
+    float a0 = 0.f, a1 = 0.f;
+    if (col + 1 < p.ldd) {
+#pragma unroll 8
+      for (int r = r0 + warp; r < r1; r += 8) {
+        if (F32) {
+          const float2 v = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(p.dz) + static_cast<long long>(r) * p.ldd + col));
+          a0 += v.x; a1 += v.y;
+        } else {
+          const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const __nv_bfloat16*>(p.dz) + static_cast<long long>(r) * p.ldd + col));
+          a0 += __uint_as_float(v << 16); a1 += __uint_as_float(v & 0xffff0000u);
+        }
+      }
+    }
+    s_part[warp][lane * 2] = a0;
+    s_part[warp][lane * 2 + 1] = a1;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      float t = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) t += s_part[w8][threadIdx.x];
+      const int c = strip * 64 + threadIdx.x;
+      if (c < p.C) p.colpart[static_cast<long long>(rg) * p.C + c] = t;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
 // fp32 -> bf16 staging (rows x cols, independent leading dims; cols % 4 == 0 fast path)
 // ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)

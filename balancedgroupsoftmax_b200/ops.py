@@ -180,11 +180,14 @@ def fused_eligible(dt: DeviceTables) -> bool:
 
 
 def fused_fwd(x, w, bias, labels, dt: DeviceTables, wmask, avg, logits: Optional[torch.Tensor] = None,
-              want_dz: bool = True, want_lse: bool = False, materialize: Optional[bool] = None):
+              want_dz: bool = True, want_lse: bool = False, materialize: Optional[bool] = None,
+              want_colsum: bool = False):
     """bags_fwd: fc_cls + grouped CE in one ABI call.  Returns (loss, logits | None, lse, dz, colsum).
 
     By default (``logits is None`` and the bin table is eligible) the fused kernel runs and no logits
     exist in HBM; pass a ``logits`` buffer or ``materialize=True`` for the GEMM -> fp32 logits -> CE route.
+    ``want_colsum`` additionally returns the forward's bias-gradient partial column sums [ceil(N/128), C]
+    (fused_bwd recomputes them from dz when they are not supplied).
     """
     _require_cuda(x, w, bias, labels, wmask, avg)
     x, w = _row_major(x), _row_major(w)
@@ -207,7 +210,8 @@ def fused_fwd(x, w, bias, labels, dt: DeviceTables, wmask, avg, logits: Optional
     if want_dz:
         ldd = pad_cols(Cc)
         dz = torch.empty((N, ldd), dtype=x.dtype, device=dev)
-        colsum = torch.empty((max((N + 127) // 128, 1), Cc), dtype=torch.float32, device=dev)   # per-row-tile partials
+        if want_colsum:   # per-row-tile partials; by default the backward recomputes them from dz instead
+            colsum = torch.empty((max((N + 127) // 128, 1), Cc), dtype=torch.float32, device=dev)
     ws = _workspace(dev)
     nat.check(nat.lib().bags_fwd(
         x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), nat.ptr(bias), labels.data_ptr(),
@@ -218,10 +222,17 @@ def fused_fwd(x, w, bias, labels, dt: DeviceTables, wmask, avg, logits: Optional
     return loss, logits, lse, dz, colsum
 
 
-def fused_bwd(dz, x, w, gout, dt: DeviceTables, colsum, need_dw=True, need_db=True, need_dx=True,
+def bwd_scratch(w: torch.Tensor) -> torch.Tensor:
+    """Scratch buffer for fused_bwd (row-scaled copy of W + bias-gradient partials), reusable across calls."""
+    nbytes = nat.lib().bags_bwd_scratch_bytes(w.shape[0], w.stride(0), _dtype_code(w.dtype))
+    return torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+
+
+def fused_bwd(dz, x, w, gout, dt: DeviceTables, colsum=None, need_dw=True, need_db=True, need_dx=True,
               dW: Optional[torch.Tensor] = None, dX: Optional[torch.Tensor] = None,
               wscratch: Optional[torch.Tensor] = None, db: Optional[torch.Tensor] = None):
-    """bags_bwd: (dW fp32 [C,K] | None, db fp32 [C] | None, dX [N,K] operand dtype | None)   (a8)."""
+    """bags_bwd: (dW fp32 [C,K] | None, db fp32 [C] | None, dX [N,K] operand dtype | None)   (a8).
+    ``colsum`` (forward's column-sum partials) is optional; without it db is recomputed from dz."""
     _require_cuda(dz, x, w, gout, colsum)
     x, w = _row_major(x), _row_major(w)
     N, K = x.shape
@@ -235,8 +246,8 @@ def fused_bwd(dz, x, w, gout, dt: DeviceTables, colsum, need_dw=True, need_db=Tr
         db = None
     if need_dx and dX is None:
         dX = torch.empty((N, K), dtype=x.dtype, device=dev)
-    if need_dx and gout is not None and wscratch is None:
-        wscratch = torch.empty_like(w)
+    if wscratch is None and ((need_dx and gout is not None) or (need_db and colsum is None)):
+        wscratch = bwd_scratch(w)
     if gout is not None:
         gout = gout.contiguous()
         assert gout.dtype == torch.float32 and gout.numel() == dt.G
@@ -245,8 +256,8 @@ def fused_bwd(dz, x, w, gout, dt: DeviceTables, colsum, need_dw=True, need_db=Tr
         dt.slices_host, nat.ptr(colsum), (colsum.shape[0] if colsum.dim() == 2 else 1) if colsum is not None else 0,
         nat.ptr(dW) if need_dw else None, dW.stride(0) if need_dw else 0,
         nat.ptr(db), nat.ptr(dX) if need_dx else None, dX.stride(0) if need_dx else 0,
-        nat.ptr(wscratch) if (need_dx and gout is not None) else None, N, K, Cc, dt.G, _dtype_code(x.dtype),
-        _stream_ptr(dev)), 'bags_bwd')
+        nat.ptr(wscratch), wscratch.numel() * wscratch.element_size() if wscratch is not None else 0,
+        N, K, Cc, dt.G, _dtype_code(x.dtype), _stream_ptr(dev)), 'bags_bwd')
     return (dW if need_dw else None), db, (dX if need_dx else None)
 
 
@@ -316,16 +327,16 @@ class GroupSoftmaxFunction(torch.autograd.Function):
         ctx.has_bias = bias is not None
         ctx.bias_dtype = None if bias is None else bias.dtype
         if need_grad:
-            ctx.save_for_backward(xc, wc, dz, colsum)
+            ctx.save_for_backward(xc, wc, dz)
         return loss
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_loss):
-        xc, wc, dz, colsum = ctx.saved_tensors
+        xc, wc, dz = ctx.saved_tensors
         need_dx, need_dw, need_db = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         gout = grad_loss.detach().to(torch.float32).contiguous()
-        dW, db, dX = fused_bwd(dz, xc, wc, gout, ctx.dt, colsum, need_dw=need_dw,
+        dW, db, dX = fused_bwd(dz, xc, wc, gout, ctx.dt, None, need_dw=need_dw,
                                need_db=(need_db and ctx.has_bias), need_dx=need_dx)
         if dX is not None and dX.dtype != ctx.x_dtype:
             dX = dX.to(ctx.x_dtype)

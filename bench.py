@@ -240,7 +240,7 @@ def run_ours(args):
         s['dW'] = s['grad'][:C * K_FEAT].view(C, K_FEAT)
         s['db'] = s['grad'][C * K_FEAT:]
         s['dX'] = torch.empty(n, K_FEAT, device=dev, dtype=dtype)
-        s['wscratch'] = torch.empty_like(s['w'])
+        s['wscratch'] = ops.bwd_scratch(s['w'])
         sets.append(s)
     gout = torch.ones(dt.G, device=dev)
     seed_ctr = [0]

@@ -112,16 +112,21 @@ int bags_fwd(const void* x, long long ldx, const void* w, long long ldw, const f
              long long ldd, float* colsum, int colsum_tiles, void* workspace, size_t workspace_bytes,
              void* stream);
 
-/* Backward of bags_fwd given dz (and colsum[colsum_tiles, C]) saved by the forward and gout[G] = dL/dloss_g
- * (NULL => 1):
+/* bytes of `wscratch` bags_bwd needs (row-scaled copy of w + bias-gradient partials) */
+size_t bags_bwd_scratch_bytes(int C, long long ldw, int dtype);
+
+/* Backward of bags_fwd given dz saved by the forward and gout[G] = dL/dloss_g (NULL => 1):
  *   dW[C,K]  = (gout ⊙ dz)^T x      fp32, overwritten         (NULL to skip)
- *   db[C]    = gout ⊙ sum_t colsum   fp32                      (NULL to skip)
+ *   db[C]    = gout ⊙ sum_n dz[n,:]  fp32                      (NULL to skip)
  *   dX[N,K]  = (gout ⊙ dz) w         dtype elements            (NULL to skip)
- * wscratch: [C, ldw] dtype elements, required when dX != NULL and gout != NULL. */
+ * colsum: optional [colsum_tiles, C] partial column sums of dz from the forward; NULL => recomputed from dz.
+ * wscratch: 256-byte aligned, bags_bwd_scratch_bytes() bytes; required when (dX and gout) or (db without colsum).
+ * Launch structure: one small preparation kernel (zero dW, scaled W, column-sum partials) whose execution is
+ * overlapped by the dW GEMM's mainloop (programmatic dependent launch), then the dX GEMM. */
 int bags_bwd(const void* dz, long long ldd, const void* x, long long ldx, const void* w,
              long long ldw, const float* gout, const int32_t* slices_host, const float* colsum,
              int colsum_tiles, float* dW, long long lddw, float* db, void* dX, long long lddx,
-             void* wscratch, int N, int K, int C, int G, int dtype, void* stream);
+             void* wscratch, size_t wscratch_bytes, int N, int K, int C, int G, int dtype, void* stream);
 
 /* scores[N,classes]: scores[:,0] = softmax(z[:,slice_0])[:,0];
  * scores[:,c] = softmax(z[:,slice_0])[:,1] * softmax(z[:,slice_g])[:,j] where cls2col[c] = start_g + j.

@@ -214,7 +214,8 @@ def case_fusedk(name):
         wmask = torch.stack([w.to(torch.uint8) for w in remapped[1]]).cuda()
         avg = ops.mask_avg(wmask)
         xc, wc = x.cuda().to(cdt), W.cuda().to(cdt)
-        loss, logits, lse, dz, colsum = ops.fused_fwd(xc, wc, b.cuda(), labels.cuda(), dt, wmask, avg, want_lse=True)
+        loss, logits, lse, dz, colsum = ops.fused_fwd(xc, wc, b.cuda(), labels.cuda(), dt, wmask, avg, want_lse=True,
+                                                      want_colsum=True)
         assert logits is None
         torch.cuda.synchronize()
         lr = max(abs(loss[g].item() - ref['loss_cls_bin%d' % g].item()) / max(abs(ref['loss_cls_bin%d' % g].item()), 1e-2)
@@ -320,7 +321,7 @@ def case_timing(name):
     loss, _, _, dz, colsum = ops.fused_fwd(xc, wc, bc, lc, dt, wmask, avg, logits=logits)
     dW = torch.empty(t.num_logits, 1024, device='cuda')
     dX = torch.empty(N, 1024, device='cuda', dtype=torch.bfloat16)
-    ws = torch.empty_like(wc)
+    ws = ops.bwd_scratch(wc)
     res['bwd_all_us'] = timeit(lambda: ops.fused_bwd(dz, xc, wc, gout, dt, colsum, dW=dW, dX=dX, wscratch=ws))
     res['bwd_dw_only_us'] = timeit(lambda: ops.fused_bwd(dz, xc, wc, gout, dt, colsum, need_dx=False, dW=dW))
     res['bwd_dx_only_us'] = timeit(lambda: ops.fused_bwd(dz, xc, wc, None, dt, colsum, need_dw=False, need_db=False, dX=dX))
