@@ -9,10 +9,12 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <utility>
 
 #include "../../include/bags_b200.h"
 #include "bags_gemm.cuh"
 #include "bags_fused_fwd.cuh"
+#include "bags_bwd_fused.cuh"
 #include "bags_kernels.cuh"
 
 using namespace bags;
@@ -151,6 +153,25 @@ static int env_int(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
+// Launch with the programmatic-stream-serialization attribute (PDL): the kernel may begin while its predecessor
+// in the stream is still running; every kernel of this library guards its first access to predecessor-produced
+// data (and its first write) with griddepcontrol.wait, so stream semantics are preserved.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = env_int("BAGS_PDL", 1) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 // ----------------------------------------------------------------------------
 // GEMM launcher
 // ----------------------------------------------------------------------------
@@ -273,10 +294,9 @@ extern "C" int bags_sample_others(const int64_t* labels, const int32_t* label2bi
   BAGS_REQUIRE(ratio >= 0.0, "bags_sample_others: negative ratio");
   const long long* lab = reinterpret_cast<const long long*>(labels);
   const unsigned long long sd = static_cast<unsigned long long>(seed);
-  if (N <= 4096)       sample_others_kernel<4><<<G, 1024, 0, stream>>>(lab, label2bin, classes, G, N, ratio, sd, wmask, avg);
-  else if (N <= 16384) sample_others_kernel<16><<<G, 1024, 0, stream>>>(lab, label2bin, classes, G, N, ratio, sd, wmask, avg);
-  else                 sample_others_kernel<0><<<G, 1024, 0, stream>>>(lab, label2bin, classes, G, N, ratio, sd, wmask, avg);
-  BAGS_CUDA(cudaGetLastError());
+  if (N <= 4096)       BAGS_CUDA(launch_pdl(sample_others_kernel<4>, dim3(G), dim3(1024), 0, stream, lab, label2bin, classes, G, N, ratio, sd, wmask, avg));
+  else if (N <= 16384) BAGS_CUDA(launch_pdl(sample_others_kernel<16>, dim3(G), dim3(1024), 0, stream, lab, label2bin, classes, G, N, ratio, sd, wmask, avg));
+  else                 BAGS_CUDA(launch_pdl(sample_others_kernel<0>, dim3(G), dim3(1024), 0, stream, lab, label2bin, classes, G, N, ratio, sd, wmask, avg));
   return BAGS_OK;
 }
 
@@ -399,8 +419,10 @@ static int launch_fused_fwd(const void* x, long long ldx, const void* w, long lo
                             void* dz, long long ldd, const DeviceInfo& di, cudaStream_t stream) {
   using Cfg = FusedCfg<TF32>;
   const int dtype = TF32 ? BAGS_DTYPE_F32 : BAGS_DTYPE_BF16;
-  CUtensorMap tx, tw;
+  CUtensorMap tx, tw, txq;
   int rc = make_tmap(&tx, x, dtype, p0.K, p0.N, ldx, Cfg::BLOCK_K, Cfg::BLOCK_M);
+  if (rc) return rc;
+  rc = make_tmap(&txq, x, dtype, p0.K, p0.N, ldx, Cfg::BLOCK_K, Cfg::BLOCK_M / Cfg::CLUSTER);   // quarter tile (multicast)
   if (rc) return rc;
   rc = make_tmap(&tw, w, dtype, p0.K, p0.C, ldw, Cfg::BLOCK_K, Cfg::UMMA_N);
   if (rc) return rc;
@@ -413,6 +435,7 @@ static int launch_fused_fwd(const void* x, long long ldx, const void* w, long lo
   p.want_dz = dz != nullptr ? 1 : 0;
   p.timing = g_timing;
   p.dbg = g_timing ? g_dbg : 0;
+  p.mc_a = env_int("BAGS_FUSED_MC", 0);
   auto kernel = bags_fwd_fused_kernel<TF32>;
   BAGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int grid = Cfg::CLUSTER * ((p.N + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M);
@@ -427,7 +450,7 @@ static int launch_fused_fwd(const void* x, long long ldx, const void* w, long lo
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = env_int("BAGS_PDL", 1) ? 1 : 0;
-  BAGS_CUDA(cudaLaunchKernelEx(&cfg, kernel, tx, tw, p));
+  BAGS_CUDA(cudaLaunchKernelEx(&cfg, kernel, tx, tw, txq, p));
   return BAGS_OK;
 }
 
@@ -496,6 +519,28 @@ scale_colsum_kernel(const float* __restrict__ colsum, int tiles, float* __restri
   db[c] = s * cs;
 }
 
+
+template <bool TF32>
+static int launch_bwd_merged(const void* dz, long long ldd, const void* x, long long ldx, const void* wb, long long ldw,
+                             const BwdFusedParams& p0, const DeviceInfo& di, cudaStream_t stream) {
+  using Cfg = BwdCfg<TF32>;
+  const int dtype = TF32 ? BAGS_DTYPE_F32 : BAGS_DTYPE_BF16;
+  CUtensorMap t_dzT, t_xT, t_dz, t_wT;
+  int rc;
+  if ((rc = make_tmap(&t_dzT, dz, dtype, p0.C, p0.Nr, ldd, Cfg::SLAB, Cfg::BLOCK_K, TF32))) return rc;
+  if ((rc = make_tmap(&t_xT, x, dtype, p0.Kf, p0.Nr, ldx, Cfg::SLAB, Cfg::BLOCK_K, TF32))) return rc;
+  if ((rc = make_tmap(&t_dz, dz, dtype, p0.C, p0.Nr, ldd, Cfg::BLOCK_K, Cfg::BLOCK_M))) return rc;
+  if ((rc = make_tmap(&t_wT, wb, dtype, p0.Kf, p0.C, ldw, Cfg::SLAB, Cfg::BLOCK_K, TF32))) return rc;
+  BwdFusedParams p = p0;
+  p.timing = g_timing;
+  auto kernel = bags_bwd_fused_kernel<TF32>;
+  BAGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  const int units = p.dw_units + p.dx_units;
+  const int grid = units < di.num_sms ? units : di.num_sms;
+  BAGS_CUDA(launch_pdl(kernel, dim3(grid), dim3(Cfg::NUM_THREADS), Cfg::SMEM_BYTES, stream, t_dzT, t_xT, t_dz, t_wT, p));
+  return BAGS_OK;
+}
+
 static constexpr int kColsumTiles = 8;   // row groups of the bias-gradient partial sums made by bwd_prep
 
 extern "C" size_t bags_bwd_scratch_bytes(int C, long long ldw, int dtype) {
@@ -557,13 +602,37 @@ extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long 
     pp.s_ctas = want_scale ? di.num_sms : 0;
     pp.c_ctas = want_colpart ? ((C + 63) / 64) * kColsumTiles : 0;
     const int grid = pp.z_ctas + pp.s_ctas + pp.c_ctas;
-    if (bf) bwd_prep_kernel<false><<<grid, 256, 0, stream>>>(pp);
-    else    bwd_prep_kernel<true><<<grid, 256, 0, stream>>>(pp);
-    BAGS_CUDA(cudaGetLastError());
+    if (bf) BAGS_CUDA(launch_pdl(bwd_prep_kernel<false>, dim3(grid), dim3(256), 0, stream, pp));
+    else    BAGS_CUDA(launch_pdl(bwd_prep_kernel<true>, dim3(grid), dim3(256), 0, stream, pp));
   }
   const float* cs_in = (colsum != nullptr) ? colsum : colpart;
   const int cs_tiles = (colsum != nullptr) ? colsum_tiles : kColsumTiles;
   if (db != nullptr) BAGS_REQUIRE(cs_in != nullptr && cs_tiles >= 1, "bags_bwd: db requested but no column sums available");
+
+  // ---- both contractions in one persistent launch when both are requested ----
+  if (dW != nullptr && dX != nullptr && N > 0 && (K % 8) == 0 && env_int("BAGS_BWD_MERGED", 1)) {
+    BAGS_REQUIRE(w != nullptr, "bags_bwd: w is NULL but dX requested");
+    BAGS_REQUIRE((reinterpret_cast<uintptr_t>(dX) & 15) == 0 && ((lddx * (bf ? 2 : 4)) % 16) == 0,
+                 "bags_bwd: dX rows must be 16-byte aligned");
+    const int bk = bf ? 64 : 32;
+    BwdFusedParams bp{};
+    bp.C = C; bp.Kf = K; bp.Nr = N;
+    bp.dw_m_tiles = (C + 127) / 128; bp.dw_n_tiles = (K + 255) / 256; bp.dw_kblocks = (N + bk - 1) / bk;
+    bp.dw_splits = env_int("BAGS_DW_SPLITS", pick_splits(bp.dw_m_tiles * bp.dw_n_tiles, bp.dw_kblocks, di.num_sms));
+    if (bp.dw_splits > bp.dw_kblocks) bp.dw_splits = bp.dw_kblocks;
+    bp.dx_m_tiles = (N + 127) / 128; bp.dx_n_tiles = (K + 255) / 256; bp.dx_kblocks = (C + bk - 1) / bk;
+    bp.dw_units = bp.dw_m_tiles * bp.dw_n_tiles * bp.dw_splits;
+    bp.dx_units = bp.dx_m_tiles * bp.dx_n_tiles;
+    bp.dW = dW; bp.lddw = lddw; bp.dX = dX; bp.lddx = lddx;
+    bp.gscale = gout; bp.G = (gout != nullptr) ? gt.G : 0;
+    for (int g = 0; g < kMaxGroups; ++g) { bp.gstart[g] = gt.start[g]; bp.glen[g] = gt.len[g]; }
+    bp.colsum_in = (db != nullptr) ? cs_in : nullptr;
+    bp.colsum_tiles = cs_tiles;
+    bp.db = db;
+    const void* wb = want_scale ? wscratch : w;
+    return bf ? launch_bwd_merged<false>(dz, ldd, x, ldx, wb, ldw, bp, di, stream)
+              : launch_bwd_merged<true>(dz, ldd, x, ldx, wb, ldw, bp, di, stream);
+  }
 
   if (dW != nullptr && N > 0) {
     GemmArgs ga{};

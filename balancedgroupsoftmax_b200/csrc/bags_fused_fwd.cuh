@@ -47,6 +47,7 @@ struct FusedFwdParams {
   int want_dz;
   long long* timing;        // debug timeline [grid][8] or nullptr
   int dbg;                  // test hook: bit0 skip dz stores, bit2 skip column sums
+  int mc_a;                 // 1: each CTA loads a quarter of the x tile and TMA-multicasts it to the cluster
 };
 
 template <bool TF32>
@@ -105,7 +106,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 template <bool TF32>
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FusedCfg<TF32>::NUM_THREADS, 1)
 bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                      const FusedFwdParams p) {
+                      const __grid_constant__ CUtensorMap tmap_xq, const FusedFwdParams p) {
   using Cfg = FusedCfg<TF32>;
   constexpr int BLOCK_M = Cfg::BLOCK_M, BLOCK_N = Cfg::BLOCK_N, BLOCK_K = Cfg::BLOCK_K, STAGES = Cfg::STAGES;
   constexpr int MAXG = Cfg::MAXG;
@@ -135,12 +136,14 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   const int n0 = static_cast<int>(rank) * BLOCK_N;   // first logit column of this CTA
   const int G = p.gt.G;
   if (threadIdx.x == 0) { stamp(p.timing, 0); if (p.timing) p.timing[blockIdx.x * 8 + 7] = sm_id(); }
+  pdl_trigger();   // dependents guard their own first dependent access with griddepcontrol.wait
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
 #pragma unroll
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    // with x multicast every stage slot is written by all four CTAs -> it is free only when all four have consumed it
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], p.mc_a ? Cfg::CLUSTER : 1); }
     mbar_init(tfull_bar, 1);
     fence_mbar_init();
   }
@@ -200,7 +203,8 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         const int k0 = kb * BLOCK_K;
         uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
         uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
-        tma_load_2d(sa, &tmap_x, &full_bar[stage], k0, m0);
+        if (p.mc_a) tma_load_2d_mc(sa + rank * 4096, &tmap_xq, &full_bar[stage], k0, m0 + static_cast<int>(rank) * 32, 0xF);
+        else        tma_load_2d(sa, &tmap_x, &full_bar[stage], k0, m0);
         tma_load_2d(sb, &tmap_w, &full_bar[stage], k0, n0);
         tma_load_2d(sb + Cfg::UMMA_N * 128, &tmap_w, &full_bar[stage], k0, n0 + Cfg::UMMA_N);
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -230,7 +234,8 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             else      umma_bf16(tmem_base + h * Cfg::UMMA_N, adesc, bdesc, idesc, accum);
           }
         }
-        umma_commit(&empty_bar[stage]);
+        if (p.mc_a) umma_commit_mc(&empty_bar[stage], 0xF);
+        else        umma_commit(&empty_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
       umma_commit(tfull_bar);
@@ -416,12 +421,19 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       if (gA != g_cur) { finish_bin(); start_bin(gA); }
       if (bpos >= 32) {
         const int tq = tcol_cur - col0;
+        // most chunks contain no row's target column ("others" targets sit in each bin's first column):
+        // a warp vote selects the loop without the per-element one-hot handling
+        if (__any_sync(0xffffffffu, tq >= 0 && tq < 32)) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float pj = fast_exp2(fmaf(d[j], kLog2e, -lb_cur));
-          float dj = coef_cur * pj;
-          if (j == tq) { pt_cur = pj; dj -= coef_cur; }
-          d[j] = dj;
+          for (int j = 0; j < 32; ++j) {
+            const float pj = fast_exp2(fmaf(d[j], kLog2e, -lb_cur));
+            float dj = coef_cur * pj;
+            if (j == tq) { pt_cur = pj; dj -= coef_cur; }
+            d[j] = dj;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) d[j] = coef_cur * fast_exp2(fmaf(d[j], kLog2e, -lb_cur));
         }
       } else {
         {

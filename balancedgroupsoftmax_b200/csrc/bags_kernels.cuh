@@ -278,7 +278,10 @@ sample_others_kernel(const long long* __restrict__ labels, const int* __restrict
   __shared__ int s_base;
   uint8_t* w = wmask + (long long)g * N;
 
+  // PDL: all reads / selection work may overlap the previous kernel in the stream; pdl_wait() before the first
+  // write guarantees that kernel (and, transitively, everything before it) no longer uses the output buffers.
   if (g == 0) {
+    pdl_wait();
     for (int n = tid; n < N; n += 1024) w[n] = 1;
     if (tid == 0) avg[0] = fmaxf((float)N, 1.0f);
     return;
@@ -322,7 +325,8 @@ sample_others_kernel(const long long* __restrict__ labels, const int* __restrict
   else if (k_ll == 0) mode = 2;
   else mode = 3;
   const int k = (int)(k_ll < (long long)O ? k_ll : 0);
-  if (tid == 0)
+  if (mode != 3) pdl_wait();
+  if (tid == 0 && mode != 3)
     avg[g] = (mode == 0) ? 1.0f : (mode == 1) ? fmaxf((float)N, 1.0f) : fmaxf((float)(F + k), 1.0f);
   if (mode != 3) {
     if (EPT > 0) {
@@ -387,7 +391,8 @@ sample_others_kernel(const long long* __restrict__ labels, const int* __restrict
     mask |= (0xFFu << shift);
   }
   // ---- write weights; ties on the threshold key broken by ascending row index ----
-  if (tid == 0) s_base = 0;
+  pdl_wait();
+  if (tid == 0) { s_base = 0; avg[g] = fmaxf((float)(F + k), 1.0f); }
   __syncthreads();
   const int rounds = (N + 1023) / 1024;
   for (int e = 0; e < rounds; ++e) {
@@ -444,6 +449,7 @@ mask_avg_kernel(const uint8_t* __restrict__ wmask, int N, float* __restrict__ av
   if (threadIdx.x == 0) {
     int t = 0;
     for (int i = 0; i < 8; ++i) t += s_w[i];
+    pdl_wait();
     avg[g] = fmaxf((float)t, 1.0f);
   }
 }
@@ -530,7 +536,8 @@ struct BwdPrepParams {
 template <bool F32>
 __global__ void __launch_bounds__(256)
 bwd_prep_kernel(const BwdPrepParams p) {
-  pdl_trigger();   // the dW GEMM may start its mainloop right away
+  pdl_wait();      // dz comes from the forward kernel; nothing before it may still be running either
+  pdl_trigger();   // from here on the dW GEMM may start: its mainloop only reads dz and x
   const int b = blockIdx.x;
   if (b < p.z_ctas) {
     // ---- (1) zero dW ----

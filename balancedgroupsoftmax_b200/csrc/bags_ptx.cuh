@@ -119,6 +119,25 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 
+// Multicast variant: the box is written to the same shared-memory offset of every CTA in `cta_mask` of the
+// cluster, and each destination's mbarrier (same offset) receives the complete_tx.
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const void* tmap, uint64_t* bar,
+                                               int32_t c_inner, int32_t c_outer, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)),
+        "r"(c_inner), "r"(c_outer), "h"(cta_mask)
+      : "memory");
+}
+// commit that arrives on the mbarrier at the same offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+
 // 2-D tiled store shared::cta -> global (bulk async group); out-of-bounds parts of the box are clipped.
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int32_t c_inner,
                                              int32_t c_outer) {
