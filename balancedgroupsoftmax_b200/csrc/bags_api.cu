@@ -397,11 +397,11 @@ static bool fused_eligible(const int32_t* slices_host, int G, int C) {
     end += slices_host[2 * g + 1];
   }
   if (end != C) return false;
-  for (int c0 = 0; c0 < C; c0 += 32) {   // at most two bins per 32-column chunk
+  for (int c0 = 0; c0 < C; c0 += 16) {   // at most two bins per 16-column chunk
     int cnt = 0;
     for (int g = 0; g < G; ++g) {
       const int s = slices_host[2 * g], e = s + slices_host[2 * g + 1];
-      if (s < c0 + 32 && e > c0) ++cnt;
+      if (s < c0 + 16 && e > c0) ++cnt;
     }
     if (cnt > 2) return false;
   }
@@ -419,10 +419,8 @@ static int launch_fused_fwd(const void* x, long long ldx, const void* w, long lo
                             void* dz, long long ldd, const DeviceInfo& di, cudaStream_t stream) {
   using Cfg = FusedCfg<TF32>;
   const int dtype = TF32 ? BAGS_DTYPE_F32 : BAGS_DTYPE_BF16;
-  CUtensorMap tx, tw, txq;
+  CUtensorMap tx, tw;
   int rc = make_tmap(&tx, x, dtype, p0.K, p0.N, ldx, Cfg::BLOCK_K, Cfg::BLOCK_M);
-  if (rc) return rc;
-  rc = make_tmap(&txq, x, dtype, p0.K, p0.N, ldx, Cfg::BLOCK_K, Cfg::BLOCK_M / Cfg::CLUSTER);   // quarter tile (multicast)
   if (rc) return rc;
   rc = make_tmap(&tw, w, dtype, p0.K, p0.C, ldw, Cfg::BLOCK_K, Cfg::UMMA_N);
   if (rc) return rc;
@@ -435,7 +433,6 @@ static int launch_fused_fwd(const void* x, long long ldx, const void* w, long lo
   p.want_dz = dz != nullptr ? 1 : 0;
   p.timing = g_timing;
   p.dbg = g_timing ? g_dbg : 0;
-  p.mc_a = env_int("BAGS_FUSED_MC", 0);
   auto kernel = bags_fwd_fused_kernel<TF32>;
   BAGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int grid = Cfg::CLUSTER * ((p.N + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M);
@@ -450,7 +447,7 @@ static int launch_fused_fwd(const void* x, long long ldx, const void* w, long lo
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = env_int("BAGS_PDL", 1) ? 1 : 0;
-  BAGS_CUDA(cudaLaunchKernelEx(&cfg, kernel, tx, tw, txq, p));
+  BAGS_CUDA(cudaLaunchKernelEx(&cfg, kernel, tx, tw, p));
   return BAGS_OK;
 }
 

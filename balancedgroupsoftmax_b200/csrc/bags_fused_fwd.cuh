@@ -5,9 +5,10 @@
 // A cluster of 4 CTAs owns one 128-row tile of RoIs; CTA r holds logit columns [320r, 320r+320)
 // of those rows in its TMEM (128 lanes x 320 fp32 columns).  The epilogue maps ONE THREAD TO ONE
 // ROW (TMEM lane), so walking the columns of a bin is a plain sequential loop: no masks, no
-// shuffles, bin boundaries are warp-uniform.  Bins usually span several CTAs, so each
-// (CTA, column-half) publishes its per-row partial (max, sum-exp) for every bin to all four CTAs
-// through distributed shared memory; after one cluster barrier every thread combines the eight
+// shuffles, bin boundaries are warp-uniform.  16 epilogue warps (4 per TMEM lane quarter) each own an
+// 80-column group; the four groups' per-row partial (max, sum-exp) of every bin are combined inside the
+// CTA, and since bins usually span several CTAs the CTA-level partials are published to all four CTAs
+// through distributed shared memory; after one cluster barrier every thread combines the four
 // partials into the bin's log-sum-exp and makes a second pass over its TMEM columns:
 //
 //   pass A  (after the mainloop):  per bin segment, online (max, sum exp(z - max))
@@ -47,7 +48,6 @@ struct FusedFwdParams {
   int want_dz;
   long long* timing;        // debug timeline [grid][8] or nullptr
   int dbg;                  // test hook: bit0 skip dz stores, bit2 skip column sums
-  int mc_a;                 // 1: each CTA loads a quarter of the x tile and TMA-multicasts it to the cluster
 };
 
 template <bool TF32>
@@ -64,20 +64,26 @@ struct FusedCfg {
   static constexpr int B_BYTES = BLOCK_N * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int CLUSTER = 4;
-  static constexpr int EPI_WARPS = 8;
+  // Epilogue: 16 warps = 4 per TMEM lane quarter (thread = RoI row) x 4 column groups of 80 columns, walked in
+  // 16-column chunks.  Four warps per SM sub-partition hide the TMEM / shared-memory / MUFU latencies that left a
+  // two-warp version issue-bound at ~25 % (profiles/README.md).
+  static constexpr int EPI_WARPS = 16;
   static constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
-  static constexpr int HALF_COLS = BLOCK_N / 2;       // 160 columns per epilogue warp
-  static constexpr int CHUNKS = HALF_COLS / 32;       // 5
+  static constexpr int CGROUPS = 4;
+  static constexpr int CG_COLS = BLOCK_N / CGROUPS;   // 80
+  static constexpr int CH = 16;                       // chunk width
+  static constexpr int CHUNKS = CG_COLS / CH;         // 5
   static constexpr int MAXG = 6;
-  static constexpr int NSRC = CLUSTER * 2;            // (cta rank, column half)
-  static constexpr int XCH_BYTES = NSRC * MAXG * BLOCK_M * 8;   // float2 (max, sum)
-  static constexpr int DZ_ROW_BYTES = 32 * (TF32 ? 4 : 2);     // 32 columns per staged row
-  static constexpr int DZ_BUF_BYTES = 32 * DZ_ROW_BYTES;
+  static constexpr int XCH_BYTES = CLUSTER * MAXG * BLOCK_M * 8;   // cluster-level partials, float2 (max, sum)
+  static constexpr int LOC_BYTES = CGROUPS * MAXG * BLOCK_M * 8;   // CTA-local partials of the 4 column groups
+  static constexpr int DZ_ROW_BYTES = CH * (TF32 ? 4 : 2);         // one staged row of a chunk: 64 B / 32 B
+  static constexpr int DZ_BUF_BYTES = 2048;                        // per-warp staging buffer (32 rows)
   static constexpr int MISC_BYTES = BLOCK_N * 4 /*bias*/ + 2 * MAXG * BLOCK_M * 4 /*tcol, coef*/ +
                                     BLOCK_N * 4 /*colsum*/ + 64 /*loss*/ + 256 /*barriers*/;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + XCH_BYTES + MISC_BYTES + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + XCH_BYTES + LOC_BYTES + MISC_BYTES + 1024;
   static_assert(SMEM_BYTES <= 232448, "fused forward exceeds shared memory");
-  static_assert(EPI_WARPS * 2 * DZ_BUF_BYTES <= STAGES * STAGE_BYTES, "staging must fit in the idle pipeline buffers");
+  static_assert(EPI_WARPS * DZ_BUF_BYTES <= STAGES * STAGE_BYTES, "staging must fit in the idle pipeline buffers");
+  static_assert(32 * DZ_ROW_BYTES <= DZ_BUF_BYTES, "staging buffer too small");
 };
 
 __device__ __forceinline__ void cluster_arrive_wait() {
@@ -106,21 +112,22 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 template <bool TF32>
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FusedCfg<TF32>::NUM_THREADS, 1)
 bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                      const __grid_constant__ CUtensorMap tmap_xq, const FusedFwdParams p) {
+                      const FusedFwdParams p) {
   using Cfg = FusedCfg<TF32>;
   constexpr int BLOCK_M = Cfg::BLOCK_M, BLOCK_N = Cfg::BLOCK_N, BLOCK_K = Cfg::BLOCK_K, STAGES = Cfg::STAGES;
-  constexpr int MAXG = Cfg::MAXG;
+  constexpr int MAXG = Cfg::MAXG, CH = Cfg::CH;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-  float2* xch = reinterpret_cast<float2*>(smem + STAGES * Cfg::STAGE_BYTES);   // [NSRC][MAXG][128]
-  float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(xch) + Cfg::XCH_BYTES);  // [320]
-  int* s_tcol = reinterpret_cast<int*>(s_bias + BLOCK_N);      // [MAXG][128] absolute target column
+  float2* xch = reinterpret_cast<float2*>(smem + STAGES * Cfg::STAGE_BYTES);                 // [4 ranks][MAXG][128]
+  float2* loc = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(xch) + Cfg::XCH_BYTES);  // [4 cgroups][MAXG][128]
+  float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(loc) + Cfg::LOC_BYTES);  // [320]
+  int* s_tcol = reinterpret_cast<int*>(s_bias + BLOCK_N);             // [MAXG][128] absolute target column
   float* s_coef = reinterpret_cast<float*>(s_tcol + MAXG * BLOCK_M);  // [MAXG][128] w / avg
-  float* s_colsum = s_coef + MAXG * BLOCK_M;                   // [320]
-  float* s_loss = s_colsum + BLOCK_N;                          // [8]
+  float* s_colsum = s_coef + MAXG * BLOCK_M;                          // [320]
+  float* s_loss = s_colsum + BLOCK_N;                                 // [8]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_loss + 16);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
@@ -142,8 +149,7 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
 #pragma unroll
-    // with x multicast every stage slot is written by all four CTAs -> it is free only when all four have consumed it
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], p.mc_a ? Cfg::CLUSTER : 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(tfull_bar, 1);
     fence_mbar_init();
   }
@@ -184,13 +190,13 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     return e;
   };
 
-  const int ew = warp - 2;                 // epilogue warp index 0..7 (valid when warp >= 2)
+  const int ew = warp - 2;                 // epilogue warp index 0..15 (valid when warp >= 2)
   const int quarter = warp & 3;            // TMEM lane quarter
-  const int half = (ew >= 0) ? (ew >> 2) : 0;
+  const int cg = (ew >= 0) ? (ew >> 2) : 0;   // column group 0..3
   const int row_l = quarter * 32 + lane;   // row inside the tile == TMEM lane
   const int row = m0 + row_l;
-  const int c_half = half * Cfg::HALF_COLS;   // first TMEM column of this warp's range
-  const int src = static_cast<int>(rank) * 2 + half;
+  const int c_cg = cg * Cfg::CG_COLS;      // first TMEM column of this warp's range
+  const int col_lo = n0 + c_cg, col_hi = col_lo + Cfg::CG_COLS;   // global logit columns of this warp
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -203,8 +209,7 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         const int k0 = kb * BLOCK_K;
         uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
         uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
-        if (p.mc_a) tma_load_2d_mc(sa + rank * 4096, &tmap_xq, &full_bar[stage], k0, m0 + static_cast<int>(rank) * 32, 0xF);
-        else        tma_load_2d(sa, &tmap_x, &full_bar[stage], k0, m0);
+        tma_load_2d(sa, &tmap_x, &full_bar[stage], k0, m0);
         tma_load_2d(sb, &tmap_w, &full_bar[stage], k0, n0);
         tma_load_2d(sb + Cfg::UMMA_N * 128, &tmap_w, &full_bar[stage], k0, n0 + Cfg::UMMA_N);
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -234,8 +239,7 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             else      umma_bf16(tmem_base + h * Cfg::UMMA_N, adesc, bdesc, idesc, accum);
           }
         }
-        if (p.mc_a) umma_commit_mc(&empty_bar[stage], 0xF);
-        else        umma_commit(&empty_bar[stage]);
+        umma_commit(&empty_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
       umma_commit(tfull_bar);
@@ -244,7 +248,7 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   } else {
     // ===================== epilogue, part 1: row info (overlaps the mainloop) + pass A ==========
     pdl_wait();   // masks / avg come from the preceding sampler kernel (programmatic dependent launch)
-    if (half == 0) {
+    if (cg == 0) {
       long long lab = 0;
       if (row < p.N) lab = __ldg(p.labels + row);
       const bool lab_ok = (row < p.N) && lab >= 0 && lab < p.classes;
@@ -258,43 +262,30 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         s_coef[g * BLOCK_M + row_l] = w * inv_avg;
       }
     }
-    named_bar_sync(1, 32 * Cfg::EPI_WARPS);
+    // bins this warp does not touch contribute the identity (-inf, 0) to the CTA-local combine
+    for (int g = 0; g < G; ++g)
+      if (s_ge[g] <= col_lo || s_gs[g] >= col_hi) loc[(cg * MAXG + g) * BLOCK_M + row_l] = make_float2(-INFINITY, 0.f);
 
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
     if (warp == 2 && lane == 0) stamp(p.timing, 3);   // accumulators complete
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c_half;
-
-    // bins this warp does not touch publish the identity (-inf, 0); touched ones are overwritten below
-    for (int g = 0; g < G; ++g) {
-      const int s = s_gs[g], e = s_ge[g];
-      const int lo = n0 + c_half, hi = lo + Cfg::HALF_COLS;
-      if (e <= lo || s >= hi) {
-        const uint32_t addr = smem_u32(&xch[(src * MAXG + g) * BLOCK_M + row_l]);
-#pragma unroll
-        for (uint32_t r = 0; r < 4; ++r) st_cluster_f2(addr, r, -INFINITY, 0.f);
-      }
-    }
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c_cg;
     {
       int g_cur = -2;
       float m_cur = -INFINITY, s_cur = 0.f;
       auto flush = [&]() {
-        if (g_cur >= 0) {
-          const uint32_t addr = smem_u32(&xch[(src * MAXG + g_cur) * BLOCK_M + row_l]);
-#pragma unroll
-          for (uint32_t r = 0; r < 4; ++r) st_cluster_f2(addr, r, m_cur, s_cur);
-        }
+        if (g_cur >= 0) loc[(cg * MAXG + g_cur) * BLOCK_M + row_l] = make_float2(m_cur, s_cur);
       };
-      // online update of (m_cur, s_cur) with elements j in [lo, hi) of z[32]
-      auto accum = [&](const float (&z)[32], int lo, int hi) {
+      // online update of (m_cur, s_cur) with elements j in [lo, hi) of z[CH]
+      auto accum = [&](const float (&z)[CH], int lo, int hi) {
         float cm = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) cm = fmaxf(cm, (j >= lo && j < hi) ? z[j] : -INFINITY);
+        for (int j = 0; j < CH; ++j) cm = fmaxf(cm, (j >= lo && j < hi) ? z[j] : -INFINITY);
         const float m_new = fmaxf(m_cur, cm);
         const float mb = m_new * kLog2e;
         float acc = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < CH; ++j) {
           const float e = fast_exp2(fmaf(z[j], kLog2e, -mb));
           acc += (j >= lo && j < hi) ? e : 0.f;
         }
@@ -302,36 +293,36 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         s_cur = s_cur * resc + acc;
         m_cur = m_new;
       };
-      uint32_t v[32];
-      if (n0 + c_half < p.C) tmem_ld_32x32b_x32(t_row, v);   // software pipeline: chunk ci+1 is in flight
-#pragma unroll 1                                                // while chunk ci is reduced
+      uint32_t v[CH];
+      if (col_lo < p.C) tmem_ld_32x32b_x16(t_row, v);   // software pipeline: chunk ci+1 is in flight
+#pragma unroll 1                                           // while chunk ci is reduced
       for (int ci = 0; ci < Cfg::CHUNKS; ++ci) {
-        const int col0 = n0 + c_half + ci * 32;
+        const int col0 = col_lo + ci * CH;
         if (col0 >= p.C) break;
         tmem_ld_wait();
-        float z[32];
+        float z[CH];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c_half + ci * 32 + j]);
+        for (int j = 0; j < CH; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c_cg + ci * CH + j]);
           z[j + 0] = __uint_as_float(v[j + 0]) + b4.x; z[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
           z[j + 2] = __uint_as_float(v[j + 2]) + b4.z; z[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
         }
-        if (ci + 1 < Cfg::CHUNKS && col0 + 32 < p.C) tmem_ld_32x32b_x32(t_row + (ci + 1) * 32, v);
+        if (ci + 1 < Cfg::CHUNKS && col0 + CH < p.C) tmem_ld_32x32b_x16(t_row + (ci + 1) * CH, v);
         const int gA = bin_of(col0);
         const int endA = bin_end(gA);
-        const int bpos = (endA - col0 < 32) ? (endA - col0) : 32;   // columns [0,bpos) belong to gA
+        const int bpos = (endA - col0 < CH) ? (endA - col0) : CH;   // columns [0,bpos) belong to gA
         if (gA != g_cur) { flush(); g_cur = gA; m_cur = -INFINITY; s_cur = 0.f; }
-        if (bpos >= 32) {
+        if (bpos >= CH) {
           // fast path: the whole chunk is one bin
           float c4[4] = {z[0], z[1], z[2], z[3]};
 #pragma unroll
-          for (int j = 4; j < 32; ++j) c4[j & 3] = fmaxf(c4[j & 3], z[j]);
+          for (int j = 4; j < CH; ++j) c4[j & 3] = fmaxf(c4[j & 3], z[j]);
           const float cm = fmaxf(fmaxf(c4[0], c4[1]), fmaxf(c4[2], c4[3]));
           const float m_new = fmaxf(m_cur, cm);
           const float mb = m_new * kLog2e;
           float a4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int j = 0; j < 32; ++j) a4[j & 3] += fast_exp2(fmaf(z[j], kLog2e, -mb));
+          for (int j = 0; j < CH; ++j) a4[j & 3] += fast_exp2(fmaf(z[j], kLog2e, -mb));
           const float acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
           const float resc = (m_cur == -INFINITY) ? 0.f : fast_exp2((m_cur - m_new) * kLog2e);
           s_cur = s_cur * resc + acc;
@@ -343,12 +334,28 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           g_cur = gB; m_cur = -INFINITY; s_cur = 0.f;
           if (gB >= 0) {
             const int endB = bin_end(gB);
-            const int hiB = (endB - col0 < 32) ? (endB - col0) : 32;
+            const int hiB = (endB - col0 < CH) ? (endB - col0) : CH;
             accum(z, bpos, hiB);
           }
         }
       }
       flush();
+    }
+    // ---- CTA-local combine of the 4 column groups, then publish to the 4 CTAs of the cluster ----
+    named_bar_sync(1, 32 * Cfg::EPI_WARPS);
+    if (cg == 0) {
+      for (int g = 0; g < G; ++g) {
+        float2 q[Cfg::CGROUPS];
+#pragma unroll
+        for (int i = 0; i < Cfg::CGROUPS; ++i) q[i] = loc[(i * MAXG + g) * BLOCK_M + row_l];
+        const float M = fmaxf(fmaxf(q[0].x, q[1].x), fmaxf(q[2].x, q[3].x));
+        float S = 0.f;
+#pragma unroll
+        for (int i = 0; i < Cfg::CGROUPS; ++i) S += (q[i].x == -INFINITY) ? 0.f : q[i].y * fast_exp2((q[i].x - M) * kLog2e);
+        const uint32_t addr = smem_u32(&xch[(static_cast<int>(rank) * MAXG + g) * BLOCK_M + row_l]);
+#pragma unroll
+        for (uint32_t r = 0; r < 4; ++r) st_cluster_f2(addr, r, M, S);
+      }
     }
   }
 
@@ -359,10 +366,9 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 
   if (warp >= 2) {
     // ===================== epilogue, part 2: combine + pass C =====================================
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c_half;
-    uint8_t* my_bufs = smem + (ew * 2) * Cfg::DZ_BUF_BYTES;   // aliases the (now idle) pipeline stages
-    uint32_t chunk_ctr = 0;
-    float* colsum_dst = s_colsum + c_half;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c_cg;
+    uint8_t* buf = smem + ew * Cfg::DZ_BUF_BYTES;   // aliases the (now idle) pipeline stages
+    const int m_warp = m0 + quarter * 32;
 
     int g_cur = -2;
     float lb_cur = 0.f, coef_cur = 0.f, pt_cur = 1.0f;
@@ -380,52 +386,49 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       pt_cur = 1.0f;
       own_cur = false;
       if (g < 0) { lb_cur = 0.f; coef_cur = 0.f; tcol_cur = -1; return; }
-      float M = -INFINITY;
+      float2 q[Cfg::CLUSTER];
 #pragma unroll
-      for (int s = 0; s < Cfg::NSRC; ++s) M = fmaxf(M, xch[(s * MAXG + g) * BLOCK_M + row_l].x);
+      for (int s = 0; s < Cfg::CLUSTER; ++s) q[s] = xch[(s * MAXG + g) * BLOCK_M + row_l];
+      const float M = fmaxf(fmaxf(q[0].x, q[1].x), fmaxf(q[2].x, q[3].x));
       float S = 0.f;
 #pragma unroll
-      for (int s = 0; s < Cfg::NSRC; ++s) {
-        const float2 ms = xch[(s * MAXG + g) * BLOCK_M + row_l];
-        S += ms.y * fast_exp2((ms.x - M) * kLog2e);
-      }
+      for (int s = 0; s < Cfg::CLUSTER; ++s) S += (q[s].x == -INFINITY) ? 0.f : q[s].y * fast_exp2((q[s].x - M) * kLog2e);
       const float lse_v = M + logf(S);
       lb_cur = lse_v * kLog2e;
       coef_cur = s_coef[g * BLOCK_M + row_l];
       tcol_cur = s_tcol[g * BLOCK_M + row_l];
-      const int lo = n0 + c_half, hi = lo + Cfg::HALF_COLS;
-      own_cur = (tcol_cur >= lo && tcol_cur < hi);
-      if (p.lse != nullptr && row < p.N && s_gs[g] >= lo && s_gs[g] < hi)
+      own_cur = (tcol_cur >= col_lo && tcol_cur < col_hi);
+      if (p.lse != nullptr && row < p.N && s_gs[g] >= col_lo && s_gs[g] < col_hi)
         p.lse[static_cast<long long>(row) * G + g] = lse_v;
     };
 
-    uint32_t v[32];
-    if (n0 + c_half < p.C) tmem_ld_32x32b_x32(t_row, v);
+    uint32_t v[CH];
+    if (col_lo < p.C) tmem_ld_32x32b_x16(t_row, v);
 #pragma unroll 1
     for (int ci = 0; ci < Cfg::CHUNKS; ++ci) {
-      const int col0 = n0 + c_half + ci * 32;
+      const int col0 = col_lo + ci * CH;
       if (col0 >= p.C) break;
       tmem_ld_wait();
-      float d[32];
+      float d[CH];
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c_half + ci * 32 + j]);
+      for (int j = 0; j < CH; j += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c_cg + ci * CH + j]);
         d[j + 0] = __uint_as_float(v[j + 0]) + b4.x; d[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
         d[j + 2] = __uint_as_float(v[j + 2]) + b4.z; d[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
       }
       // next chunk's TMEM load overlaps the exp / pack / store phases of this one
-      if (ci + 1 < Cfg::CHUNKS && col0 + 32 < p.C) tmem_ld_32x32b_x32(t_row + (ci + 1) * 32, v);
+      if (ci + 1 < Cfg::CHUNKS && col0 + CH < p.C) tmem_ld_32x32b_x16(t_row + (ci + 1) * CH, v);
       const int gA = bin_of(col0);
       const int endA = bin_end(gA);
-      const int bpos = (endA - col0 < 32) ? (endA - col0) : 32;
+      const int bpos = (endA - col0 < CH) ? (endA - col0) : CH;
       if (gA != g_cur) { finish_bin(); start_bin(gA); }
-      if (bpos >= 32) {
+      if (bpos >= CH) {
         const int tq = tcol_cur - col0;
         // most chunks contain no row's target column ("others" targets sit in each bin's first column):
         // a warp vote selects the loop without the per-element one-hot handling
-        if (__any_sync(0xffffffffu, tq >= 0 && tq < 32)) {
+        if (__any_sync(0xffffffffu, tq >= 0 && tq < CH)) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < CH; ++j) {
             const float pj = fast_exp2(fmaf(d[j], kLog2e, -lb_cur));
             float dj = coef_cur * pj;
             if (j == tq) { pt_cur = pj; dj -= coef_cur; }
@@ -433,13 +436,13 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) d[j] = coef_cur * fast_exp2(fmaf(d[j], kLog2e, -lb_cur));
+          for (int j = 0; j < CH; ++j) d[j] = coef_cur * fast_exp2(fmaf(d[j], kLog2e, -lb_cur));
         }
       } else {
         {
           const int tq = tcol_cur - col0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < CH; ++j) {
             if (j < bpos) {
               const float pj = fast_exp2(fmaf(d[j], kLog2e, -lb_cur));
               float dj = coef_cur * pj;
@@ -452,10 +455,10 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         finish_bin();
         start_bin(gB);
         const int endB = (gB >= 0) ? bin_end(gB) : 0;
-        const int hiB = (gB >= 0) ? ((endB - col0 < 32) ? (endB - col0) : 32) : 0;
+        const int hiB = (gB >= 0) ? ((endB - col0 < CH) ? (endB - col0) : CH) : 0;
         const int tq = tcol_cur - col0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < CH; ++j) {
           if (j >= bpos) {
             float dj = 0.f;
             if (j < hiB) {
@@ -468,61 +471,57 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         }
       }
       if (p.want_dz) {
-        uint8_t* buf = my_bufs + (chunk_ctr & 1u) * Cfg::DZ_BUF_BYTES;
-        ++chunk_ctr;
-        const int m_warp = m0 + quarter * 32;
+        // stage the 32-row x 16-column tile in (swizzled) shared memory, read it back transposed so that each
+        // warp-wide 16-byte store writes whole 32-byte (bf16) / 64-byte (fp32) row segments
         if (TF32) {
-          uint4* rowp = reinterpret_cast<uint4*>(buf + lane * 128);
+          uint4* rowp = reinterpret_cast<uint4*>(buf + lane * 64);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 4; ++j) {
             float4 r = make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
-            rowp[j ^ (lane & 7)] = *reinterpret_cast<uint4*>(&r);
+            rowp[j ^ ((lane >> 1) & 3)] = *reinterpret_cast<uint4*>(&r);
           }
           __syncwarp();
-          // transposed read-back: each warp-wide 16-byte store covers 4 complete 128-byte rows
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int r = it * 4 + (lane >> 3), ch = lane & 7;
-            const uint4 val = *reinterpret_cast<const uint4*>(buf + r * 128 + ((ch ^ (r & 7)) << 4));
+          for (int it = 0; it < 4; ++it) {
+            const int r = it * 8 + (lane >> 2), ch = lane & 3;
+            const uint4 val = *reinterpret_cast<const uint4*>(buf + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4));
             if (m_warp + r < p.N && !(p.dbg & 1))
               *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.dz) + static_cast<long long>(m_warp + r) * p.ldd + col0 + ch * 4) = val;
           }
         } else {
-          uint4* rowp = reinterpret_cast<uint4*>(buf + lane * 64);   // 64-byte rows, 64B-style swizzle
+          uint4* rowp = reinterpret_cast<uint4*>(buf + lane * 32);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < 2; ++j) {
             uint4 r;
             r.x = pack_bf16x2(d[8 * j + 0], d[8 * j + 1]); r.y = pack_bf16x2(d[8 * j + 2], d[8 * j + 3]);
             r.z = pack_bf16x2(d[8 * j + 4], d[8 * j + 5]); r.w = pack_bf16x2(d[8 * j + 6], d[8 * j + 7]);
-            rowp[j ^ ((lane >> 1) & 3)] = r;
+            rowp[j ^ ((lane >> 2) & 1)] = r;
           }
           __syncwarp();
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {   // 8 rows x 64 bytes per warp-wide store
-            const int r = it * 8 + (lane >> 2), ch = lane & 3;
-            const uint4 val = *reinterpret_cast<const uint4*>(buf + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4));
+          for (int it = 0; it < 2; ++it) {
+            const int r = it * 16 + (lane >> 1), ch = lane & 1;
+            const uint4 val = *reinterpret_cast<const uint4*>(buf + r * 32 + ((ch ^ ((r >> 2) & 1)) << 4));
             if (m_warp + r < p.N && !(p.dbg & 1))
               *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.dz) + static_cast<long long>(m_warp + r) * p.ldd + col0 + ch * 8) = val;
           }
         }
-        // bias-gradient column sums from the staged tile: lane l owns column l of the chunk
+        // optional bias-gradient column sums from the staged tile: lanes l and l+16 share column l % 16
         if (p.colsum != nullptr && !(p.dbg & 4)) {
-          float cs4[4] = {0.f, 0.f, 0.f, 0.f};
-          if (TF32) {
+          const int cc = lane & 15, rbase = (lane >> 4) * 16;
+          float cs = 0.f;
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
-              const int chunk16 = (lane >> 2) ^ (r & 7);
-              cs4[r & 3] += *reinterpret_cast<const float*>(buf + r * 128 + chunk16 * 16 + (lane & 3) * 4);
-            }
-          } else {
-#pragma unroll
-            for (int r = 0; r < 32; ++r) {
-              const int chunk16 = (lane >> 3) ^ ((r >> 1) & 3);
-              const unsigned short h = *reinterpret_cast<const unsigned short*>(buf + r * 64 + chunk16 * 16 + (lane & 7) * 2);
-              cs4[r & 3] += __uint_as_float(static_cast<uint32_t>(h) << 16);
+          for (int i = 0; i < 16; ++i) {
+            const int r = rbase + i;
+            if (TF32) {
+              cs += *reinterpret_cast<const float*>(buf + r * 64 + (((cc >> 2) ^ ((r >> 1) & 3)) << 4) + (cc & 3) * 4);
+            } else {
+              const unsigned short h = *reinterpret_cast<const unsigned short*>(buf + r * 32 + (((cc >> 3) ^ ((r >> 2) & 1)) << 4) + (cc & 7) * 2);
+              cs += __uint_as_float(static_cast<uint32_t>(h) << 16);
             }
           }
-          atomicAdd(&colsum_dst[ci * 32 + lane], (cs4[0] + cs4[1]) + (cs4[2] + cs4[3]));   // 4 quarters share a column
+          cs += __shfl_xor_sync(0xffffffffu, cs, 16);
+          if (lane < 16) atomicAdd(&s_colsum[c_cg + ci * CH + lane], cs);   // 4 quarters share a column
         }
         __syncwarp();
       }
@@ -532,7 +531,7 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     named_bar_sync(1, 32 * Cfg::EPI_WARPS);
 
     // ---- CTA results -> global ----
-    const int et = threadIdx.x - 64;   // 0..255
+    const int et = threadIdx.x - 64;   // 0..511
     if (p.colsum != nullptr && p.want_dz) {
       for (int c = et; c < BLOCK_N; c += 32 * Cfg::EPI_WARPS)
         if (n0 + c < p.C) p.colsum[static_cast<long long>(row_tile) * p.C + n0 + c] = s_colsum[c];

@@ -94,7 +94,7 @@ int bags_group_ce(const float* logits, long long ldz, const int64_t* labels,
                   size_t workspace_bytes, void* stream);
 
 /* 1 if bags_fwd can run its fused kernel (logits == NULL) for this bin table: C <= 1280, G <= 6, C % 4 == 0,
- * bins tile [0, C) contiguously and no 32-column chunk intersects more than two bins. */
+ * bins tile [0, C) contiguously and no 16-column chunk intersects more than two bins. */
 int bags_fused_eligible(const int32_t* slices_host, int G, int C);
 
 /* fc_cls + grouped softmax-CE (+ dz, colsum) in one call.
