@@ -538,6 +538,85 @@ static int launch_bwd_merged(const void* dz, long long ldd, const void* x, long 
   return BAGS_OK;
 }
 
+// CTA pairs that can be co-resident (GPCs with an odd number of usable SMs leave one SM without a partner)
+template <bool TF32>
+static int pair_capacity(const DeviceInfo& di) {
+  static int cached[2] = {0, 0};
+  int& c = cached[TF32 ? 1 : 0];
+  if (c > 0) return c;
+  using Cfg = BwdPairCfg<TF32>;
+  auto kernel = bags_bwd_pair_kernel<TF32>;
+  int n = di.num_sms / 2;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) == cudaSuccess) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * (di.num_sms / 2));
+    cfg.blockDim = dim3(Cfg::NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int q = 0;
+    if (cudaOccupancyMaxActiveClusters(&q, kernel, &cfg) == cudaSuccess && q > 0 && q < n) n = q;
+    else (void)cudaGetLastError();
+  }
+  const int forced = env_int("BAGS_PAIRS", 0);
+  if (forced > 0 && forced < n) n = forced;
+  c = n;
+  return c;
+}
+
+// split-K factor of the dW units for the pair kernel: fewest (rounds x longest unit), units costed in k-blocks
+static int pick_pair_splits(int dw_tiles, int dw_kblocks, int dx_units, int dx_kblocks, int pairs) {
+  int best = 1;
+  long best_cost = -1;
+  for (int s = 1; s <= 16 && s <= dw_kblocks; ++s) {
+    const int units = dw_tiles * s + dx_units;
+    const int rounds = (units + pairs - 1) / pairs;
+    const int dwk = (dw_kblocks + s - 1) / s;
+    const long unit = (dwk > dx_kblocks ? dwk : dx_kblocks) + 4;   // + epilogue, in k-block equivalents
+    const long cost = rounds * unit;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+  }
+  return best;
+}
+
+// CTA-pair (cta_group::2) variant: cluster of 2, units are 256-row pairs
+template <bool TF32>
+static int launch_bwd_pair(const void* dz, long long ldd, const void* x, long long ldx, const void* wb, long long ldw,
+                           const BwdFusedParams& p0, const DeviceInfo& di, cudaStream_t stream) {
+  using Cfg = BwdPairCfg<TF32>;
+  const int dtype = TF32 ? BAGS_DTYPE_F32 : BAGS_DTYPE_BF16;
+  CUtensorMap t_dzT, t_xT, t_dz, t_wT;
+  int rc;
+  if ((rc = make_tmap(&t_dzT, dz, dtype, p0.C, p0.Nr, ldd, Cfg::SLAB, Cfg::BLOCK_K, TF32))) return rc;
+  if ((rc = make_tmap(&t_xT, x, dtype, p0.Kf, p0.Nr, ldx, Cfg::SLAB, Cfg::BLOCK_K, TF32))) return rc;
+  if ((rc = make_tmap(&t_dz, dz, dtype, p0.C, p0.Nr, ldd, Cfg::BLOCK_K, Cfg::BLOCK_M))) return rc;
+  if ((rc = make_tmap(&t_wT, wb, dtype, p0.Kf, p0.C, ldw, Cfg::SLAB, Cfg::BLOCK_K, TF32))) return rc;
+  BwdFusedParams p = p0;
+  p.timing = g_timing;
+  auto kernel = bags_bwd_pair_kernel<TF32>;
+  BAGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  const int units = p.dw_units + p.dx_units;
+  const int max_pairs = pair_capacity<TF32>(di);
+  const int pairs = units < max_pairs ? units : max_pairs;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(Cfg::NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = env_int("BAGS_PDL", 1) ? 2 : 1;
+  BAGS_CUDA(cudaLaunchKernelEx(&cfg, kernel, t_dzT, t_xT, t_dz, t_wT, p));
+  return BAGS_OK;
+}
+
 static constexpr int kColsumTiles = 8;   // row groups of the bias-gradient partial sums made by bwd_prep
 
 extern "C" size_t bags_bwd_scratch_bytes(int C, long long ldw, int dtype) {
@@ -627,6 +706,19 @@ extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long 
     bp.colsum_tiles = cs_tiles;
     bp.db = db;
     const void* wb = want_scale ? wscratch : w;
+    if (env_int("BAGS_BWD_PAIR", 0)) {
+      // units are 256-row CTA pairs
+      bp.dw_m_tiles = (bp.dw_m_tiles + 1) / 2;
+      bp.dx_m_tiles = (bp.dx_m_tiles + 1) / 2;
+      const int cap = bf ? pair_capacity<false>(di) : pair_capacity<true>(di);
+      bp.dw_splits = env_int("BAGS_DW_SPLITS", pick_pair_splits(bp.dw_m_tiles * bp.dw_n_tiles, bp.dw_kblocks,
+                                                                bp.dx_m_tiles * bp.dx_n_tiles, bp.dx_kblocks, cap));
+      if (bp.dw_splits > bp.dw_kblocks) bp.dw_splits = bp.dw_kblocks;
+      bp.dw_units = bp.dw_m_tiles * bp.dw_n_tiles * bp.dw_splits;
+      bp.dx_units = bp.dx_m_tiles * bp.dx_n_tiles;
+      return bf ? launch_bwd_pair<false>(dz, ldd, x, ldx, wb, ldw, bp, di, stream)
+                : launch_bwd_pair<true>(dz, ldd, x, ldx, wb, ldw, bp, di, stream);
+    }
     return bf ? launch_bwd_merged<false>(dz, ldd, x, ldx, wb, ldw, bp, di, stream)
               : launch_bwd_merged<true>(dz, ldd, x, ldx, wb, ldw, bp, di, stream);
   }

@@ -297,4 +297,288 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
   if (threadIdx.x == 0) stamp(p.timing, 6);
 }
 
+
+// ======================================================================================================
+// CTA-pair variant (tcgen05 cta_group::2)
+// ======================================================================================================
+template <bool TF32>
+struct BwdPairCfg {
+  // CTA pair (cta_group::2): the MMA unit is 256 x 256; each CTA stages its own 128 A rows and HALF of the B
+  // tile, so a stage is 32 KB (6 stages) and every SM ingests a third less operand data per FLOP.
+  static constexpr int BLOCK_M = 128, BLOCK_N = 256, STAGES = 6, ACC_STAGES = 2;
+  static constexpr int HALF_B = BLOCK_N / 2;
+  static constexpr int ELT = TF32 ? 4 : 2;
+  static constexpr int BLOCK_K = 128 / ELT, UMMA_K = 32 / ELT, K_STEPS = BLOCK_K / UMMA_K;
+  static constexpr int SLAB = 128 / ELT;
+  static constexpr int A_BYTES = BLOCK_M * 128, B_BYTES = (BLOCK_N / 2) * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_WARPS = 8, EPI_BUF_BYTES = 32 * 128, EPI_STAGING_BYTES = EPI_WARPS * EPI_BUF_BYTES;
+  static constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGING_BYTES + 1024 + 256;
+  static_assert(SMEM_BYTES <= 232448, "exceeds shared memory");
+};
+
+template <bool TF32>
+__global__ void __launch_bounds__(64 + 32 * 8, 1)
+bags_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as MN-major A of dW  (box SLAB x BLOCK_K)
+                      const __grid_constant__ CUtensorMap tmap_xT,    // x  as MN-major B of dW  (box SLAB x BLOCK_K)
+                      const __grid_constant__ CUtensorMap tmap_dz,    // dz as K-major  A of dX  (box BLOCK_K x 128)
+                      const __grid_constant__ CUtensorMap tmap_wT,    // W' as MN-major B of dX  (box SLAB x BLOCK_K)
+                      const BwdFusedParams p) {
+  using Cfg = BwdPairCfg<TF32>;
+  constexpr int BLOCK_M = Cfg::BLOCK_M, BLOCK_N = Cfg::BLOCK_N, BLOCK_K = Cfg::BLOCK_K, STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+  uint8_t* smem_epi = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::EPI_STAGING_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + Cfg::ACC_STAGES;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * Cfg::ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = static_cast<int>(blockIdx.x & 1);   // position in the CTA pair (== %cluster_ctarank for 2x1x1 clusters)
+  const bool leader = (rank == 0);
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  if (threadIdx.x == 0) { stamp(p.timing, 0); if (p.timing) p.timing[blockIdx.x * 8 + 7] = sm_id(); }
+  pdl_trigger();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_dzT); tma_prefetch_desc(&tmap_xT); tma_prefetch_desc(&tmap_dz); tma_prefetch_desc(&tmap_wT);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+#pragma unroll
+    for (int a = 0; a < Cfg::ACC_STAGES; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 2 * Cfg::EPI_WARPS); }
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc_2sm(tmem_holder, 512); tmem_relinquish_2sm(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // peer barriers are live
+  const uint32_t tmem_base = *tmem_holder;
+  if (threadIdx.x == 0) stamp(p.timing, 1);
+
+  const int num_units = p.dw_units + p.dx_units;
+  // unit -> (kind, m0, n0, kb0, kb1, n_tile, split)
+  struct Unit { bool is_dw; int m_tile, n_tile, split, kb0, kb1; };
+  auto decode = [&](int u) -> Unit {
+    Unit r;
+    if (u < p.dw_units) {
+      r.is_dw = true;
+      const int per = p.dw_m_tiles * p.dw_n_tiles;
+      r.split = u / per;
+      const int t = u - r.split * per;
+      r.m_tile = t / p.dw_n_tiles;
+      r.n_tile = t - r.m_tile * p.dw_n_tiles;
+      const int base = p.dw_kblocks / p.dw_splits, rem = p.dw_kblocks % p.dw_splits;
+      r.kb0 = r.split * base + (r.split < rem ? r.split : rem);
+      r.kb1 = r.kb0 + base + (r.split < rem ? 1 : 0);
+    } else {
+      r.is_dw = false;
+      const int t = u - p.dw_units;
+      r.split = 0;
+      r.m_tile = t / p.dx_n_tiles;
+      r.n_tile = t - r.m_tile * p.dx_n_tiles;
+      r.kb0 = 0;
+      r.kb1 = p.dx_kblocks;
+    }
+    return r;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool waited = false;
+      for (int u = pair_id; u < num_units; u += num_pairs) {
+        const Unit un = decode(u);
+        // this CTA's 128 rows of the 256-row unit, and its half of the 256 B columns
+        const int m0 = (un.m_tile * 2 + rank) * BLOCK_M, n0 = un.n_tile * BLOCK_N + rank * Cfg::HALF_B;
+        if (!un.is_dw && !waited) { pdl_wait(); waited = true; }   // W' is written by bwd_prep
+        for (int kb = un.kb0; kb < un.kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          // all four loads of the pair are counted on the LEADER's barrier
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          const int k0 = kb * BLOCK_K;
+          uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
+          uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
+          if (un.is_dw) {
+#pragma unroll
+            for (int i = 0; i < BLOCK_M / Cfg::SLAB; ++i)
+              tma_load_2d_2sm(sa + i * (BLOCK_K * 128), &tmap_dzT, &full_bar[stage], m0 + i * Cfg::SLAB, k0);
+#pragma unroll
+            for (int i = 0; i < Cfg::HALF_B / Cfg::SLAB; ++i)
+              tma_load_2d_2sm(sb + i * (BLOCK_K * 128), &tmap_xT, &full_bar[stage], n0 + i * Cfg::SLAB, k0);
+          } else {
+            tma_load_2d_2sm(sa, &tmap_dz, &full_bar[stage], k0, m0);
+#pragma unroll
+            for (int i = 0; i < Cfg::HALF_B / Cfg::SLAB; ++i)
+              tma_load_2d_2sm(sb + i * (BLOCK_K * 128), &tmap_wT, &full_bar[stage], n0 + i * Cfg::SLAB, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== UMMA issuer (single thread) =====================
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc_dw = make_instr_desc(TF32 ? 2u : 1u, true, true, 2 * BLOCK_M, BLOCK_N);
+      constexpr uint32_t idesc_dx = make_instr_desc(TF32 ? 2u : 1u, false, true, 2 * BLOCK_M, BLOCK_N);
+      constexpr uint64_t MN_LAYOUT = TF32 ? kSwizzle128B_Base32B : kSwizzle128B;
+      constexpr uint32_t MN_LBO = BLOCK_K * 128, MN_SBO = TF32 ? 512 : 1024, MN_KSTEP = Cfg::UMMA_K * 128;
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int u = pair_id; u < num_units; u += num_pairs, ++local) {
+        const Unit un = decode(u);
+        const int acc = local % Cfg::ACC_STAGES;
+        const uint32_t acc_phase = (local / Cfg::ACC_STAGES) & 1u;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = un.kb0; kb < un.kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (local == 0 && kb == un.kb0) stamp(p.timing, 2);
+          const uint32_t sa = smem_u32(smem_a + stage * Cfg::A_BYTES);
+          const uint32_t sb = smem_u32(smem_b + stage * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < Cfg::K_STEPS; ++k) {
+            const uint64_t bdesc = make_smem_desc(sb + k * MN_KSTEP, MN_LBO, MN_SBO, MN_LAYOUT);
+            const uint32_t accum = (kb > un.kb0 || k > 0) ? 1u : 0u;
+            if (un.is_dw) {
+              const uint64_t adesc = make_smem_desc(sa + k * MN_KSTEP, MN_LBO, MN_SBO, MN_LAYOUT);
+              if (TF32) umma_tf32_2sm(d_tmem, adesc, bdesc, idesc_dw, accum);
+              else      umma_bf16_2sm(d_tmem, adesc, bdesc, idesc_dw, accum);
+            } else {
+              const uint64_t adesc = make_smem_desc(sa + k * 32, 16, 1024, kSwizzle128B);
+              if (TF32) umma_tf32_2sm(d_tmem, adesc, bdesc, idesc_dx, accum);
+              else      umma_bf16_2sm(d_tmem, adesc, bdesc, idesc_dx, accum);
+            }
+          }
+          umma_commit_2sm_mc(&empty_bar[stage], 0x3);   // frees the slot in both CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm_mc(&tfull_bar[acc], 0x3);       // both CTAs' epilogues may read their 128 rows
+        if (local == 0) stamp(p.timing, 3);
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    uint8_t* buf = smem_epi + (warp - 2) * Cfg::EPI_BUF_BYTES;
+    constexpr int HALF_N = BLOCK_N / 2;
+    bool waited = false;
+    int local = 0;
+    for (int u = pair_id; u < num_units; u += num_pairs, ++local) {
+      const Unit un = decode(u);
+      const int m_warp = (un.m_tile * 2 + rank) * BLOCK_M + quarter * 32;
+      const int m = m_warp + lane;
+      const int n0 = un.n_tile * BLOCK_N;
+      const int acc = local % Cfg::ACC_STAGES;
+      const uint32_t acc_phase = (local / Cfg::ACC_STAGES) & 1u;
+      const int Mrows = un.is_dw ? p.C : p.Nr;
+
+      float scale = 1.0f;
+      if (un.is_dw) {
+        if (!waited) { pdl_wait(); waited = true; }   // dW was zeroed / column-sum partials were made by bwd_prep
+        scale = 0.f;
+        if (m < p.C) {
+          if (p.gscale == nullptr) scale = 1.0f;
+          else {
+#pragma unroll
+            for (int g = 0; g < kMaxGroups; ++g)
+              if (g < p.G && m >= p.gstart[g] && m < p.gstart[g] + p.glen[g]) scale = __ldg(p.gscale + g);
+          }
+          if (p.db != nullptr && un.n_tile == 0 && un.split == 0 && half == 0) {
+            float cs = 0.f;
+            for (int tt = 0; tt < p.colsum_tiles; ++tt) cs += __ldg(p.colsum_in + static_cast<long long>(tt) * p.C + m);
+            p.db[m] = scale * cs;
+          }
+        }
+      }
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      if (local == 0 && warp == 2 && lane == 0) stamp(p.timing, 4);
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+      const bool out_bf16 = (!un.is_dw) && !TF32;
+      const int epi_cols = out_bf16 ? 64 : 32;
+#pragma unroll 1
+      for (int c = half * HALF_N; c < (half + 1) * HALF_N; c += epi_cols) {
+        const int n = n0 + c;
+        if (n >= p.Kf) break;
+        uint32_t v[32];
+        uint32_t v2[32];
+        tmem_ld_32x32b_x32(t_row + c, v);
+        if (out_bf16) tmem_ld_32x32b_x32(t_row + c + 32, v2);
+        tmem_ld_wait();
+        uint4* rowp = reinterpret_cast<uint4*>(buf + lane * 128);
+        if (out_bf16) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t* src = (j < 4) ? (v + 8 * j) : (v2 + 8 * (j - 4));
+            uint4 r;
+            r.x = pack_bf16x2(__uint_as_float(src[0]), __uint_as_float(src[1]));
+            r.y = pack_bf16x2(__uint_as_float(src[2]), __uint_as_float(src[3]));
+            r.z = pack_bf16x2(__uint_as_float(src[4]), __uint_as_float(src[5]));
+            r.w = pack_bf16x2(__uint_as_float(src[6]), __uint_as_float(src[7]));
+            rowp[j ^ (lane & 7)] = r;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 r;
+            r.x = __uint_as_float(v[4 * j + 0]) * scale; r.y = __uint_as_float(v[4 * j + 1]) * scale;
+            r.z = __uint_as_float(v[4 * j + 2]) * scale; r.w = __uint_as_float(v[4 * j + 3]) * scale;
+            rowp[j ^ (lane & 7)] = *reinterpret_cast<uint4*>(&r);
+          }
+        }
+        __syncwarp();
+        const int vec = out_bf16 ? 8 : 4;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + (lane >> 3);
+          const int ch = lane & 7;
+          const uint4 val = *reinterpret_cast<const uint4*>(buf + r * 128 + ((ch ^ (r & 7)) << 4));
+          const int gm = m_warp + r;
+          const int gn = n + ch * vec;
+          if (gm < Mrows && gn + vec <= p.Kf) {
+            if (un.is_dw) {
+              red_add_v4_f32(p.dW + static_cast<long long>(gm) * p.lddw + gn, __uint_as_float(val.x), __uint_as_float(val.y),
+                             __uint_as_float(val.z), __uint_as_float(val.w));
+            } else if (out_bf16) {
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.dX) + static_cast<long long>(gm) * p.lddx + gn) = val;
+            } else {
+              *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.dX) + static_cast<long long>(gm) * p.lddx + gn) = val;
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+      if (local == 0 && warp == 2 && lane == 0) stamp(p.timing, 5);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  // the peer may still be reading this CTA's shared memory / signalling its barriers
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+  if (threadIdx.x == 0) stamp(p.timing, 6);
+}
+
 }  // namespace bags

@@ -285,6 +285,10 @@ def case_timeline(name):
     dX = torch.empty(N, 1024, device='cuda', dtype=torch.bfloat16)
     run('gemm_dX_256', lambda: ops.fused_bwd(dz, xc, wc, None, dt, colsum, need_dw=False, need_db=False, dX=dX), 128)
     run('gemm_dW_256_split3', lambda: ops.fused_bwd(dz, xc, wc, None, dt, colsum, need_dx=False, dW=dW), 120)
+    ws = ops.bwd_scratch(wc)
+    gout = torch.ones(5, device='cuda')
+    run('bwd_merged (s2=first data, s3=unit0 mma issued, s4=unit0 acc done, s5=unit0 epi done)',
+        lambda: ops.fused_bwd(dz, xc, wc, gout, dt, colsum, dW=dW, dX=dX, wscratch=ws), 148)
     run('fused_fwd (s3=acc done, s4=passA, s5=xchg barrier, end=passC...)',
         lambda: ops.fused_fwd(xc, wc, bc, lc, dt, wmask, avg), 128)
     return res
