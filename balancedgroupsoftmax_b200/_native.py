@@ -12,7 +12,8 @@ import threading
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libbags_b200.so')
+# BAGS_LIB: development hook to A/B two builds of the same ABI inside one GPU session
+LIB_PATH = os.environ.get('BAGS_LIB') or os.path.join(_HERE, 'libbags_b200.so')
 
 ABI_VERSION = 1
 DTYPE_F32 = 0

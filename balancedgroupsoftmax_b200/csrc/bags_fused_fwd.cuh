@@ -11,12 +11,19 @@
 // through distributed shared memory; after one cluster barrier every thread combines the four
 // partials into the bin's log-sum-exp and makes a second pass over its TMEM columns:
 //
-//   pass A  (after the mainloop):  per bin segment, online (max, sum exp(z - max))
+//   bias -> TMEM before the first MMA (the accumulators start at b, so the epilogue never adds it)
+//   pass A  (after the mainloop):  per bin segment, online (max, sum exp(z - max)); the exponentials
+//            e = exp(z - m_chunk) are written back over z in TMEM, m_chunk (the running max they refer to)
+//            goes to shared memory (two floats per thread and chunk)
 //   exchange + barrier.cluster
-//   pass C:  p = exp(z - lse_bin) ; dz~ = w/avg * (p - onehot)  -> bf16/fp32 -> swizzled smem
-//            -> transposed, fully coalesced 16-byte stores ; column sums of dz~ (bias gradient) from the
-//            staged tile ;
+//   pass C:  dz~ = e * [ w/avg * exp(m_chunk - lse_bin) ] - onehot * w/avg : one MUFU per chunk instead of
+//            one per element  -> bf16/fp32 -> swizzled smem -> transposed, fully coalesced 16-byte stores ;
+//            column sums of dz~ (bias gradient) from the staged tile ;
 //            loss_bin += w/avg * -log p[target]
+//
+// Costs that shaped this (profiles/README.md): TMEM reads run at ~64 B/clk/SM (1.3 us per pass over the
+// 128 x 320 fp32 tile), MUFU at 4 lanes/clk per sub-partition, and the first version spent ~45 issue slots
+// per element on bin lookups, bias adds and generic-address shared loads.
 //
 // reference semantics: gs_bbox_head_with0.py:91-112 (labels/weights), :134-171 (slices + CE),
 // cross_entropy_loss.py:9-19, losses/utils.py:26-53 (sum / avg_factor).
@@ -78,11 +85,15 @@ struct FusedCfg {
   static constexpr int LOC_BYTES = CGROUPS * MAXG * BLOCK_M * 8;   // CTA-local partials of the 4 column groups
   static constexpr int DZ_ROW_BYTES = CH * (TF32 ? 4 : 2);         // one staged row of a chunk: 64 B / 32 B
   static constexpr int DZ_BUF_BYTES = 2048;                        // per-warp staging buffer (32 rows)
+  static constexpr int META_BYTES = CGROUPS * 8 * 16;             // chunk table per column group (int4 per chunk)
   static constexpr int MISC_BYTES = BLOCK_N * 4 /*bias*/ + 2 * MAXG * BLOCK_M * 4 /*tcol, coef*/ +
-                                    BLOCK_N * 4 /*colsum*/ + 64 /*loss*/ + 256 /*barriers*/;
+                                    BLOCK_N * 4 /*colsum*/ + 64 /*loss*/ + META_BYTES + 256 /*barriers*/;
+  // after the mainloop the pipeline stages are idle: [0, 32 KB) stages the dz tiles, then the chunk references
+  static constexpr int REF_OFFSET = EPI_WARPS * DZ_BUF_BYTES;
+  static constexpr int REF_BYTES = CHUNKS * 32 * EPI_WARPS * 8;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + XCH_BYTES + LOC_BYTES + MISC_BYTES + 1024;
   static_assert(SMEM_BYTES <= 232448, "fused forward exceeds shared memory");
-  static_assert(EPI_WARPS * DZ_BUF_BYTES <= STAGES * STAGE_BYTES, "staging must fit in the idle pipeline buffers");
+  static_assert(REF_OFFSET + REF_BYTES <= STAGES * STAGE_BYTES, "staging + references must fit in the idle pipeline buffers");
   static_assert(32 * DZ_ROW_BYTES <= DZ_BUF_BYTES, "staging buffer too small");
 };
 
@@ -118,7 +129,7 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   constexpr int MAXG = Cfg::MAXG, CH = Cfg::CH;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1 KB aligned, still a shared-space pointer
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
   float2* xch = reinterpret_cast<float2*>(smem + STAGES * Cfg::STAGE_BYTES);                 // [4 ranks][MAXG][128]
@@ -128,11 +139,13 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   float* s_coef = reinterpret_cast<float*>(s_tcol + MAXG * BLOCK_M);  // [MAXG][128] w / avg
   float* s_colsum = s_coef + MAXG * BLOCK_M;                          // [320]
   float* s_loss = s_colsum + BLOCK_N;                                 // [8]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_loss + 16);
+  int4* s_meta = reinterpret_cast<int4*>(s_loss + 16);                // [CGROUPS][8] (gA, bpos, gB, hiB) per chunk
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_meta) + Cfg::META_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint64_t* bias_bar = bars + 2 * STAGES + 1;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
   __shared__ bool s_last;
   __shared__ int s_gs[kMaxG], s_ge[kMaxG];   // bin start / end, for runtime-indexed access
 
@@ -151,6 +164,7 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(tfull_bar, 1);
+    mbar_init(bias_bar, Cfg::EPI_WARPS);
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_holder, 512); tmem_relinquish(); }
@@ -222,6 +236,8 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       constexpr uint32_t idesc = make_instr_desc(TF32 ? 2u : 1u, false, false, BLOCK_M, Cfg::UMMA_N);
       int stage = 0;
       uint32_t phase = 0;
+      mbar_wait(bias_bar, 0);   // the accumulators were preset to the bias by the epilogue warps
+      tc_fence_after();
       for (int kb = 0; kb < p.kblocks; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
@@ -234,9 +250,8 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const uint64_t bdesc = make_smem_desc(sb + h * Cfg::UMMA_N * 128 + k * 32, 16, 1024);
-            const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
-            if (TF32) umma_tf32(tmem_base + h * Cfg::UMMA_N, adesc, bdesc, idesc, accum);
-            else      umma_bf16(tmem_base + h * Cfg::UMMA_N, adesc, bdesc, idesc, accum);
+            if (TF32) umma_tf32(tmem_base + h * Cfg::UMMA_N, adesc, bdesc, idesc, 1u);
+            else      umma_bf16(tmem_base + h * Cfg::UMMA_N, adesc, bdesc, idesc, 1u);
           }
         }
         umma_commit(&empty_bar[stage]);
@@ -246,6 +261,44 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     }
     __syncwarp();
   } else {
+    // ===================== epilogue, part 0: accumulators := bias, chunk table ===================
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c_cg;
+    {
+#pragma unroll 1
+      for (int ci = 0; ci < Cfg::CHUNKS; ++ci) {
+        uint32_t bv[CH];
+#pragma unroll
+        for (int j = 0; j < CH; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c_cg + ci * CH + j]);
+          bv[j + 0] = __float_as_uint(b4.x); bv[j + 1] = __float_as_uint(b4.y);
+          bv[j + 2] = __float_as_uint(b4.z); bv[j + 3] = __float_as_uint(b4.w);
+        }
+        tmem_st_32x32b_x16(t_row + ci * CH, bv);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bias_bar);
+    }
+    // per-chunk bin layout of this warp's 80 columns (warp-uniform): columns [0,bpos) of the chunk belong to
+    // bin gA, [bpos,hiB) to bin gB (or to no bin); gA = -1 marks a chunk beyond the last logit column
+    if (lane < Cfg::CHUNKS) {
+      const int col0 = col_lo + lane * CH;
+      int gA = -1, bpos = 0, gB = -1, hiB = 0;
+      if (col0 < p.C) {
+        gA = bin_of(col0);
+        const int endA = bin_end(gA);
+        bpos = (endA - col0 < CH) ? (endA - col0) : CH;
+        hiB = bpos;
+        if (bpos < CH) {
+          gB = bin_of(col0 + bpos);
+          if (gB >= 0) { const int endB = bin_end(gB); hiB = (endB - col0 < CH) ? (endB - col0) : CH; }
+        }
+      }
+      s_meta[cg * 8 + lane] = make_int4(gA, bpos, gB, hiB);   // the 4 quarters write identical values
+    }
+    __syncwarp();
+
     // ===================== epilogue, part 1: row info (overlaps the mainloop) + pass A ==========
     pdl_wait();   // masks / avg come from the preceding sampler kernel (programmatic dependent launch)
     if (cg == 0) {
@@ -269,50 +322,28 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
     if (warp == 2 && lane == 0) stamp(p.timing, 3);   // accumulators complete
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c_cg;
+    float2* refs = reinterpret_cast<float2*>(smem + Cfg::REF_OFFSET) + (threadIdx.x - 64);   // [chunk][512 threads]
     {
       int g_cur = -2;
       float m_cur = -INFINITY, s_cur = 0.f;
       auto flush = [&]() {
         if (g_cur >= 0) loc[(cg * MAXG + g_cur) * BLOCK_M + row_l] = make_float2(m_cur, s_cur);
       };
-      // online update of (m_cur, s_cur) with elements j in [lo, hi) of z[CH]
-      auto accum = [&](const float (&z)[CH], int lo, int hi) {
-        float cm = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < CH; ++j) cm = fmaxf(cm, (j >= lo && j < hi) ? z[j] : -INFINITY);
-        const float m_new = fmaxf(m_cur, cm);
-        const float mb = m_new * kLog2e;
-        float acc = 0.f;
-#pragma unroll
-        for (int j = 0; j < CH; ++j) {
-          const float e = fast_exp2(fmaf(z[j], kLog2e, -mb));
-          acc += (j >= lo && j < hi) ? e : 0.f;
-        }
-        const float resc = (m_cur == -INFINITY) ? 0.f : fast_exp2((m_cur - m_new) * kLog2e);
-        s_cur = s_cur * resc + acc;
-        m_cur = m_new;
-      };
       uint32_t v[CH];
       if (col_lo < p.C) tmem_ld_32x32b_x16(t_row, v);   // software pipeline: chunk ci+1 is in flight
 #pragma unroll 1                                           // while chunk ci is reduced
       for (int ci = 0; ci < Cfg::CHUNKS; ++ci) {
-        const int col0 = col_lo + ci * CH;
-        if (col0 >= p.C) break;
+        const int4 md = s_meta[cg * 8 + ci];
+        if (md.x < 0) break;
         tmem_ld_wait();
         float z[CH];
 #pragma unroll
-        for (int j = 0; j < CH; j += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c_cg + ci * CH + j]);
-          z[j + 0] = __uint_as_float(v[j + 0]) + b4.x; z[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-          z[j + 2] = __uint_as_float(v[j + 2]) + b4.z; z[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
-        }
-        if (ci + 1 < Cfg::CHUNKS && col0 + CH < p.C) tmem_ld_32x32b_x16(t_row + (ci + 1) * CH, v);
-        const int gA = bin_of(col0);
-        const int endA = bin_end(gA);
-        const int bpos = (endA - col0 < CH) ? (endA - col0) : CH;   // columns [0,bpos) belong to gA
-        if (gA != g_cur) { flush(); g_cur = gA; m_cur = -INFINITY; s_cur = 0.f; }
-        if (bpos >= CH) {
+        for (int j = 0; j < CH; ++j) z[j] = __uint_as_float(v[j]);
+        if (ci + 1 < Cfg::CHUNKS && col_lo + (ci + 1) * CH < p.C) tmem_ld_32x32b_x16(t_row + (ci + 1) * CH, v);
+        if (md.x != g_cur) { flush(); g_cur = md.x; m_cur = -INFINITY; s_cur = 0.f; }
+        uint32_t e[CH];
+        float refA, refB = 0.f;
+        if (md.y >= CH) {
           // fast path: the whole chunk is one bin
           float c4[4] = {z[0], z[1], z[2], z[3]};
 #pragma unroll
@@ -322,40 +353,60 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           const float mb = m_new * kLog2e;
           float a4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int j = 0; j < CH; ++j) a4[j & 3] += fast_exp2(fmaf(z[j], kLog2e, -mb));
-          const float acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
-          const float resc = (m_cur == -INFINITY) ? 0.f : fast_exp2((m_cur - m_new) * kLog2e);
-          s_cur = s_cur * resc + acc;
-          m_cur = m_new;
-        } else {
-          accum(z, 0, bpos);
-          const int gB = bin_of(col0 + bpos);     // -1 beyond the last logit column
-          flush();
-          g_cur = gB; m_cur = -INFINITY; s_cur = 0.f;
-          if (gB >= 0) {
-            const int endB = bin_end(gB);
-            const int hiB = (endB - col0 < CH) ? (endB - col0) : CH;
-            accum(z, bpos, hiB);
+          for (int j = 0; j < CH; ++j) {
+            const float ej = fast_exp2(fmaf(z[j], kLog2e, -mb));
+            a4[j & 3] += ej;
+            e[j] = __float_as_uint(ej);
           }
+          const float acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+          s_cur = s_cur * fast_exp2((m_cur - m_new) * kLog2e) + acc;   // 2^-inf = 0 on the first chunk of a bin
+          m_cur = m_new;
+          refA = m_new;
+        } else {
+          // two segments: [0,bpos) continues bin gA, [bpos,hiB) opens bin gB
+          const int bpos = md.y, hiB = md.w;
+          float cmA = -INFINITY, cmB = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            if (j < bpos) cmA = fmaxf(cmA, z[j]);
+            else if (j < hiB) cmB = fmaxf(cmB, z[j]);
+          }
+          const float m_newA = fmaxf(m_cur, cmA);
+          const float mbA = m_newA * kLog2e, mbB = cmB * kLog2e;
+          float accA = 0.f, accB = 0.f;
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            float ej = 0.f;
+            if (j < bpos) { ej = fast_exp2(fmaf(z[j], kLog2e, -mbA)); accA += ej; }
+            else if (j < hiB) { ej = fast_exp2(fmaf(z[j], kLog2e, -mbB)); accB += ej; }
+            e[j] = __float_as_uint(ej);
+          }
+          s_cur = s_cur * fast_exp2((m_cur - m_newA) * kLog2e) + accA;
+          m_cur = m_newA;
+          flush();
+          g_cur = md.z; m_cur = cmB; s_cur = accB;
+          refA = m_newA; refB = cmB;
         }
+        tmem_st_32x32b_x16(t_row + ci * CH, e);
+        refs[ci * (32 * Cfg::EPI_WARPS)] = make_float2(refA, refB);
       }
       flush();
+      tmem_st_wait();
     }
     // ---- CTA-local combine of the 4 column groups, then publish to the 4 CTAs of the cluster ----
+    // (bins are dealt round-robin to the column groups so that all 16 warps share the work)
     named_bar_sync(1, 32 * Cfg::EPI_WARPS);
-    if (cg == 0) {
-      for (int g = 0; g < G; ++g) {
-        float2 q[Cfg::CGROUPS];
+    for (int g = cg; g < G; g += Cfg::CGROUPS) {
+      float2 q[Cfg::CGROUPS];
 #pragma unroll
-        for (int i = 0; i < Cfg::CGROUPS; ++i) q[i] = loc[(i * MAXG + g) * BLOCK_M + row_l];
-        const float M = fmaxf(fmaxf(q[0].x, q[1].x), fmaxf(q[2].x, q[3].x));
-        float S = 0.f;
+      for (int i = 0; i < Cfg::CGROUPS; ++i) q[i] = loc[(i * MAXG + g) * BLOCK_M + row_l];
+      const float M = fmaxf(fmaxf(q[0].x, q[1].x), fmaxf(q[2].x, q[3].x));
+      float S = 0.f;
 #pragma unroll
-        for (int i = 0; i < Cfg::CGROUPS; ++i) S += (q[i].x == -INFINITY) ? 0.f : q[i].y * fast_exp2((q[i].x - M) * kLog2e);
-        const uint32_t addr = smem_u32(&xch[(static_cast<int>(rank) * MAXG + g) * BLOCK_M + row_l]);
+      for (int i = 0; i < Cfg::CGROUPS; ++i) S += (q[i].x == -INFINITY) ? 0.f : q[i].y * fast_exp2((q[i].x - M) * kLog2e);
+      const uint32_t addr = smem_u32(&xch[(static_cast<int>(rank) * MAXG + g) * BLOCK_M + row_l]);
 #pragma unroll
-        for (uint32_t r = 0; r < 4; ++r) st_cluster_f2(addr, r, M, S);
-      }
+      for (uint32_t r = 0; r < 4; ++r) st_cluster_f2(addr, r, M, S);
     }
   }
 
@@ -368,7 +419,25 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     // ===================== epilogue, part 2: combine + pass C =====================================
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c_cg;
     uint8_t* buf = smem + ew * Cfg::DZ_BUF_BYTES;   // aliases the (now idle) pipeline stages
+    const float2* refs = reinterpret_cast<const float2*>(smem + Cfg::REF_OFFSET) + (threadIdx.x - 64);
     const int m_warp = m0 + quarter * 32;
+    tc_fence_after();
+
+    // transposed stores: the rows / 16-byte columns this lane writes for every chunk, and whether it may
+    constexpr int ST_ITERS = TF32 ? 4 : 2;            // 16-byte stores per lane and chunk
+    constexpr int ST_ROWS = 32 / ST_ITERS;            // rows covered by one warp-wide store
+    constexpr int ST_CHN = TF32 ? 4 : 2;              // 16-byte pieces per staged row
+    constexpr int ST_ELT = TF32 ? 4 : 2;
+    const int st_r0 = lane / ST_CHN, st_ch = lane % ST_CHN;
+    uint8_t* st_ptr[ST_ITERS];
+    bool st_ok[ST_ITERS];
+#pragma unroll
+    for (int it = 0; it < ST_ITERS; ++it) {
+      const int r = it * ST_ROWS + st_r0;
+      st_ok[it] = p.want_dz && (m_warp + r < p.N) && !(p.dbg & 1);
+      st_ptr[it] = reinterpret_cast<uint8_t*>(p.dz) +
+                   (static_cast<long long>(m_warp + r) * p.ldd + col_lo) * ST_ELT + st_ch * 16;
+    }
 
     int g_cur = -2;
     float lb_cur = 0.f, coef_cur = 0.f, pt_cur = 1.0f;
@@ -406,65 +475,61 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     if (col_lo < p.C) tmem_ld_32x32b_x16(t_row, v);
 #pragma unroll 1
     for (int ci = 0; ci < Cfg::CHUNKS; ++ci) {
+      const int4 md = s_meta[cg * 8 + ci];
+      if (md.x < 0) break;
       const int col0 = col_lo + ci * CH;
-      if (col0 >= p.C) break;
+      const float2 rf = refs[ci * (32 * Cfg::EPI_WARPS)];
       tmem_ld_wait();
       float d[CH];
 #pragma unroll
-      for (int j = 0; j < CH; j += 4) {
-        const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c_cg + ci * CH + j]);
-        d[j + 0] = __uint_as_float(v[j + 0]) + b4.x; d[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-        d[j + 2] = __uint_as_float(v[j + 2]) + b4.z; d[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
-      }
-      // next chunk's TMEM load overlaps the exp / pack / store phases of this one
+      for (int j = 0; j < CH; ++j) d[j] = __uint_as_float(v[j]);   // e = exp(z - m_chunk) from pass A
+      // next chunk's TMEM load overlaps the scale / pack / store phases of this one
       if (ci + 1 < Cfg::CHUNKS && col0 + CH < p.C) tmem_ld_32x32b_x16(t_row + (ci + 1) * CH, v);
-      const int gA = bin_of(col0);
-      const int endA = bin_end(gA);
-      const int bpos = (endA - col0 < CH) ? (endA - col0) : CH;
-      if (gA != g_cur) { finish_bin(); start_bin(gA); }
-      if (bpos >= CH) {
+      if (md.x != g_cur) { finish_bin(); start_bin(md.x); }
+      if (md.y >= CH) {
+        const float f = fast_exp2(fmaf(rf.x, kLog2e, -lb_cur));   // exp(m_chunk - lse)
+        const float gf = coef_cur * f;
         const int tq = tcol_cur - col0;
         // most chunks contain no row's target column ("others" targets sit in each bin's first column):
         // a warp vote selects the loop without the per-element one-hot handling
         if (__any_sync(0xffffffffu, tq >= 0 && tq < CH)) {
 #pragma unroll
           for (int j = 0; j < CH; ++j) {
-            const float pj = fast_exp2(fmaf(d[j], kLog2e, -lb_cur));
-            float dj = coef_cur * pj;
-            if (j == tq) { pt_cur = pj; dj -= coef_cur; }
+            float dj = d[j] * gf;
+            if (j == tq) { pt_cur = d[j] * f; dj -= coef_cur; }
             d[j] = dj;
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < CH; ++j) d[j] = coef_cur * fast_exp2(fmaf(d[j], kLog2e, -lb_cur));
+          for (int j = 0; j < CH; ++j) d[j] *= gf;
         }
       } else {
+        const int bpos = md.y, hiB = md.w;
         {
+          const float f = fast_exp2(fmaf(rf.x, kLog2e, -lb_cur));
+          const float gf = coef_cur * f;
           const int tq = tcol_cur - col0;
 #pragma unroll
           for (int j = 0; j < CH; ++j) {
             if (j < bpos) {
-              const float pj = fast_exp2(fmaf(d[j], kLog2e, -lb_cur));
-              float dj = coef_cur * pj;
-              if (j == tq) { pt_cur = pj; dj -= coef_cur; }
+              float dj = d[j] * gf;
+              if (j == tq) { pt_cur = d[j] * f; dj -= coef_cur; }
               d[j] = dj;
             }
           }
         }
-        const int gB = bin_of(col0 + bpos);
         finish_bin();
-        start_bin(gB);
-        const int endB = (gB >= 0) ? bin_end(gB) : 0;
-        const int hiB = (gB >= 0) ? ((endB - col0 < CH) ? (endB - col0) : CH) : 0;
+        start_bin(md.z);
+        const float f = (md.z >= 0) ? fast_exp2(fmaf(rf.y, kLog2e, -lb_cur)) : 0.f;
+        const float gf = coef_cur * f;
         const int tq = tcol_cur - col0;
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
           if (j >= bpos) {
             float dj = 0.f;
             if (j < hiB) {
-              const float pj = fast_exp2(fmaf(d[j], kLog2e, -lb_cur));
-              dj = coef_cur * pj;
-              if (j == tq) { pt_cur = pj; dj -= coef_cur; }
+              dj = d[j] * gf;
+              if (j == tq) { pt_cur = d[j] * f; dj -= coef_cur; }
             }
             d[j] = dj;
           }
@@ -482,11 +547,10 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           }
           __syncwarp();
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int r = it * 8 + (lane >> 2), ch = lane & 3;
-            const uint4 val = *reinterpret_cast<const uint4*>(buf + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4));
-            if (m_warp + r < p.N && !(p.dbg & 1))
-              *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.dz) + static_cast<long long>(m_warp + r) * p.ldd + col0 + ch * 4) = val;
+          for (int it = 0; it < ST_ITERS; ++it) {
+            const int r = it * ST_ROWS + st_r0;
+            const uint4 val = *reinterpret_cast<const uint4*>(buf + r * 64 + ((st_ch ^ ((r >> 1) & 3)) << 4));
+            if (st_ok[it]) *reinterpret_cast<uint4*>(st_ptr[it] + ci * (CH * ST_ELT)) = val;
           }
         } else {
           uint4* rowp = reinterpret_cast<uint4*>(buf + lane * 32);
@@ -499,11 +563,10 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           }
           __syncwarp();
 #pragma unroll
-          for (int it = 0; it < 2; ++it) {
-            const int r = it * 16 + (lane >> 1), ch = lane & 1;
-            const uint4 val = *reinterpret_cast<const uint4*>(buf + r * 32 + ((ch ^ ((r >> 2) & 1)) << 4));
-            if (m_warp + r < p.N && !(p.dbg & 1))
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.dz) + static_cast<long long>(m_warp + r) * p.ldd + col0 + ch * 8) = val;
+          for (int it = 0; it < ST_ITERS; ++it) {
+            const int r = it * ST_ROWS + st_r0;
+            const uint4 val = *reinterpret_cast<const uint4*>(buf + r * 32 + ((st_ch ^ ((r >> 2) & 1)) << 4));
+            if (st_ok[it]) *reinterpret_cast<uint4*>(st_ptr[it] + ci * (CH * ST_ELT)) = val;
           }
         }
         // optional bias-gradient column sums from the staged tile: lanes l and l+16 share column l % 16
