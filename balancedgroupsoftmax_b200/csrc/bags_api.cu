@@ -488,6 +488,7 @@ extern "C" int bags_fwd(const void* x, long long ldx, const void* w, long long l
     if (colsum != nullptr) BAGS_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * C * colsum_tiles, stream));
     return BAGS_OK;
   }
+  if (bias != nullptr) BAGS_REQUIRE((reinterpret_cast<uintptr_t>(bias) & 15) == 0, "bags_fwd: bias must be 16-byte aligned");
   const int grid = 4 * ((N + 127) / 128);
   BAGS_REQUIRE(grid <= 4096, "bags_fwd: N=%d too large for the fused path's loss workspace", N);
   FusedFwdParams p{};
@@ -716,6 +717,9 @@ extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long 
       if (bp.dw_splits > bp.dw_kblocks) bp.dw_splits = bp.dw_kblocks;
       bp.dw_units = bp.dw_m_tiles * bp.dw_n_tiles * bp.dw_splits;
       bp.dx_units = bp.dx_m_tiles * bp.dx_n_tiles;
+      const int only = env_int("BAGS_PAIR_ONLY", 0);   // timing experiments: 1 = dW units only, 2 = dX units only
+      if (only == 1) bp.dx_units = 0;
+      if (only == 2) bp.dw_units = 0;
       return bf ? launch_bwd_pair<false>(dz, ldd, x, ldx, wb, ldw, bp, di, stream)
                 : launch_bwd_pair<true>(dz, ldd, x, ldx, wb, ldw, bp, di, stream);
     }

@@ -305,7 +305,10 @@ template <bool TF32>
 struct BwdPairCfg {
   // CTA pair (cta_group::2): the MMA unit is 256 x 256; each CTA stages its own 128 A rows and HALF of the B
   // tile, so a stage is 32 KB (6 stages) and every SM ingests a third less operand data per FLOP.
-  static constexpr int BLOCK_M = 128, BLOCK_N = 256, STAGES = 6, ACC_STAGES = 2;
+#ifndef BAGS_PAIR_STAGES
+#define BAGS_PAIR_STAGES 6
+#endif
+  static constexpr int BLOCK_M = 128, BLOCK_N = 256, STAGES = BAGS_PAIR_STAGES, ACC_STAGES = 2;
   static constexpr int HALF_B = BLOCK_N / 2;
   static constexpr int ELT = TF32 ? 4 : 2;
   static constexpr int BLOCK_K = 128 / ELT, UMMA_K = 32 / ELT, K_STEPS = BLOCK_K / UMMA_K;
@@ -451,6 +454,16 @@ bags_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as MN
           for (int k = 0; k < Cfg::K_STEPS; ++k) {
             const uint64_t bdesc = make_smem_desc(sb + k * MN_KSTEP, MN_LBO, MN_SBO, MN_LAYOUT);
             const uint32_t accum = (kb > un.kb0 || k > 0) ? 1u : 0u;
+#ifdef BAGS_X_PAIR_KMAJOR   // timing experiment only (wrong results): both operands read as K-major tiles
+            {
+              constexpr uint32_t idesc_kk = make_instr_desc(TF32 ? 2u : 1u, false, false, 2 * BLOCK_M, BLOCK_N);
+              const uint64_t ad = make_smem_desc(sa + k * 32, 16, 1024, kSwizzle128B);
+              const uint64_t bd = make_smem_desc(sb + k * 32, 16, 1024, kSwizzle128B);
+              if (TF32) umma_tf32_2sm(d_tmem, ad, bd, idesc_kk, accum);
+              else      umma_bf16_2sm(d_tmem, ad, bd, idesc_kk, accum);
+              continue;
+            }
+#endif
             if (un.is_dw) {
               const uint64_t adesc = make_smem_desc(sa + k * MN_KSTEP, MN_LBO, MN_SBO, MN_LAYOUT);
               if (TF32) umma_tf32_2sm(d_tmem, adesc, bdesc, idesc_dw, accum);

@@ -97,6 +97,12 @@ struct FusedCfg {
   static_assert(32 * DZ_ROW_BYTES <= DZ_BUF_BYTES, "staging buffer too small");
 };
 
+__device__ __forceinline__ void cluster_arrive() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void cluster_arrive_wait() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -112,12 +118,44 @@ __device__ __forceinline__ void st_cluster_f2(uint32_t local_smem_addr, uint32_t
 }
 // single-MUFU 2^x (ex2.approx.ftz, ~2 ulp): the inputs are <= 0 after max subtraction
 __device__ __forceinline__ float fast_exp2(float x) {
+#ifdef BAGS_X_NOMUFU   // timing experiment only: wrong results
+  return x * 0.5f;
+#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
+#ifdef BAGS_X_NOTMEMLD   // timing experiment only: wrong results
+#define BAGS_TMEM_LD16(addr, regs) do { } while (0)
+#else
+#define BAGS_TMEM_LD16(addr, regs) tmem_ld_32x32b_x16(addr, regs)
+#endif
+#ifdef BAGS_X_NOTMEMST
+#define BAGS_TMEM_ST16(addr, regs) do { asm volatile("" :: "r"(regs[0]), "r"(regs[5]), "r"(regs[15])); } while (0)
+#else
+#define BAGS_TMEM_ST16(addr, regs) tmem_st_32x32b_x16(addr, regs)
+#endif
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {   // arrive without waiting
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// 8-byte store into the shared memory of CTA `rank` of the cluster that also credits 8 bytes to that CTA's
+// mbarrier: the receiver just waits on its own barrier, no cluster-wide barrier / fence is involved
+__device__ __forceinline__ void st_async_cluster_f2(uint32_t local_smem_addr, uint32_t local_bar_addr, uint32_t rank,
+                                                    float a, float b) {
+  uint32_t raddr, rbar;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_smem_addr), "r"(rank));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(local_bar_addr), "r"(rank));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+               ::"r"(raddr), "f"(a), "f"(b), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ unsigned int atom_add_release_gpu(unsigned int* addr, unsigned int v) {
+  unsigned int old;
+  asm volatile("atom.add.release.gpu.u32 %0, [%1], %2;" : "=r"(old) : "l"(addr), "r"(v) : "memory");
+  return old;
 }
 
 template <bool TF32>
@@ -145,8 +183,8 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* bias_bar = bars + 2 * STAGES + 1;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
-  __shared__ bool s_last;
+  uint64_t* xch_bar = bars + 2 * STAGES + 2;   // counts the bytes of the four CTAs' softmax partials landing in xch
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 3);
   __shared__ int s_gs[kMaxG], s_ge[kMaxG];   // bin start / end, for runtime-indexed access
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -165,7 +203,10 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(tfull_bar, 1);
     mbar_init(bias_bar, Cfg::EPI_WARPS);
+    mbar_init(xch_bar, 1);
     fence_mbar_init();
+    // every row of every CTA of the cluster sends one float2 per bin
+    mbar_arrive_expect_tx(xch_bar, static_cast<uint32_t>(G) * Cfg::CLUSTER * BLOCK_M * 8u);
   }
   if (warp == 1) { tmem_alloc(tmem_holder, 512); tmem_relinquish(); }
   if (threadIdx.x < 8) s_loss[threadIdx.x] = 0.f;
@@ -177,16 +218,22 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     s_gs[threadIdx.x] = gs;
     s_ge[threadIdx.x] = ge;
   }
-  for (int c = threadIdx.x; c < BLOCK_N; c += Cfg::NUM_THREADS) {
-    s_colsum[c] = 0.f;
-    s_bias[c] = (p.bias != nullptr && n0 + c < p.C) ? __ldg(p.bias + n0 + c) : 0.f;
+  // the bias reaches shared memory while warp 0 issues the first loads and warp 1 allocates tensor memory
+  if (threadIdx.x >= 64) {
+    for (int c = threadIdx.x - 64; c < BLOCK_N; c += Cfg::NUM_THREADS - 64) {
+      s_colsum[c] = 0.f;
+      s_bias[c] = (p.bias != nullptr && n0 + c < p.C) ? __ldg(p.bias + n0 + c) : 0.f;
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  // CTA-wide setup barrier.  The TMA producer warp only ARRIVES (its barrier initialisation is ordered before the
+  // arrive): it starts loading at once instead of waiting for the bias / tensor-memory setup of the others.
+  if (warp == 0) { __syncwarp(); named_bar_arrive(4, Cfg::NUM_THREADS); }
+  else           named_bar_sync(4, Cfg::NUM_THREADS);
   tc_fence_after();
-  cluster_arrive_wait();   // every CTA of the cluster is running before anyone touches remote smem
-  const uint32_t tmem_base = *tmem_holder;
-  if (threadIdx.x == 0) stamp(p.timing, 1);   // setup + first cluster barrier done
+  cluster_arrive();   // phase 1 of the cluster barrier; waited for just before the first remote shared-memory store
+  const uint32_t tmem_base = (warp == 0) ? 0u : *tmem_holder;   // (warp 0 never touches tensor memory)
+  if (threadIdx.x == 32) stamp(p.timing, 1);   // setup done
 
   // warp-uniform helpers over the bin table -----------------------------------------------------
   auto bin_of = [&](int col) -> int {   // -1 : not a logit column
@@ -212,12 +259,30 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   const int c_cg = cg * Cfg::CG_COLS;      // first TMEM column of this warp's range
   const int col_lo = n0 + c_cg, col_hi = col_lo + Cfg::CG_COLS;   // global logit columns of this warp
 
+  // (address arithmetic done here, i.e. under the mainloop, by the epilogue warps)
+  const int m_warp = m0 + quarter * 32;
+  // transposed stores: the rows / 16-byte columns this lane writes for every chunk, and whether it may
+  constexpr int ST_ITERS = TF32 ? 4 : 2;            // 16-byte stores per lane and chunk
+  constexpr int ST_ROWS = 32 / ST_ITERS;            // rows covered by one warp-wide store
+  constexpr int ST_CHN = TF32 ? 4 : 2;              // 16-byte pieces per staged row
+  constexpr int ST_ELT = TF32 ? 4 : 2;
+  const int st_r0 = lane / ST_CHN, st_ch = lane % ST_CHN;
+  uint8_t* st_ptr[ST_ITERS];
+  bool st_ok[ST_ITERS];
+#pragma unroll
+  for (int it = 0; it < ST_ITERS; ++it) {
+    const int r = it * ST_ROWS + st_r0;
+    st_ok[it] = p.want_dz && (m_warp + r < p.N) && !(p.dbg & 1);
+    st_ptr[it] = reinterpret_cast<uint8_t*>(p.dz) +
+                 (static_cast<long long>(m_warp + r) * p.ldd + col_lo) * ST_ELT + st_ch * 16;
+  }
+
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
       for (int kb = 0; kb < p.kblocks; ++kb) {
+        const int stage = kb % STAGES;
+        const uint32_t phase = static_cast<uint32_t>(kb / STAGES) & 1u;
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
         const int k0 = kb * BLOCK_K;
@@ -226,10 +291,10 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         tma_load_2d(sa, &tmap_x, &full_bar[stage], k0, m0);
         tma_load_2d(sb, &tmap_w, &full_bar[stage], k0, n0);
         tma_load_2d(sb + Cfg::UMMA_N * 128, &tmap_w, &full_bar[stage], k0, n0 + Cfg::UMMA_N);
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
     __syncwarp();
+    cluster_wait();
   } else if (warp == 1) {
     // ===================== UMMA issuer =====================
     if (lane == 0) {
@@ -260,6 +325,7 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       umma_commit(tfull_bar);
     }
     __syncwarp();
+    cluster_wait();
   } else {
     // ===================== epilogue, part 0: accumulators := bias, chunk table ===================
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c_cg;
@@ -330,16 +396,18 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         if (g_cur >= 0) loc[(cg * MAXG + g_cur) * BLOCK_M + row_l] = make_float2(m_cur, s_cur);
       };
       uint32_t v[CH];
-      if (col_lo < p.C) tmem_ld_32x32b_x16(t_row, v);   // software pipeline: chunk ci+1 is in flight
+#ifdef BAGS_X_NOTMEMLD
+      for (int j = 0; j < CH; ++j) v[j] = __float_as_uint(0.01f * (lane + j));
+#endif
+      if (col_lo < p.C) BAGS_TMEM_LD16(t_row, v);   // software pipeline: chunk ci+1 is in flight
 #pragma unroll 1                                           // while chunk ci is reduced
       for (int ci = 0; ci < Cfg::CHUNKS; ++ci) {
         const int4 md = s_meta[cg * 8 + ci];
         if (md.x < 0) break;
         tmem_ld_wait();
-        float z[CH];
+        float z[CH];   // aliases v: the next chunk's load is issued only after the last use of z
 #pragma unroll
         for (int j = 0; j < CH; ++j) z[j] = __uint_as_float(v[j]);
-        if (ci + 1 < Cfg::CHUNKS && col_lo + (ci + 1) * CH < p.C) tmem_ld_32x32b_x16(t_row + (ci + 1) * CH, v);
         if (md.x != g_cur) { flush(); g_cur = md.x; m_cur = -INFINITY; s_cur = 0.f; }
         uint32_t e[CH];
         float refA, refB = 0.f;
@@ -351,34 +419,42 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           const float cm = fmaxf(fmaxf(c4[0], c4[1]), fmaxf(c4[2], c4[3]));
           const float m_new = fmaxf(m_cur, cm);
           const float mb = m_new * kLog2e;
-          float a4[4] = {0.f, 0.f, 0.f, 0.f};
+          const float2 k2 = make_float2(kLog2e, kLog2e), nb2 = make_float2(-mb, -mb);
+          float2 a2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-          for (int j = 0; j < CH; ++j) {
-            const float ej = fast_exp2(fmaf(z[j], kLog2e, -mb));
-            a4[j & 3] += ej;
-            e[j] = __float_as_uint(ej);
+          for (int j = 0; j < CH; j += 2) {   // packed f32x2 FMA / ADD: half the issue slots
+            const float2 t = __ffma2_rn(make_float2(z[j], z[j + 1]), k2, nb2);
+            const float2 ej = make_float2(fast_exp2(t.x), fast_exp2(t.y));
+            a2[(j >> 1) & 1] = __fadd2_rn(a2[(j >> 1) & 1], ej);
+            e[j] = __float_as_uint(ej.x);
+            e[j + 1] = __float_as_uint(ej.y);
           }
-          const float acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+          const float2 a1 = __fadd2_rn(a2[0], a2[1]);
+          const float acc = a1.x + a1.y;
           s_cur = s_cur * fast_exp2((m_cur - m_new) * kLog2e) + acc;   // 2^-inf = 0 on the first chunk of a bin
           m_cur = m_new;
           refA = m_new;
         } else {
-          // two segments: [0,bpos) continues bin gA, [bpos,hiB) opens bin gB
+          // two segments: [0,bpos) continues bin gA, [bpos,hiB) opens bin gB.  Branch-free (selects): this chunk
+          // sits on the critical path of its CTA's pass A
           const int bpos = md.y, hiB = md.w;
           float cmA = -INFINITY, cmB = -INFINITY;
 #pragma unroll
           for (int j = 0; j < CH; ++j) {
-            if (j < bpos) cmA = fmaxf(cmA, z[j]);
-            else if (j < hiB) cmB = fmaxf(cmB, z[j]);
+            const bool a = j < bpos, b = (j >= bpos) && (j < hiB);
+            cmA = fmaxf(cmA, a ? z[j] : -INFINITY);
+            cmB = fmaxf(cmB, b ? z[j] : -INFINITY);
           }
           const float m_newA = fmaxf(m_cur, cmA);
-          const float mbA = m_newA * kLog2e, mbB = cmB * kLog2e;
+          const float mbA = m_newA * kLog2e, mbB = cmB * kLog2e;   // mbB = -inf without a second bin: selected away
           float accA = 0.f, accB = 0.f;
 #pragma unroll
           for (int j = 0; j < CH; ++j) {
-            float ej = 0.f;
-            if (j < bpos) { ej = fast_exp2(fmaf(z[j], kLog2e, -mbA)); accA += ej; }
-            else if (j < hiB) { ej = fast_exp2(fmaf(z[j], kLog2e, -mbB)); accB += ej; }
+            const bool a = j < bpos, b = (j >= bpos) && (j < hiB);
+            float ej = fast_exp2(fmaf(z[j], kLog2e, a ? -mbA : -mbB));
+            ej = (a || b) ? ej : 0.f;
+            accA += a ? ej : 0.f;
+            accB += b ? ej : 0.f;
             e[j] = __float_as_uint(ej);
           }
           s_cur = s_cur * fast_exp2((m_cur - m_newA) * kLog2e) + accA;
@@ -387,15 +463,20 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           g_cur = md.z; m_cur = cmB; s_cur = accB;
           refA = m_newA; refB = cmB;
         }
-        tmem_st_32x32b_x16(t_row + ci * CH, e);
+        if (ci + 1 < Cfg::CHUNKS && col_lo + (ci + 1) * CH < p.C) BAGS_TMEM_LD16(t_row + (ci + 1) * CH, v);
+        BAGS_TMEM_ST16(t_row + ci * CH, e);
         refs[ci * (32 * Cfg::EPI_WARPS)] = make_float2(refA, refB);
       }
+      if (warp == 2 && lane == 0) stamp2(p.timing, 0);    // chunk loop of pass A done (this warp)
+      if (warp == 17 && lane == 0) stamp2(p.timing, 6);
       flush();
       tmem_st_wait();
     }
     // ---- CTA-local combine of the 4 column groups, then publish to the 4 CTAs of the cluster ----
     // (bins are dealt round-robin to the column groups so that all 16 warps share the work)
     named_bar_sync(1, 32 * Cfg::EPI_WARPS);
+    cluster_wait();   // (phase 1, arrived during setup) every CTA of the cluster is running: remote smem is live
+    if (warp == 2 && lane == 0) stamp2(p.timing, 1);      // all 16 warps done with pass A
     for (int g = cg; g < G; g += Cfg::CGROUPS) {
       float2 q[Cfg::CGROUPS];
 #pragma unroll
@@ -405,39 +486,27 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 #pragma unroll
       for (int i = 0; i < Cfg::CGROUPS; ++i) S += (q[i].x == -INFINITY) ? 0.f : q[i].y * fast_exp2((q[i].x - M) * kLog2e);
       const uint32_t addr = smem_u32(&xch[(static_cast<int>(rank) * MAXG + g) * BLOCK_M + row_l]);
+      const uint32_t baddr = smem_u32(xch_bar);
 #pragma unroll
-      for (uint32_t r = 0; r < 4; ++r) st_cluster_f2(addr, r, M, S);
+      for (uint32_t r = 0; r < 4; ++r) st_async_cluster_f2(addr, baddr, r, M, S);
     }
   }
 
-  // all partials of all four CTAs are in place after this barrier (release/acquire at cluster scope)
   if (warp == 2 && lane == 0) stamp(p.timing, 4);   // pass A done
-  cluster_arrive_wait();
-  if (warp == 2 && lane == 0) stamp(p.timing, 5);   // exchange barrier passed
+
+  if (warp >= 2) {
+    // all partials of all four CTAs have landed once the transaction count of xch_bar is reached; nobody leaves
+    // before that, so no CTA exits while a peer still writes into its shared memory
+    mbar_wait(xch_bar, 0);
+    if (warp == 2 && lane == 0) stamp(p.timing, 5);   // exchange complete
+  }
 
   if (warp >= 2) {
     // ===================== epilogue, part 2: combine + pass C =====================================
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c_cg;
     uint8_t* buf = smem + ew * Cfg::DZ_BUF_BYTES;   // aliases the (now idle) pipeline stages
     const float2* refs = reinterpret_cast<const float2*>(smem + Cfg::REF_OFFSET) + (threadIdx.x - 64);
-    const int m_warp = m0 + quarter * 32;
     tc_fence_after();
-
-    // transposed stores: the rows / 16-byte columns this lane writes for every chunk, and whether it may
-    constexpr int ST_ITERS = TF32 ? 4 : 2;            // 16-byte stores per lane and chunk
-    constexpr int ST_ROWS = 32 / ST_ITERS;            // rows covered by one warp-wide store
-    constexpr int ST_CHN = TF32 ? 4 : 2;              // 16-byte pieces per staged row
-    constexpr int ST_ELT = TF32 ? 4 : 2;
-    const int st_r0 = lane / ST_CHN, st_ch = lane % ST_CHN;
-    uint8_t* st_ptr[ST_ITERS];
-    bool st_ok[ST_ITERS];
-#pragma unroll
-    for (int it = 0; it < ST_ITERS; ++it) {
-      const int r = it * ST_ROWS + st_r0;
-      st_ok[it] = p.want_dz && (m_warp + r < p.N) && !(p.dbg & 1);
-      st_ptr[it] = reinterpret_cast<uint8_t*>(p.dz) +
-                   (static_cast<long long>(m_warp + r) * p.ldd + col_lo) * ST_ELT + st_ch * 16;
-    }
 
     int g_cur = -2;
     float lb_cur = 0.f, coef_cur = 0.f, pt_cur = 1.0f;
@@ -472,7 +541,11 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     };
 
     uint32_t v[CH];
-    if (col_lo < p.C) tmem_ld_32x32b_x16(t_row, v);
+#ifdef BAGS_X_NOTMEMLD
+    for (int j = 0; j < CH; ++j) v[j] = __float_as_uint(0.01f * (lane + j));
+#endif
+    if (col_lo < p.C) BAGS_TMEM_LD16(t_row, v);
+    if (warp == 2 && lane == 0) stamp2(p.timing, 2);      // pass C starts
 #pragma unroll 1
     for (int ci = 0; ci < Cfg::CHUNKS; ++ci) {
       const int4 md = s_meta[cg * 8 + ci];
@@ -480,12 +553,11 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       const int col0 = col_lo + ci * CH;
       const float2 rf = refs[ci * (32 * Cfg::EPI_WARPS)];
       tmem_ld_wait();
-      float d[CH];
+      float d[CH];   // aliases v (e = exp(z - m_chunk) from pass A) until the scaling below
 #pragma unroll
-      for (int j = 0; j < CH; ++j) d[j] = __uint_as_float(v[j]);   // e = exp(z - m_chunk) from pass A
-      // next chunk's TMEM load overlaps the scale / pack / store phases of this one
-      if (ci + 1 < Cfg::CHUNKS && col0 + CH < p.C) tmem_ld_32x32b_x16(t_row + (ci + 1) * CH, v);
+      for (int j = 0; j < CH; ++j) d[j] = __uint_as_float(v[j]);
       if (md.x != g_cur) { finish_bin(); start_bin(md.x); }
+      if (warp == 2 && lane == 0 && ci == 0) stamp_bank(p.timing, 2, 6);
       if (md.y >= CH) {
         const float f = fast_exp2(fmaf(rf.x, kLog2e, -lb_cur));   // exp(m_chunk - lse)
         const float gf = coef_cur * f;
@@ -500,41 +572,39 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             d[j] = dj;
           }
         } else {
+          const float2 g2 = make_float2(gf, gf);
 #pragma unroll
-          for (int j = 0; j < CH; ++j) d[j] *= gf;
+          for (int j = 0; j < CH; j += 2) {
+            const float2 r = __fmul2_rn(make_float2(d[j], d[j + 1]), g2);
+            d[j] = r.x;
+            d[j + 1] = r.y;
+          }
         }
       } else {
-        const int bpos = md.y, hiB = md.w;
-        {
-          const float f = fast_exp2(fmaf(rf.x, kLog2e, -lb_cur));
-          const float gf = coef_cur * f;
-          const int tq = tcol_cur - col0;
+        // branch-free: e is already zero beyond hiB, so a per-element select of the bin's scale is all it takes
+        const int bpos = md.y;
+        const float fA = fast_exp2(fmaf(rf.x, kLog2e, -lb_cur));
+        const float gfA = coef_cur * fA, coefA = coef_cur;
+        const int tqA = tcol_cur - col0;          // target column of bin A relative to the chunk (maybe outside)
 #pragma unroll
-          for (int j = 0; j < CH; ++j) {
-            if (j < bpos) {
-              float dj = d[j] * gf;
-              if (j == tq) { pt_cur = d[j] * f; dj -= coef_cur; }
-              d[j] = dj;
-            }
-          }
-        }
+        for (int j = 0; j < CH; ++j)
+          if (j == tqA && j < bpos) pt_cur = d[j] * fA;
         finish_bin();
         start_bin(md.z);
-        const float f = (md.z >= 0) ? fast_exp2(fmaf(rf.y, kLog2e, -lb_cur)) : 0.f;
-        const float gf = coef_cur * f;
-        const int tq = tcol_cur - col0;
+        const float fB = (md.z >= 0) ? fast_exp2(fmaf(rf.y, kLog2e, -lb_cur)) : 0.f;
+        const float gfB = coef_cur * fB, coefB = coef_cur;
+        const int tqB = tcol_cur - col0;
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
-          if (j >= bpos) {
-            float dj = 0.f;
-            if (j < hiB) {
-              dj = d[j] * gf;
-              if (j == tq) { pt_cur = d[j] * f; dj -= coef_cur; }
-            }
-            d[j] = dj;
-          }
+          const bool a = j < bpos;
+          float dj = d[j] * (a ? gfA : gfB);
+          if (j == tqA && a) dj -= coefA;
+          if (j == tqB && !a) { pt_cur = d[j] * fB; dj -= coefB; }
+          d[j] = dj;
         }
       }
+      // the e values are consumed: the next chunk's TMEM load overlaps the pack / stage / store phase
+      if (ci + 1 < Cfg::CHUNKS && col0 + CH < p.C) BAGS_TMEM_LD16(t_row + (ci + 1) * CH, v);
       if (p.want_dz) {
         // stage the 32-row x 16-column tile in (swizzled) shared memory, read it back transposed so that each
         // warp-wide 16-byte store writes whole 32-byte (bf16) / 64-byte (fp32) row segments
@@ -588,41 +658,58 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         }
         __syncwarp();
       }
+      if (warp == 2 && lane == 0) stamp_bank(p.timing, 2, ci);
     }
+    if (warp == 2 && lane == 0) stamp2(p.timing, 3);      // chunk loop of pass C done (this warp)
+    if (warp == 17 && lane == 0) stamp2(p.timing, 7);
     finish_bin();
     if (warp == 2 && lane == 0) stamp(p.timing, 6);   // pass C done
-    named_bar_sync(1, 32 * Cfg::EPI_WARPS);
+    tc_fence_before();
+    named_bar_arrive(2, 32 * Cfg::EPI_WARPS + 32);   // this warp is done with TMEM (warp 1 deallocates)
 
     // ---- CTA results -> global ----
-    const int et = threadIdx.x - 64;   // 0..511
-    if (p.colsum != nullptr && p.want_dz) {
+    if (p.colsum != nullptr && p.want_dz) {   // optional per-row-tile bias-gradient partials
+      named_bar_sync(3, 32 * Cfg::EPI_WARPS);
+      const int et = threadIdx.x - 64;   // 0..511
       for (int c = et; c < BLOCK_N; c += 32 * Cfg::EPI_WARPS)
         if (n0 + c < p.C) p.colsum[static_cast<long long>(row_tile) * p.C + n0 + c] = s_colsum[c];
     }
-    if (et < kMaxG) p.part[blockIdx.x * kMaxG + et] = (et < G) ? s_loss[et] : 0.f;
-    __threadfence();
-    named_bar_sync(1, 32 * Cfg::EPI_WARPS);
-    if (et == 0) {
-      const unsigned int done = atomicAdd(p.counter, 1u);
-      s_last = (done == gridDim.x - 1);
-    }
-    named_bar_sync(1, 32 * Cfg::EPI_WARPS);
-    if (s_last) {
-      __threadfence();
-      if (ew < G) {
-        float s = 0.f;
-        for (int b = lane; b < static_cast<int>(gridDim.x); b += 32) s += __ldcg(p.part + b * kMaxG + ew);
-        s = warp_sum(s);
-        if (lane == 0) p.loss[ew] = s;   // already divided by avg (coef = w/avg)
+    // losses: one warp stays for the bookkeeping, the other fifteen leave
+    if (ew != 0) {
+      named_bar_arrive(1, 32 * Cfg::EPI_WARPS);
+    } else {
+      named_bar_sync(1, 32 * Cfg::EPI_WARPS);           // s_loss is final
+      if (warp == 2 && lane == 0) stamp2(p.timing, 4);  // all 16 warps done with pass C
+      unsigned int last = 0;
+      if (lane == 0) {
+        float4* dst = reinterpret_cast<float4*>(p.part + static_cast<size_t>(blockIdx.x) * kMaxG);
+        dst[0] = make_float4(s_loss[0], s_loss[1], s_loss[2], s_loss[3]);
+        dst[1] = make_float4(s_loss[4], s_loss[5], s_loss[6], s_loss[7]);
+        last = (atom_add_release_gpu(p.counter, 1u) == gridDim.x - 1) ? 1u : 0u;   // release: the partials first
       }
-      if (et == 0) *p.counter = 0u;
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last) {   // the last CTA of the grid sums the per-CTA partials in a fixed order
+        __threadfence();
+        float acc[kMaxG];
+#pragma unroll
+        for (int g = 0; g < kMaxG; ++g) acc[g] = 0.f;
+        for (int b = lane; b < static_cast<int>(gridDim.x); b += 32) {
+          const float4* src = reinterpret_cast<const float4*>(p.part + static_cast<size_t>(b) * kMaxG);
+          const float4 u = __ldcg(src), w = __ldcg(src + 1);
+          acc[0] += u.x; acc[1] += u.y; acc[2] += u.z; acc[3] += u.w;
+          acc[4] += w.x; acc[5] += w.y; acc[6] += w.z; acc[7] += w.w;
+        }
+#pragma unroll
+        for (int g = 0; g < kMaxG; ++g) {
+          const float t = warp_sum(acc[g]);
+          if (lane == 0 && g < G) p.loss[g] = t;   // already divided by avg (coef = w/avg)
+        }
+        if (lane == 0) *p.counter = 0u;
+      }
     }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
+    if (warp == 2 && lane == 0) stamp2(p.timing, 5);    // bookkeeping warp done
+  } else if (warp == 1) {
+    named_bar_sync(2, 32 * Cfg::EPI_WARPS + 32);        // every epilogue warp has finished reading TMEM
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }

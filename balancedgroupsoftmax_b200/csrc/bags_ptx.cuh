@@ -51,6 +51,14 @@ __device__ __forceinline__ int sm_id() {
 __device__ __forceinline__ void stamp(long long* timing, int slot) {
   if (timing != nullptr) timing[blockIdx.x * 8 + slot] = global_timer_ns();
 }
+// further banks of 8 slots per CTA, stored after the first bank of the whole grid
+__device__ __forceinline__ void stamp_bank(long long* timing, int bank, int slot) {
+  if (timing != nullptr) timing[(bank * gridDim.x + blockIdx.x) * 8 + slot] = global_timer_ns();
+}
+// second bank of 8 slots per CTA, stored after the first bank of the whole grid
+__device__ __forceinline__ void stamp2(long long* timing, int slot) {
+  if (timing != nullptr) timing[(gridDim.x + blockIdx.x) * 8 + slot] = global_timer_ns();
+}
 
 // ----------------------------------------------------------------------------
 // mbarrier
@@ -136,6 +144,13 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask)
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
       ::"r"(smem_u32(bar)), "h"(cta_mask)
       : "memory");
+}
+
+// pull one box of a tiled tensor map into L2 ahead of the TMA load that will need it (no smem, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int32_t c_inner, int32_t c_outer) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c_inner), "r"(c_outer)
+               : "memory");
 }
 
 // ---- CTA-pair (cta_group::2) variants: two CTAs of a cluster (ranks 2i, 2i+1) act as one 256-row MMA unit ----

@@ -258,6 +258,8 @@ def case_timeline(name):
         torch.cuda.synchronize()
         nat.check(nat.lib().bags_debug_set_timing(None), 'set_timing')
         tb = tbuf[:nctas].cpu().double()
+        if 'bwd_merged' in label and os.environ.get('BAGS_BWD_PAIR') == '1':
+            tb = tb[0::2]   # only the leader CTA of a pair stamps the MMA slots
         t0 = tb[:, 0].min()
         end = tb[:, 6].max()
         d = {}
@@ -270,6 +272,22 @@ def case_timeline(name):
         d['cta_life_us(mean,max)'] = [round(float(((tb[:, 6] - tb[:, 0]) / 1e3).mean()), 2),
                                       round(float(((tb[:, 6] - tb[:, 0]) / 1e3).max()), 2)]
         d['distinct_sms'] = int(tb[:, 7].unique().numel())
+        if 'fused' in label:   # second stamp bank: finer epilogue phases (us after 'acc done')
+            t2 = tbuf[nctas:2 * nctas].cpu().double()
+            base = tb[:, 3]
+            nm = ['A_loop(w2)', 'A_allwarps', 'C_start', 'C_loop(w2)', 'C_allwarps', 'cta_done', 'A_loop(w17)', 'C_loop(w17)']
+            d['fine_us_after_acc_done(mean)'] = {nm[i]: round(float(((t2[:, i] - base) / 1e3).mean()), 2) for i in range(8)}
+            d['coarse_us_after_acc_done(mean)'] = {'passA(s4)': round(float(((tb[:, 4] - base) / 1e3).mean()), 2),
+                                                   'xchg(s5)': round(float(((tb[:, 5] - base) / 1e3).mean()), 2),
+                                                   'passC(s6)': round(float(((tb[:, 6] - base) / 1e3).mean()), 2)}
+            t3 = tbuf[2 * nctas:3 * nctas].cpu().double()
+            c0 = t2[:, 2]   # pass C start
+            for r in (0, 2):
+                d['passC_w2_rank%d_us_after_C_start' % r] = {
+                    'start_bin0': round(float(((t3[r::4, 6] - c0[r::4]) / 1e3).mean()), 2),
+                    **{'chunk%d' % i: round(float(((t3[r::4, i] - c0[r::4]) / 1e3).mean()), 2) for i in range(5)}}
+            for r in range(4):
+                d['fine_rank%d' % r] = {nm[i]: round(float(((t2[r::4, i] - base[r::4]) / 1e3).mean()), 2) for i in range(8)}
         if 'fused' in label:   # per cluster-rank means of pass A / barrier / pass C
             for r in range(4):
                 sub = tb[r::4]
