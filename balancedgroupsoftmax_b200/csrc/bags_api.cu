@@ -77,6 +77,34 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 
+// Library-owned counter pairs for the merged backward kernel's in-kernel grid synchronisation: one 256-byte slot
+// per (device, stream) that has used it, zeroed once here and left zero by every launch.
+static unsigned int* g_sync_pool[64] = {nullptr};
+static cudaStream_t g_sync_streams[64][64];
+static int g_sync_count[64] = {0};
+static unsigned int* sync_slot(int dev, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lk(g_mutex);
+  if (g_sync_pool[dev] == nullptr) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+      (void)cudaGetLastError();
+      return nullptr;   // cannot allocate while capturing: the caller falls back to the separate preparation kernel
+    }
+    void* ptr = nullptr;
+    if (cudaMalloc(&ptr, 64 * 256) != cudaSuccess || cudaMemset(ptr, 0, 64 * 256) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return nullptr;
+    }
+    g_sync_pool[dev] = static_cast<unsigned int*>(ptr);
+  }
+  for (int i = 0; i < g_sync_count[dev]; ++i)
+    if (g_sync_streams[dev][i] == stream) return g_sync_pool[dev] + i * 64;
+  if (g_sync_count[dev] >= 64) return nullptr;
+  const int i = g_sync_count[dev]++;
+  g_sync_streams[dev][i] = stream;
+  return g_sync_pool[dev] + i * 64;
+}
+
 static int device_info(DeviceInfo& out) {
   int dev = 0;
   BAGS_CUDA(cudaGetDevice(&dev));
@@ -530,7 +558,7 @@ static int launch_bwd_merged(const void* dz, long long ldd, const void* x, long 
   if ((rc = make_tmap(&t_dz, dz, dtype, p0.C, p0.Nr, ldd, Cfg::BLOCK_K, Cfg::BLOCK_M))) return rc;
   if ((rc = make_tmap(&t_wT, wb, dtype, p0.Kf, p0.C, ldw, Cfg::SLAB, Cfg::BLOCK_K, TF32))) return rc;
   BwdFusedParams p = p0;
-  p.timing = g_timing;
+  p.timing = g_timing ? g_timing + 2048 * 8 : nullptr;   // rows [2048, ..): the forward of the same step uses [0, 2048)
   auto kernel = bags_bwd_fused_kernel<TF32>;
   BAGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int units = p.dw_units + p.dx_units;
@@ -596,7 +624,7 @@ static int launch_bwd_pair(const void* dz, long long ldd, const void* x, long lo
   if ((rc = make_tmap(&t_dz, dz, dtype, p0.C, p0.Nr, ldd, Cfg::BLOCK_K, Cfg::BLOCK_M))) return rc;
   if ((rc = make_tmap(&t_wT, wb, dtype, p0.Kf, p0.C, ldw, Cfg::SLAB, Cfg::BLOCK_K, TF32))) return rc;
   BwdFusedParams p = p0;
-  p.timing = g_timing;
+  p.timing = g_timing ? g_timing + 2048 * 8 : nullptr;
   auto kernel = bags_bwd_pair_kernel<TF32>;
   BAGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int units = p.dw_units + p.dx_units;
@@ -667,11 +695,22 @@ extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long 
   if (want_scale)
     BAGS_REQUIRE(w != nullptr && (K % vecw) == 0 && (ldw % vecw) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
                  "bags_bwd: w must be 16-byte aligned with K and ldw multiples of %d", vecw);
-  if (want_colpart) BAGS_REQUIRE((ldd % 2) == 0, "bags_bwd: ldd must be even");
+  if (want_colpart)
+    BAGS_REQUIRE(((ldd * (bf ? 2 : 4)) % 16) == 0 && (reinterpret_cast<uintptr_t>(dz) & 15) == 0,
+                 "bags_bwd: dz rows must be 16-byte aligned");
 
-  // ---- one preparation kernel: zero dW, W' = gout-scaled W, bias-gradient partial column sums ----
+  // ---- preparation: zero dW, W' = gout-scaled W, bias-gradient partial column sums.  On the merged single-CTA path
+  // these jobs run inside the GEMM kernel (no extra launch in the dependent chain); otherwise one small kernel. ----
+  const bool merged_path = dW != nullptr && dX != nullptr && N > 0 && (K % 8) == 0 && env_int("BAGS_BWD_MERGED", 1);
+  unsigned int* sync = nullptr;
+  if (merged_path && !env_int("BAGS_BWD_PAIR", 0) && env_int("BAGS_BWD_INKERNEL_PREP", 1)) {
+    int dev = 0;
+    BAGS_CUDA(cudaGetDevice(&dev));
+    sync = sync_slot(dev, stream);
+  }
+  BwdPrepParams pp{};
+  int prep_jobs = 0;
   if (dW != nullptr || want_scale || want_colpart) {
-    BwdPrepParams pp{};
     pp.dW = dW; pp.lddw = lddw; pp.C = C; pp.K = K;
     pp.w = w; pp.wscr = wscratch; pp.ldw = ldw; pp.gout = gout; pp.gt = gt;
     pp.dz = dz; pp.ldd = ldd; pp.N = N; pp.colpart = colpart; pp.ctiles = kColsumTiles;
@@ -679,15 +718,16 @@ extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long 
     pp.s_ctas = want_scale ? di.num_sms : 0;
     pp.c_ctas = want_colpart ? ((C + 63) / 64) * kColsumTiles : 0;
     const int grid = pp.z_ctas + pp.s_ctas + pp.c_ctas;
-    if (bf) BAGS_CUDA(launch_pdl(bwd_prep_kernel<false>, dim3(grid), dim3(256), 0, stream, pp));
-    else    BAGS_CUDA(launch_pdl(bwd_prep_kernel<true>, dim3(grid), dim3(256), 0, stream, pp));
+    if (sync != nullptr) prep_jobs = grid;
+    else if (bf) BAGS_CUDA(launch_pdl(bwd_prep_kernel<false>, dim3(grid), dim3(256), 0, stream, pp));
+    else         BAGS_CUDA(launch_pdl(bwd_prep_kernel<true>, dim3(grid), dim3(256), 0, stream, pp));
   }
   const float* cs_in = (colsum != nullptr) ? colsum : colpart;
   const int cs_tiles = (colsum != nullptr) ? colsum_tiles : kColsumTiles;
   if (db != nullptr) BAGS_REQUIRE(cs_in != nullptr && cs_tiles >= 1, "bags_bwd: db requested but no column sums available");
 
   // ---- both contractions in one persistent launch when both are requested ----
-  if (dW != nullptr && dX != nullptr && N > 0 && (K % 8) == 0 && env_int("BAGS_BWD_MERGED", 1)) {
+  if (merged_path) {
     BAGS_REQUIRE(w != nullptr, "bags_bwd: w is NULL but dX requested");
     BAGS_REQUIRE((reinterpret_cast<uintptr_t>(dX) & 15) == 0 && ((lddx * (bf ? 2 : 4)) % 16) == 0,
                  "bags_bwd: dX rows must be 16-byte aligned");
@@ -706,6 +746,7 @@ extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long 
     bp.colsum_in = (db != nullptr) ? cs_in : nullptr;
     bp.colsum_tiles = cs_tiles;
     bp.db = db;
+    bp.prep = pp; bp.prep_jobs = prep_jobs; bp.sync = sync;
     const void* wb = want_scale ? wscratch : w;
     if (env_int("BAGS_BWD_PAIR", 0)) {
       // units are 256-row CTA pairs

@@ -25,8 +25,27 @@ struct BwdFusedParams {
   void* dX; long long lddx;
   const float* gscale; int G; int gstart[kMaxGroups]; int glen[kMaxGroups];
   const float* colsum_in; int colsum_tiles; float* db;
+  // In-kernel preparation (single-CTA kernel): the jobs bwd_prep_kernel would run (zero dW, W' = gout-scaled W,
+  // bias-gradient partials) are done by the epilogue warps while the first mainloop runs; `sync` is a library-owned
+  // pair of counters {jobs done, CTAs exited} that is zero between launches.  prep_jobs == 0: a separate
+  // bwd_prep_kernel ran before this one (programmatic dependent launch).
+  BwdPrepParams prep; int prep_jobs; unsigned int* sync;
   long long* timing;
 };
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// wait until every CTA of the grid has finished its preparation jobs (bounded: a broken launch must not hang the box)
+__device__ __forceinline__ void wait_grid_jobs(const unsigned int* ctr, unsigned int target) {
+  unsigned int spins = 0;
+  while (ld_acquire_gpu(ctr) < target) {
+    __nanosleep(64);
+    if (++spins > (1u << 24)) { printf("bags: grid job counter timed out (block %d)\n", (int)blockIdx.x); __trap(); }
+  }
+}
 
 template <bool TF32>
 struct BwdCfg {
@@ -115,10 +134,16 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
       int stage = 0;
       uint32_t phase = 0;
       bool waited = false;
+      const bool inkernel = p.prep_jobs > 0;
+      if (inkernel) pdl_wait();   // dz comes from the forward kernel (no preparation kernel in between)
       for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
         const Unit un = decode(u);
         const int m0 = un.m_tile * BLOCK_M, n0 = un.n_tile * BLOCK_N;
-        if (!un.is_dw && !waited) { pdl_wait(); waited = true; }   // W' is written by bwd_prep
+        if (!un.is_dw && !waited) {   // W' is written by bwd_prep / by the preparation jobs of all CTAs
+          if (inkernel) { wait_grid_jobs(p.sync, gridDim.x); asm volatile("fence.proxy.async;" ::: "memory"); }
+          else pdl_wait();
+          waited = true;
+        }
         for (int kb = un.kb0; kb < un.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -194,6 +219,21 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
     constexpr int HALF_N = BLOCK_N / 2;
     bool waited = false;
     int local = 0;
+    const bool inkernel = p.prep_jobs > 0;
+    if (inkernel) {
+      // preparation jobs, spread over the grid; they run under the first mainloop (these warps are idle until then)
+      const int tid = static_cast<int>(threadIdx.x) - 64;
+      float (*s_part)[64] = reinterpret_cast<float (*)[64]>(smem_epi);
+      pdl_wait();   // dW / W' may still be in use by whatever ran before the forward kernel; dz comes from it
+      for (int j = blockIdx.x; j < p.prep_jobs; j += gridDim.x) {
+        bwd_prep_job<TF32, 5>(p.prep, j, tid, s_part);
+        asm volatile("bar.sync 5, 256;" ::: "memory");   // s_part is reused by the next job
+      }
+      asm volatile("fence.proxy.async;" ::: "memory");   // W' is read through TMA (async proxy) by other CTAs
+      __threadfence();
+      asm volatile("bar.sync 5, 256;" ::: "memory");
+      if (tid == 0) atomicAdd(p.sync, 1u);
+    }
     for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++local) {
       const Unit un = decode(u);
       const int m_warp = un.m_tile * BLOCK_M + quarter * 32;
@@ -205,7 +245,11 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
 
       float scale = 1.0f;
       if (un.is_dw) {
-        if (!waited) { pdl_wait(); waited = true; }   // dW was zeroed / column-sum partials were made by bwd_prep
+        if (!waited) {   // dW was zeroed / column-sum partials were made by bwd_prep or by every CTA's jobs
+          if (inkernel) { if (lane == 0) wait_grid_jobs(p.sync, gridDim.x); __syncwarp(); __threadfence(); }
+          else pdl_wait();
+          waited = true;
+        }
         scale = 0.f;
         if (m < p.C) {
           if (p.gscale == nullptr) scale = 1.0f;
@@ -216,7 +260,7 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
           }
           if (p.db != nullptr && un.n_tile == 0 && un.split == 0 && half == 0) {
             float cs = 0.f;
-            for (int tt = 0; tt < p.colsum_tiles; ++tt) cs += __ldg(p.colsum_in + static_cast<long long>(tt) * p.C + m);
+            for (int tt = 0; tt < p.colsum_tiles; ++tt) cs += __ldcg(p.colsum_in + static_cast<long long>(tt) * p.C + m);
             p.db[m] = scale * cs;
           }
         }
@@ -293,6 +337,10 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+  if (threadIdx.x == 0 && p.prep_jobs > 0) {
+    // the last CTA to get here re-arms the counters for the next launch (nobody is waiting on them any more)
+    if (atomicAdd(p.sync + 1, 1u) == gridDim.x - 1) { p.sync[0] = 0u; p.sync[1] = 0u; __threadfence(); }
   }
   if (threadIdx.x == 0) stamp(p.timing, 6);
 }

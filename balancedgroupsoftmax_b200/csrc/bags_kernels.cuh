@@ -533,80 +533,144 @@ struct BwdPrepParams {
   int z_ctas, s_ctas, c_ctas;   // CTA ranges of the three jobs (0 = job disabled)
 };
 
-template <bool F32>
-__global__ void __launch_bounds__(256)
-bwd_prep_kernel(const BwdPrepParams p) {
-  pdl_wait();      // dz comes from the forward kernel; nothing before it may still be running either
-  pdl_trigger();   // from here on the dW GEMM may start: its mainloop only reads dz and x
-  const int b = blockIdx.x;
+// One job of the backward preparation, executed by 256 threads (`tid` in [0,256)).  `b` indexes the job like a CTA
+// of bwd_prep_kernel would; `s_part` is 2 KB of shared memory; BAR_ID < 0 synchronises with __syncthreads(),
+// otherwise with the named barrier BAR_ID over 256 threads (used from inside the merged backward kernel).
+template <bool F32, int BAR_ID>
+__device__ __forceinline__ void bwd_prep_job(const BwdPrepParams& p, int b, int tid, float (*s_part)[64]) {
   if (b < p.z_ctas) {
     // ---- (1) zero dW ----
     const int vec_per_row = p.K >> 2;
     const long long total = static_cast<long long>(p.C) * vec_per_row;
-    for (long long i = b * 256ll + threadIdx.x; i < total; i += p.z_ctas * 256ll) {
+    for (long long i = b * 256ll + tid; i < total; i += p.z_ctas * 256ll) {
       const int r = static_cast<int>(i / vec_per_row), c = static_cast<int>(i - static_cast<long long>(r) * vec_per_row);
       reinterpret_cast<float4*>(p.dW + static_cast<long long>(r) * p.lddw)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   } else if (b < p.z_ctas + p.s_ctas) {
-    // ---- (2) row-scaled copy of W ----
+    // ---- (2) row-scaled copy of W: flat index space, four independent 16-byte loads in flight per thread ----
     constexpr int V = F32 ? 4 : 8;
-    for (int r = b - p.z_ctas; r < p.C; r += p.s_ctas) {
-      float s = 0.f;
+    const int vec_per_row = p.K / V;
+    const long long total = static_cast<long long>(p.C) * vec_per_row;
+    const long long stride = static_cast<long long>(p.s_ctas) * 256;
+    const char* wsrc = reinterpret_cast<const char*>(p.w);
+    char* wdst = reinterpret_cast<char*>(p.wscr);
+    const long long row_bytes = p.ldw * (F32 ? 4 : 2);
+    for (long long i0 = static_cast<long long>(b - p.z_ctas) * 256 + tid; i0 < total; i0 += 4 * stride) {
+      uint4 raw[4];
+      int rr[4], cc[4];
 #pragma unroll
-      for (int g = 0; g < kMaxG; ++g)
-        if (g < p.gt.G && r >= p.gt.start[g] && r < p.gt.start[g] + p.gt.len[g]) s = __ldg(p.gout + g);
-      for (int c = threadIdx.x * V; c < p.K; c += 256 * V) {
+      for (int u = 0; u < 4; ++u) {
+        const long long i = i0 + u * stride;
+        rr[u] = -1;
+        if (i < total) {
+          rr[u] = static_cast<int>(i / vec_per_row);
+          cc[u] = static_cast<int>(i - static_cast<long long>(rr[u]) * vec_per_row);
+          raw[u] = __ldg(reinterpret_cast<const uint4*>(wsrc + rr[u] * row_bytes) + cc[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (rr[u] < 0) continue;
+        float sc = 0.f;
+#pragma unroll
+        for (int g = 0; g < kMaxG; ++g)
+          if (g < p.gt.G && rr[u] >= p.gt.start[g] && rr[u] < p.gt.start[g] + p.gt.len[g]) sc = __ldg(p.gout + g);
+        uint4 o;
         if (F32) {
-          float4 v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.w) + static_cast<long long>(r) * p.ldw + c));
-          v.x *= s; v.y *= s; v.z *= s; v.w *= s;
-          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.wscr) + static_cast<long long>(r) * p.ldw + c) = v;
+          o.x = __float_as_uint(__uint_as_float(raw[u].x) * sc); o.y = __float_as_uint(__uint_as_float(raw[u].y) * sc);
+          o.z = __float_as_uint(__uint_as_float(raw[u].z) * sc); o.w = __float_as_uint(__uint_as_float(raw[u].w) * sc);
         } else {
-          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.w) + static_cast<long long>(r) * p.ldw + c));
-          const uint32_t in[4] = {raw.x, raw.y, raw.z, raw.w};
-          uint32_t o[4];
+          const uint32_t in[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+          uint32_t q4[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            o[q] = pack_bf16x2(__uint_as_float(in[q] << 16) * s, __uint_as_float(in[q] & 0xffff0000u) * s);
-          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.wscr) + static_cast<long long>(r) * p.ldw + c) =
-              make_uint4(o[0], o[1], o[2], o[3]);
+            q4[q] = pack_bf16x2(__uint_as_float(in[q] << 16) * sc, __uint_as_float(in[q] & 0xffff0000u) * sc);
+          o = make_uint4(q4[0], q4[1], q4[2], q4[3]);
         }
+        reinterpret_cast<uint4*>(wdst + rr[u] * row_bytes)[cc[u]] = o;
       }
     }
   } else if (b < p.z_ctas + p.s_ctas + p.c_ctas) {
-    // ---- (3) column sums of dz over one row group, one 64-column strip per CTA ----
-    __shared__ float s_part[8][64];
+    // ---- (3) column sums of dz over one row group, one 64-column strip per job.  Thread t owns 8 columns
+    // (t % 8) of rows (t / 8) + 32 i: 16-byte loads, 8 of them in flight per thread; padded columns of dz exist
+    // up to ldd (a multiple of 8), columns beyond that read as zero ----
     const int ci = b - p.z_ctas - p.s_ctas;
     const int nstrips = (p.C + 63) / 64;
     const int strip = ci % nstrips, rg = ci / nstrips;
     const int rows_per_group = (p.N + p.ctiles - 1) / p.ctiles;
     const int r0 = rg * rows_per_group;
     const int r1 = (r0 + rows_per_group < p.N) ? r0 + rows_per_group : p.N;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int col = strip * 64 + lane * 2;   // two columns per lane; padded columns of dz exist up to ldd
-    float a0 = 0.f, a1 = 0.f;
-    if (col + 1 < p.ldd) {
-#pragma unroll 8
-      for (int r = r0 + warp; r < r1; r += 8) {
-        if (F32) {
-          const float2 v = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(p.dz) + static_cast<long long>(r) * p.ldd + col));
-          a0 += v.x; a1 += v.y;
-        } else {
-          const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const __nv_bfloat16*>(p.dz) + static_cast<long long>(r) * p.ldd + col));
-          a0 += __uint_as_float(v << 16); a1 += __uint_as_float(v & 0xffff0000u);
+    const int cgp = tid & 7, rl = tid >> 3;
+    const int col = strip * 64 + cgp * 8;
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    if (col + 8 <= p.ldd) {
+      for (int rb = r0 + rl; rb < r1; rb += 32 * 8) {
+        uint4 v[8], v2[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = rb + 32 * u;
+          v[u] = make_uint4(0u, 0u, 0u, 0u);
+          v2[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (r < r1) {
+            if (F32) {
+              const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.dz) + static_cast<long long>(r) * p.ldd + col);
+              v[u] = __ldcg(src);
+              v2[u] = __ldcg(src + 1);
+            } else {
+              v[u] = __ldcg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.dz) + static_cast<long long>(r) * p.ldd + col));
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (F32) {
+            acc[0] += __uint_as_float(v[u].x); acc[1] += __uint_as_float(v[u].y);
+            acc[2] += __uint_as_float(v[u].z); acc[3] += __uint_as_float(v[u].w);
+            acc[4] += __uint_as_float(v2[u].x); acc[5] += __uint_as_float(v2[u].y);
+            acc[6] += __uint_as_float(v2[u].z); acc[7] += __uint_as_float(v2[u].w);
+          } else {
+            const uint32_t in[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              acc[2 * q] += __uint_as_float(in[q] << 16);
+              acc[2 * q + 1] += __uint_as_float(in[q] & 0xffff0000u);
+            }
+          }
         }
       }
     }
-    s_part[warp][lane * 2] = a0;
-    s_part[warp][lane * 2 + 1] = a1;
-    __syncthreads();
-    if (threadIdx.x < 64) {
+    // 32 row-lanes per column: fold lanes l and l ^ 8, 16 (rows 1, 2 apart within the warp), then 8 warps via smem
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 8);
+      acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 16);
+    }
+    const int warp = tid >> 5, lane = tid & 31;
+    if (lane < 8) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s_part[warp][lane * 8 + q] = acc[q];
+    }
+    if (BAR_ID < 0) __syncthreads();
+    else asm volatile("bar.sync %0, 256;" ::"r"(BAR_ID) : "memory");
+    if (tid < 64) {
       float t = 0.f;
 #pragma unroll
-      for (int w8 = 0; w8 < 8; ++w8) t += s_part[w8][threadIdx.x];
-      const int c = strip * 64 + threadIdx.x;
+      for (int w8 = 0; w8 < 8; ++w8) t += s_part[w8][tid];
+      const int c = strip * 64 + tid;
       if (c < p.C) p.colpart[static_cast<long long>(rg) * p.C + c] = t;
     }
   }
+}
+
+template <bool F32>
+__global__ void __launch_bounds__(256)
+bwd_prep_kernel(const BwdPrepParams p) {
+  __shared__ float s_part[8][64];
+  pdl_wait();      // dz comes from the forward kernel; nothing before it may still be running either
+  pdl_trigger();   // from here on the dW GEMM may start: its mainloop only reads dz and x
+  bwd_prep_job<F32, -1>(p, blockIdx.x, threadIdx.x, s_part);
 }
 
 // ----------------------------------------------------------------------------

@@ -257,7 +257,8 @@ def case_timeline(name):
         fn()
         torch.cuda.synchronize()
         nat.check(nat.lib().bags_debug_set_timing(None), 'set_timing')
-        tb = tbuf[:nctas].cpu().double()
+        off = 2048 if 'bwd_merged' in label else 0   # the merged backward stamps rows [2048, ..)
+        tb = tbuf[off:off + nctas].cpu().double()
         if 'bwd_merged' in label and os.environ.get('BAGS_BWD_PAIR') == '1':
             tb = tb[0::2]   # only the leader CTA of a pair stamps the MMA slots
         t0 = tb[:, 0].min()
@@ -312,6 +313,78 @@ def case_timeline(name):
     return res
 
 
+def case_steptimeline(name):
+    """absolute %globaltimer picture of consecutive training steps replayed from one CUDA graph (bench.py's loop):
+    when do the forward / backward CTAs of step i start and end relative to each other"""
+    np, torch, ops, _, O = _setup()
+    from balancedgroupsoftmax_b200 import _native as nat
+    N, POOL = 4096, 5
+    t, x, W, b, labels, l2b, ps, remapped = _problem(N)
+    dt = ops.DeviceTables.from_tables(t, 'cuda')
+    g = torch.Generator().manual_seed(1)
+    sets = []
+    for i in range(POOL):
+        s = dict(x=torch.relu(torch.randn(N, 1024, generator=g)).cuda().bfloat16(), w=W.cuda().bfloat16(), bias=b.cuda(),
+                 labels=labels.cuda(), dW=torch.empty(t.num_logits, 1024, device='cuda'),
+                 db=torch.empty(t.num_logits, device='cuda'), dX=torch.empty(N, 1024, device='cuda', dtype=torch.bfloat16),
+                 tb=torch.zeros(4096, 8, dtype=torch.int64, device='cuda'))
+        s['ws'] = ops.bwd_scratch(s['w'])
+        sets.append(s)
+    gout = torch.ones(5, device='cuda')
+    seed = [0]
+
+    def step(s, timed):
+        seed[0] += 1
+        if timed:
+            nat.check(nat.lib().bags_debug_set_timing(s['tb'].data_ptr()), 'set_timing')
+        wmask, avg = ops.sample_others(s['labels'], dt, 8.0, seed[0])
+        loss, _, _, dz, colsum = ops.fused_fwd(s['x'], s['w'], s['bias'], s['labels'], dt, wmask, avg)
+        ops.fused_bwd(dz, s['x'], s['w'], gout, dt, colsum, dW=s['dW'], dX=s['dX'], wscratch=s['ws'], db=s['db'])
+
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        for s in sets[:2]:
+            step(s, False)
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            for s in sets:
+                step(s, True)    # every step's launches capture their own stamp buffer
+        nat.check(nat.lib().bags_debug_set_timing(None), 'set_timing')
+        for _ in range(6):
+            graph.replay()
+        stream.synchronize()
+    res = {}
+    t0 = None
+    rows = []
+    for i, s in enumerate(sets):
+        tb = s['tb'].cpu().double()
+        f = tb[:128]
+        bw = tb[2048:2048 + 148]
+        if t0 is None:
+            t0 = f[:, 0].min()
+        us = lambda v: round(float((v - t0) / 1e3), 2)
+        rows.append(dict(step=i,
+                         fwd_first_cta_start=us(f[:, 0].min()), fwd_median_cta_start=us(f[:, 0].median()),
+                         fwd_last_cta_start=us(f[:, 0].max()),
+                         fwd_first_acc_done=us(f[:, 3].min()), fwd_last_acc_done=us(f[:, 3].max()),
+                         fwd_first_exchange_done=us(f[:, 5].min()), fwd_last_exchange_done=us(f[:, 5].max()),
+                         fwd_first_end=us(f[:, 6].min()), fwd_last_end=us(f[:, 6].max()),
+                         bwd_first_cta_start=us(bw[:, 0].min()), bwd_last_cta_start=us(bw[:, 0].max()),
+                         bwd_median_first_data=us(bw[:, 2].median()), bwd_last_first_data=us(bw[:, 2].max()),
+                         bwd_first_end=us(bw[:, 6].min()), bwd_median_end=us(bw[:, 6].median()), bwd_last_end=us(bw[:, 6].max())))
+    res['steps'] = rows
+    res['period_us(bwd_last_end deltas)'] = [round(rows[i + 1]['bwd_last_end'] - rows[i]['bwd_last_end'], 2) for i in range(POOL - 1)]
+    # how many forward CTAs of step i+1 started before the backward of step i had finished
+    early = []
+    for i in range(POOL - 1):
+        fe = sets[i + 1]['tb'][:128, 0].cpu().double()
+        be = sets[i]['tb'][2048:2048 + 148, 6].cpu().double().max()
+        early.append(int((fe < be).sum()))
+    res['fwd_ctas_started_before_prev_bwd_end'] = early
+    return res
+
+
 def case_timing(name):
     """rough CUDA-event timings of each launch at the benchmark shape (not a bench number)"""
     np, torch, ops, _, O = _setup()
@@ -360,7 +433,7 @@ CASES = {
     'gemm.mnmn.bf16': case_gemm,
     'gemm.kk256.f32': case_gemm, 'gemm.kk320.f32': case_gemm, 'gemm.kmn.f32': case_gemm, 'gemm.mnmn.f32': case_gemm,
     'fused.bf16': case_fused, 'fused.f32': case_fused, 'fusedk.bf16': case_fusedk, 'fusedk.f32': case_fusedk,
-    'timeline': case_timeline, 'timing': case_timing,
+    'timeline': case_timeline, 'steptimeline': case_steptimeline, 'timing': case_timing,
 }
 
 
