@@ -547,12 +547,13 @@ scale_colsum_kernel(const float* __restrict__ colsum, int tiles, float* __restri
 
 
 template <bool TF32>
-static int launch_bwd_merged(const void* dz, long long ldd, const void* x, long long ldx, const void* wb, long long ldw,
-                             const BwdFusedParams& p0, const DeviceInfo& di, cudaStream_t stream) {
+static int launch_bwd_merged(const void* dz, long long ldd, const void* x, long long ldx, const void* wb, const void* w,
+                             long long ldw, const BwdFusedParams& p0, const DeviceInfo& di, cudaStream_t stream) {
   using Cfg = BwdCfg<TF32>;
   const int dtype = TF32 ? BAGS_DTYPE_F32 : BAGS_DTYPE_BF16;
-  CUtensorMap t_dzT, t_xT, t_dz, t_wT;
+  CUtensorMap t_dzT, t_xT, t_dz, t_wT, t_w;
   int rc;
+  if ((rc = make_tmap(&t_w, w, dtype, p0.Kf, p0.C, ldw, Cfg::SLAB, Cfg::BLOCK_K, TF32))) return rc;
   if ((rc = make_tmap(&t_dzT, dz, dtype, p0.C, p0.Nr, ldd, Cfg::SLAB, Cfg::BLOCK_K, TF32))) return rc;
   if ((rc = make_tmap(&t_xT, x, dtype, p0.Kf, p0.Nr, ldx, Cfg::SLAB, Cfg::BLOCK_K, TF32))) return rc;
   if ((rc = make_tmap(&t_dz, dz, dtype, p0.C, p0.Nr, ldd, Cfg::BLOCK_K, Cfg::BLOCK_M))) return rc;
@@ -563,7 +564,7 @@ static int launch_bwd_merged(const void* dz, long long ldd, const void* x, long 
   BAGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int units = p.dw_units + p.dx_units;
   const int grid = units < di.num_sms ? units : di.num_sms;
-  BAGS_CUDA(launch_pdl(kernel, dim3(grid), dim3(Cfg::NUM_THREADS), Cfg::SMEM_BYTES, stream, t_dzT, t_xT, t_dz, t_wT, p));
+  BAGS_CUDA(launch_pdl(kernel, dim3(grid), dim3(Cfg::NUM_THREADS), Cfg::SMEM_BYTES, stream, t_dzT, t_xT, t_dz, t_wT, t_w, p));
   return BAGS_OK;
 }
 
@@ -764,8 +765,10 @@ extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long 
       return bf ? launch_bwd_pair<false>(dz, ldd, x, ldx, wb, ldw, bp, di, stream)
                 : launch_bwd_pair<true>(dz, ldd, x, ldx, wb, ldw, bp, di, stream);
     }
-    return bf ? launch_bwd_merged<false>(dz, ldd, x, ldx, wb, ldw, bp, di, stream)
-              : launch_bwd_merged<true>(dz, ldd, x, ldx, wb, ldw, bp, di, stream);
+    bp.dx_uniform_ok = (want_scale && env_int("BAGS_DX_UNIFORM", 1)) ? 1 : 0;
+    bp.prep.skip_scale_if_uniform = (bp.dx_uniform_ok && prep_jobs > 0) ? 1 : 0;
+    return bf ? launch_bwd_merged<false>(dz, ldd, x, ldx, wb, w, ldw, bp, di, stream)
+              : launch_bwd_merged<true>(dz, ldd, x, ldx, wb, w, ldw, bp, di, stream);
   }
 
   if (dW != nullptr && N > 0) {

@@ -30,6 +30,7 @@ struct BwdFusedParams {
   // pair of counters {jobs done, CTAs exited} that is zero between launches.  prep_jobs == 0: a separate
   // bwd_prep_kernel ran before this one (programmatic dependent launch).
   BwdPrepParams prep; int prep_jobs; unsigned int* sync;
+  int dx_uniform_ok;   // gout given and tmap_w valid: dX units may read W and scale by gout[0] when gout is uniform
   long long* timing;
 };
 
@@ -66,6 +67,8 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
                       const __grid_constant__ CUtensorMap tmap_xT,    // x  as MN-major B of dW  (box SLAB x BLOCK_K)
                       const __grid_constant__ CUtensorMap tmap_dz,    // dz as K-major  A of dX  (box BLOCK_K x 128)
                       const __grid_constant__ CUtensorMap tmap_wT,    // W' as MN-major B of dX  (box SLAB x BLOCK_K)
+                      const __grid_constant__ CUtensorMap tmap_w,     // W  (unscaled), same geometry: used instead of
+                                                                      // W' when all gout[g] are equal
                       const BwdFusedParams p) {
   using Cfg = BwdCfg<TF32>;
   constexpr int BLOCK_M = Cfg::BLOCK_M, BLOCK_N = Cfg::BLOCK_N, BLOCK_K = Cfg::BLOCK_K, STAGES = Cfg::STAGES;
@@ -88,6 +91,7 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_dzT); tma_prefetch_desc(&tmap_xT); tma_prefetch_desc(&tmap_dz); tma_prefetch_desc(&tmap_wT);
+    tma_prefetch_desc(&tmap_w);
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
 #pragma unroll
@@ -136,10 +140,14 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
       bool waited = false;
       const bool inkernel = p.prep_jobs > 0;
       if (inkernel) pdl_wait();   // dz comes from the forward kernel (no preparation kernel in between)
+      // equal per-bin upstream gradients (the usual case: every bin's loss has weight 1): dX = g0 * dz W, so the
+      // scaled copy W' is neither made nor waited for
+      float g0 = 1.f;
+      const bool plain_w = p.dx_uniform_ok && gout_uniform(p.gscale, p.G, g0);
       for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
         const Unit un = decode(u);
         const int m0 = un.m_tile * BLOCK_M, n0 = un.n_tile * BLOCK_N;
-        if (!un.is_dw && !waited) {   // W' is written by bwd_prep / by the preparation jobs of all CTAs
+        if (!un.is_dw && !waited && !plain_w) {   // W' is written by bwd_prep / by the preparation jobs of all CTAs
           if (inkernel) { wait_grid_jobs(p.sync, gridDim.x); asm volatile("fence.proxy.async;" ::: "memory"); }
           else pdl_wait();
           waited = true;
@@ -159,9 +167,10 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
               tma_load_2d(sb + i * (BLOCK_K * 128), &tmap_xT, &full_bar[stage], n0 + i * Cfg::SLAB, k0);
           } else {
             tma_load_2d(sa, &tmap_dz, &full_bar[stage], k0, m0);
+            const CUtensorMap* tw = plain_w ? &tmap_w : &tmap_wT;
 #pragma unroll
             for (int i = 0; i < BLOCK_N / Cfg::SLAB; ++i)
-              tma_load_2d(sb + i * (BLOCK_K * 128), &tmap_wT, &full_bar[stage], n0 + i * Cfg::SLAB, k0);
+              tma_load_2d(sb + i * (BLOCK_K * 128), tw, &full_bar[stage], n0 + i * Cfg::SLAB, k0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -220,6 +229,11 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
     bool waited = false;
     int local = 0;
     const bool inkernel = p.prep_jobs > 0;
+    float dx_scale = 1.f;
+    if (p.dx_uniform_ok) {
+      float g0;
+      if (gout_uniform(p.gscale, p.G, g0)) dx_scale = g0;
+    }
     if (inkernel) {
       // preparation jobs, spread over the grid; they run under the first mainloop (these warps are idle until then)
       const int tid = static_cast<int>(threadIdx.x) - 64;
@@ -243,7 +257,7 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
       const uint32_t acc_phase = (local / Cfg::ACC_STAGES) & 1u;
       const int Mrows = un.is_dw ? p.C : p.Nr;
 
-      float scale = 1.0f;
+      float scale = dx_scale;
       if (un.is_dw) {
         if (!waited) {   // dW was zeroed / column-sum partials were made by bwd_prep or by every CTA's jobs
           if (inkernel) { if (lane == 0) wait_grid_jobs(p.sync, gridDim.x); __syncwarp(); __threadfence(); }
@@ -287,10 +301,10 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
           for (int j = 0; j < 8; ++j) {
             const uint32_t* src = (j < 4) ? (v + 8 * j) : (v2 + 8 * (j - 4));
             uint4 r;
-            r.x = pack_bf16x2(__uint_as_float(src[0]), __uint_as_float(src[1]));
-            r.y = pack_bf16x2(__uint_as_float(src[2]), __uint_as_float(src[3]));
-            r.z = pack_bf16x2(__uint_as_float(src[4]), __uint_as_float(src[5]));
-            r.w = pack_bf16x2(__uint_as_float(src[6]), __uint_as_float(src[7]));
+            r.x = pack_bf16x2(__uint_as_float(src[0]) * scale, __uint_as_float(src[1]) * scale);
+            r.y = pack_bf16x2(__uint_as_float(src[2]) * scale, __uint_as_float(src[3]) * scale);
+            r.z = pack_bf16x2(__uint_as_float(src[4]) * scale, __uint_as_float(src[5]) * scale);
+            r.w = pack_bf16x2(__uint_as_float(src[6]) * scale, __uint_as_float(src[7]) * scale);
             rowp[j ^ (lane & 7)] = r;
           }
         } else {

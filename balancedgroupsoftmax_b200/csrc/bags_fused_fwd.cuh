@@ -91,9 +91,11 @@ struct FusedCfg {
   // after the mainloop the pipeline stages are idle: [0, 32 KB) stages the dz tiles, then the chunk references
   static constexpr int REF_OFFSET = EPI_WARPS * DZ_BUF_BYTES;
   static constexpr int REF_BYTES = CHUNKS * 32 * EPI_WARPS * 8;
+  static constexpr int ZT_OFFSET = REF_OFFSET + REF_BYTES;          // [MAXG][128] logit of each row's target column
+  static constexpr int ZT_BYTES = MAXG * BLOCK_M * 4;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + XCH_BYTES + LOC_BYTES + MISC_BYTES + 1024;
   static_assert(SMEM_BYTES <= 232448, "fused forward exceeds shared memory");
-  static_assert(REF_OFFSET + REF_BYTES <= STAGES * STAGE_BYTES, "staging + references must fit in the idle pipeline buffers");
+  static_assert(ZT_OFFSET + ZT_BYTES <= STAGES * STAGE_BYTES, "staging + references must fit in the idle pipeline buffers");
   static_assert(32 * DZ_ROW_BYTES <= DZ_BUF_BYTES, "staging buffer too small");
 };
 
@@ -385,13 +387,28 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     for (int g = 0; g < G; ++g)
       if (s_ge[g] <= col_lo || s_gs[g] >= col_hi) loc[(cg * MAXG + g) * BLOCK_M + row_l] = make_float2(-INFINITY, 0.f);
 
+    named_bar_sync(1, 32 * Cfg::EPI_WARPS);   // s_tcol / s_coef (written by the cg == 0 warps) are visible
+
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
     if (warp == 2 && lane == 0) stamp(p.timing, 3);   // accumulators complete
     float2* refs = reinterpret_cast<float2*>(smem + Cfg::REF_OFFSET) + (threadIdx.x - 64);   // [chunk][512 threads]
+    float* s_zt = reinterpret_cast<float*>(smem + Cfg::ZT_OFFSET);
     {
       int g_cur = -2;
+      int tcol_a = -(1 << 30);
       float m_cur = -INFINITY, s_cur = 0.f;
+      // the logit of the row's target column of bin g, for the loss: saved when this warp walks past it
+      // (most chunks hold no row's target: "others" targets sit in each bin's first column)
+      auto capture = [&](int g, int tcol, const float (&zz)[CH], int col0) {
+        const unsigned tq = static_cast<unsigned>(tcol - col0);
+        if (__any_sync(0xffffffffu, tq < static_cast<unsigned>(CH))) {
+          float zt = 0.f;
+#pragma unroll
+          for (int j = 0; j < CH; ++j) zt = (static_cast<unsigned>(j) == tq) ? zz[j] : zt;
+          if (tq < static_cast<unsigned>(CH)) s_zt[g * BLOCK_M + row_l] = zt;
+        }
+      };
       auto flush = [&]() {
         if (g_cur >= 0) loc[(cg * MAXG + g_cur) * BLOCK_M + row_l] = make_float2(m_cur, s_cur);
       };
@@ -408,7 +425,12 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         float z[CH];   // aliases v: the next chunk's load is issued only after the last use of z
 #pragma unroll
         for (int j = 0; j < CH; ++j) z[j] = __uint_as_float(v[j]);
-        if (md.x != g_cur) { flush(); g_cur = md.x; m_cur = -INFINITY; s_cur = 0.f; }
+        if (md.x != g_cur) {
+          flush();
+          g_cur = md.x; m_cur = -INFINITY; s_cur = 0.f;
+          tcol_a = s_tcol[g_cur * BLOCK_M + row_l];
+        }
+        capture(g_cur, tcol_a, z, col_lo + ci * CH);
         uint32_t e[CH];
         float refA, refB = 0.f;
         if (md.y >= CH) {
@@ -462,6 +484,10 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           flush();
           g_cur = md.z; m_cur = cmB; s_cur = accB;
           refA = m_newA; refB = cmB;
+          if (g_cur >= 0) {
+            tcol_a = s_tcol[g_cur * BLOCK_M + row_l];
+            capture(g_cur, tcol_a, z, col_lo + ci * CH);
+          }
         }
         if (ci + 1 < Cfg::CHUNKS && col_lo + (ci + 1) * CH < p.C) BAGS_TMEM_LD16(t_row + (ci + 1) * CH, v);
         BAGS_TMEM_ST16(t_row + ci * CH, e);
@@ -509,20 +535,14 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     tc_fence_after();
 
     int g_cur = -2;
-    float lb_cur = 0.f, coef_cur = 0.f, pt_cur = 1.0f;
+    float lb_cur = 0.f, coef_cur = 0.f;
     int tcol_cur = -1;
-    bool own_cur = false;
-    auto finish_bin = [&]() {   // loss terms of the bin: rows whose target column lies in this warp's range
-      if (g_cur >= 0) {           // warp-uniform
-        float term = own_cur ? coef_cur * (-__logf(pt_cur)) : 0.f;
-        term = warp_sum(term);    // one shared-memory atomic per warp instead of 32 contending CAS loops
-        if (lane == 0) atomicAdd(&s_loss[g_cur], term);
-      }
-    };
+    const float* s_zt = reinterpret_cast<const float*>(smem + Cfg::ZT_OFFSET);
+    // last bin this warp's columns reach: once its loss terms are in, the warp reports to the bookkeeping warp
+    const int g_last = (col_lo < p.C) ? bin_of(((col_hi < p.C) ? col_hi : p.C) - 1) : -1;
+    if (g_last < 0) named_bar_arrive(6, 32 * Cfg::EPI_WARPS + 32);
     auto start_bin = [&](int g) {
       g_cur = g;
-      pt_cur = 1.0f;
-      own_cur = false;
       if (g < 0) { lb_cur = 0.f; coef_cur = 0.f; tcol_cur = -1; return; }
       float2 q[Cfg::CLUSTER];
 #pragma unroll
@@ -535,9 +555,15 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       lb_cur = lse_v * kLog2e;
       coef_cur = s_coef[g * BLOCK_M + row_l];
       tcol_cur = s_tcol[g * BLOCK_M + row_l];
-      own_cur = (tcol_cur >= col_lo && tcol_cur < col_hi);
+      // loss of the bin: rows whose target column lies in this warp's range (its logit was saved in pass A);
+      // one shared-memory atomic per warp instead of 32 contending CAS loops
+      const bool own = (tcol_cur >= col_lo && tcol_cur < col_hi);
+      float term = own ? coef_cur * (lse_v - s_zt[g * BLOCK_M + row_l]) : 0.f;
+      term = warp_sum(term);
+      if (lane == 0) atomicAdd(&s_loss[g], term);
       if (p.lse != nullptr && row < p.N && s_gs[g] >= col_lo && s_gs[g] < col_hi)
         p.lse[static_cast<long long>(row) * G + g] = lse_v;
+      if (g == g_last) { __syncwarp(); named_bar_arrive(6, 32 * Cfg::EPI_WARPS + 32); }
     };
 
     uint32_t v[CH];
@@ -556,7 +582,7 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       float d[CH];   // aliases v (e = exp(z - m_chunk) from pass A) until the scaling below
 #pragma unroll
       for (int j = 0; j < CH; ++j) d[j] = __uint_as_float(v[j]);
-      if (md.x != g_cur) { finish_bin(); start_bin(md.x); }
+      if (md.x != g_cur) start_bin(md.x);
       if (warp == 2 && lane == 0 && ci == 0) stamp_bank(p.timing, 2, 6);
       if (md.y >= CH) {
         const float f = fast_exp2(fmaf(rf.x, kLog2e, -lb_cur));   // exp(m_chunk - lse)
@@ -568,7 +594,7 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 #pragma unroll
           for (int j = 0; j < CH; ++j) {
             float dj = d[j] * gf;
-            if (j == tq) { pt_cur = d[j] * f; dj -= coef_cur; }
+            if (j == tq) dj -= coef_cur;
             d[j] = dj;
           }
         } else {
@@ -586,10 +612,6 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         const float fA = fast_exp2(fmaf(rf.x, kLog2e, -lb_cur));
         const float gfA = coef_cur * fA, coefA = coef_cur;
         const int tqA = tcol_cur - col0;          // target column of bin A relative to the chunk (maybe outside)
-#pragma unroll
-        for (int j = 0; j < CH; ++j)
-          if (j == tqA && j < bpos) pt_cur = d[j] * fA;
-        finish_bin();
         start_bin(md.z);
         const float fB = (md.z >= 0) ? fast_exp2(fmaf(rf.y, kLog2e, -lb_cur)) : 0.f;
         const float gfB = coef_cur * fB, coefB = coef_cur;
@@ -599,7 +621,7 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           const bool a = j < bpos;
           float dj = d[j] * (a ? gfA : gfB);
           if (j == tqA && a) dj -= coefA;
-          if (j == tqB && !a) { pt_cur = d[j] * fB; dj -= coefB; }
+          if (j == tqB && !a) dj -= coefB;
           d[j] = dj;
         }
       }
@@ -662,54 +684,49 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     }
     if (warp == 2 && lane == 0) stamp2(p.timing, 3);      // chunk loop of pass C done (this warp)
     if (warp == 17 && lane == 0) stamp2(p.timing, 7);
-    finish_bin();
     if (warp == 2 && lane == 0) stamp(p.timing, 6);   // pass C done
     tc_fence_before();
     named_bar_arrive(2, 32 * Cfg::EPI_WARPS + 32);   // this warp is done with TMEM (warp 1 deallocates)
 
-    // ---- CTA results -> global ----
     if (p.colsum != nullptr && p.want_dz) {   // optional per-row-tile bias-gradient partials
       named_bar_sync(3, 32 * Cfg::EPI_WARPS);
       const int et = threadIdx.x - 64;   // 0..511
       for (int c = et; c < BLOCK_N; c += 32 * Cfg::EPI_WARPS)
         if (n0 + c < p.C) p.colsum[static_cast<long long>(row_tile) * p.C + n0 + c] = s_colsum[c];
     }
-    // losses: one warp stays for the bookkeeping, the other fifteen leave
-    if (ew != 0) {
-      named_bar_arrive(1, 32 * Cfg::EPI_WARPS);
-    } else {
-      named_bar_sync(1, 32 * Cfg::EPI_WARPS);           // s_loss is final
-      if (warp == 2 && lane == 0) stamp2(p.timing, 4);  // all 16 warps done with pass C
-      unsigned int last = 0;
-      if (lane == 0) {
-        float4* dst = reinterpret_cast<float4*>(p.part + static_cast<size_t>(blockIdx.x) * kMaxG);
-        dst[0] = make_float4(s_loss[0], s_loss[1], s_loss[2], s_loss[3]);
-        dst[1] = make_float4(s_loss[4], s_loss[5], s_loss[6], s_loss[7]);
-        last = (atom_add_release_gpu(p.counter, 1u) == gridDim.x - 1) ? 1u : 0u;   // release: the partials first
-      }
-      last = __shfl_sync(0xffffffffu, last, 0);
-      if (last) {   // the last CTA of the grid sums the per-CTA partials in a fixed order
-        __threadfence();
-        float acc[kMaxG];
-#pragma unroll
-        for (int g = 0; g < kMaxG; ++g) acc[g] = 0.f;
-        for (int b = lane; b < static_cast<int>(gridDim.x); b += 32) {
-          const float4* src = reinterpret_cast<const float4*>(p.part + static_cast<size_t>(b) * kMaxG);
-          const float4 u = __ldcg(src), w = __ldcg(src + 1);
-          acc[0] += u.x; acc[1] += u.y; acc[2] += u.z; acc[3] += u.w;
-          acc[4] += w.x; acc[5] += w.y; acc[6] += w.z; acc[7] += w.w;
-        }
-#pragma unroll
-        for (int g = 0; g < kMaxG; ++g) {
-          const float t = warp_sum(acc[g]);
-          if (lane == 0 && g < G) p.loss[g] = t;   // already divided by avg (coef = w/avg)
-        }
-        if (lane == 0) *p.counter = 0u;
-      }
-    }
-    if (warp == 2 && lane == 0) stamp2(p.timing, 5);    // bookkeeping warp done
   } else if (warp == 1) {
-    named_bar_sync(2, 32 * Cfg::EPI_WARPS + 32);        // every epilogue warp has finished reading TMEM
+    // ---- loss bookkeeping by the (idle) MMA warp, overlapped with pass C: every epilogue warp reports as soon
+    // as the loss terms of its last bin are in shared memory ----
+    named_bar_sync(6, 32 * Cfg::EPI_WARPS + 32);
+    if (lane == 0) stamp2(p.timing, 4);                   // s_loss final
+    unsigned int last = 0;
+    if (lane == 0) {
+      float4* dst = reinterpret_cast<float4*>(p.part + static_cast<size_t>(blockIdx.x) * kMaxG);
+      dst[0] = make_float4(s_loss[0], s_loss[1], s_loss[2], s_loss[3]);
+      dst[1] = make_float4(s_loss[4], s_loss[5], s_loss[6], s_loss[7]);
+      last = (atom_add_release_gpu(p.counter, 1u) == gridDim.x - 1) ? 1u : 0u;   // release: the partials first
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {   // the last CTA of the grid sums the per-CTA partials in a fixed order
+      __threadfence();
+      float acc[kMaxG];
+#pragma unroll
+      for (int g = 0; g < kMaxG; ++g) acc[g] = 0.f;
+      for (int b = lane; b < static_cast<int>(gridDim.x); b += 32) {
+        const float4* src = reinterpret_cast<const float4*>(p.part + static_cast<size_t>(b) * kMaxG);
+        const float4 u = __ldcg(src), w = __ldcg(src + 1);
+        acc[0] += u.x; acc[1] += u.y; acc[2] += u.z; acc[3] += u.w;
+        acc[4] += w.x; acc[5] += w.y; acc[6] += w.z; acc[7] += w.w;
+      }
+#pragma unroll
+      for (int g = 0; g < kMaxG; ++g) {
+        const float t = warp_sum(acc[g]);
+        if (lane == 0 && g < G) p.loss[g] = t;   // already divided by avg (coef = w/avg)
+      }
+      if (lane == 0) *p.counter = 0u;
+    }
+    if (lane == 0) stamp2(p.timing, 5);                   // bookkeeping done
+    named_bar_sync(2, 32 * Cfg::EPI_WARPS + 32);          // every epilogue warp has finished reading TMEM
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }

@@ -531,7 +531,16 @@ struct BwdPrepParams {
   const void* w; void* wscr; long long ldw; const float* gout; GroupTable gt;
   const void* dz; long long ldd; int N; float* colpart; int ctiles;
   int z_ctas, s_ctas, c_ctas;   // CTA ranges of the three jobs (0 = job disabled)
+  int skip_scale_if_uniform;    // the consumer reads W itself and scales its output when all gout[g] are equal
 };
+
+// all per-bin upstream gradients equal?  (then diag(gout) W == gout[0] W: no scaled copy of W is needed)
+__device__ __forceinline__ bool gout_uniform(const float* gout, int G, float& g0) {
+  g0 = __ldg(gout);
+  bool u = true;
+  for (int g = 1; g < G; ++g) u = u && (__ldg(gout + g) == g0);
+  return u;
+}
 
 // One job of the backward preparation, executed by 256 threads (`tid` in [0,256)).  `b` indexes the job like a CTA
 // of bwd_prep_kernel would; `s_part` is 2 KB of shared memory; BAR_ID < 0 synchronises with __syncthreads(),
@@ -549,6 +558,10 @@ __device__ __forceinline__ void bwd_prep_job(const BwdPrepParams& p, int b, int 
   } else if (b < p.z_ctas + p.s_ctas) {
     // ---- (2) row-scaled copy of W: flat index space, four independent 16-byte loads in flight per thread ----
     constexpr int V = F32 ? 4 : 8;
+    if (p.skip_scale_if_uniform) {
+      float g0;
+      if (gout_uniform(p.gout, p.gt.G, g0)) return;
+    }
     const int vec_per_row = p.K / V;
     const long long total = static_cast<long long>(p.C) * vec_per_row;
     const long long stride = static_cast<long long>(p.s_ctas) * 256;
