@@ -546,10 +546,10 @@ scale_colsum_kernel(const float* __restrict__ colsum, int tiles, float* __restri
 }
 
 
-template <bool TF32>
+template <bool TF32, int MT>
 static int launch_bwd_merged(const void* dz, long long ldd, const void* x, long long ldx, const void* wb, const void* w,
                              long long ldw, const BwdFusedParams& p0, const DeviceInfo& di, cudaStream_t stream) {
-  using Cfg = BwdCfg<TF32>;
+  using Cfg = BwdCfg<TF32, MT>;
   const int dtype = TF32 ? BAGS_DTYPE_F32 : BAGS_DTYPE_BF16;
   CUtensorMap t_dzT, t_xT, t_dz, t_wT, t_w;
   int rc;
@@ -560,7 +560,7 @@ static int launch_bwd_merged(const void* dz, long long ldd, const void* x, long 
   if ((rc = make_tmap(&t_wT, wb, dtype, p0.Kf, p0.C, ldw, Cfg::SLAB, Cfg::BLOCK_K, TF32))) return rc;
   BwdFusedParams p = p0;
   p.timing = g_timing ? g_timing + 2048 * 8 : nullptr;   // rows [2048, ..): the forward of the same step uses [0, 2048)
-  auto kernel = bags_bwd_fused_kernel<TF32>;
+  auto kernel = bags_bwd_fused_kernel<TF32, MT>;
   BAGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int units = p.dw_units + p.dx_units;
   const int grid = units < di.num_sms ? units : di.num_sms;
@@ -767,8 +767,21 @@ extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long 
     }
     bp.dx_uniform_ok = (want_scale && env_int("BAGS_DX_UNIFORM", 1)) ? 1 : 0;
     bp.prep.skip_scale_if_uniform = (bp.dx_uniform_ok && prep_jobs > 0) ? 1 : 0;
-    return bf ? launch_bwd_merged<false>(dz, ldd, x, ldx, wb, w, ldw, bp, di, stream)
-              : launch_bwd_merged<true>(dz, ldd, x, ldx, wb, w, ldw, bp, di, stream);
+    // 256 x 256 units (two accumulator sub-tiles sharing the B tile) once the problem fills the machine with them
+    const int mt_auto = (bp.dx_units + bp.dw_m_tiles * bp.dw_n_tiles >= di.num_sms) ? 2 : 1;
+    if (env_int("BAGS_BWD_MT", mt_auto) == 2) {
+      bp.dw_m_tiles = (C + 255) / 256;
+      bp.dx_m_tiles = (N + 255) / 256;
+      bp.dx_units = bp.dx_m_tiles * bp.dx_n_tiles;
+      bp.dw_splits = env_int("BAGS_DW_SPLITS", pick_pair_splits(bp.dw_m_tiles * bp.dw_n_tiles, bp.dw_kblocks, bp.dx_units,
+                                                                bp.dx_kblocks, di.num_sms));
+      if (bp.dw_splits > bp.dw_kblocks) bp.dw_splits = bp.dw_kblocks;
+      bp.dw_units = bp.dw_m_tiles * bp.dw_n_tiles * bp.dw_splits;
+      return bf ? launch_bwd_merged<false, 2>(dz, ldd, x, ldx, wb, w, ldw, bp, di, stream)
+                : launch_bwd_merged<true, 2>(dz, ldd, x, ldx, wb, w, ldw, bp, di, stream);
+    }
+    return bf ? launch_bwd_merged<false, 1>(dz, ldd, x, ldx, wb, w, ldw, bp, di, stream)
+              : launch_bwd_merged<true, 1>(dz, ldd, x, ldx, wb, w, ldw, bp, di, stream);
   }
 
   if (dW != nullptr && N > 0) {

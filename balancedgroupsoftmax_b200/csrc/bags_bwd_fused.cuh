@@ -48,9 +48,16 @@ __device__ __forceinline__ void wait_grid_jobs(const unsigned int* ctr, unsigned
   }
 }
 
-template <bool TF32>
+// MT = number of 128-row accumulator sub-tiles of one unit.  MT = 1: 128 x 256 units, two TMEM accumulator stages
+// (a unit's epilogue overlaps the next unit's mainloop), 4 pipeline stages of 48 KB.  MT = 2: 256 x 256 units -- the
+// B tile is shared by two MMAs, so a unit ingests 64 KB instead of 96 KB per 2 x (128 x 256 x 64) of work and the
+// mainloop is no longer bound by the SM's 64 B/clk L2 port; all 512 TMEM columns hold one unit (no epilogue
+// overlap), 3 pipeline stages of 64 KB.  Pays off when the problem is about one wave of 256 x 256 units.
+template <bool TF32, int MT = 1>
 struct BwdCfg {
-  static constexpr int BLOCK_M = 128, BLOCK_N = 256, STAGES = 4, ACC_STAGES = 2;
+  static_assert(MT == 1 || MT == 2, "one or two accumulator sub-tiles");
+  static constexpr int SUB_M = 128;
+  static constexpr int BLOCK_M = SUB_M * MT, BLOCK_N = 256, STAGES = (MT == 1) ? 4 : 3, ACC_STAGES = 2 / MT;
   static constexpr int ELT = TF32 ? 4 : 2;
   static constexpr int BLOCK_K = 128 / ELT, UMMA_K = 32 / ELT, K_STEPS = BLOCK_K / UMMA_K;
   static constexpr int SLAB = 128 / ELT;
@@ -61,7 +68,7 @@ struct BwdCfg {
   static_assert(SMEM_BYTES <= 232448, "exceeds shared memory");
 };
 
-template <bool TF32>
+template <bool TF32, int MT>
 __global__ void __launch_bounds__(64 + 32 * 8, 1)
 bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as MN-major A of dW  (box SLAB x BLOCK_K)
                       const __grid_constant__ CUtensorMap tmap_xT,    // x  as MN-major B of dW  (box SLAB x BLOCK_K)
@@ -70,7 +77,7 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
                       const __grid_constant__ CUtensorMap tmap_w,     // W  (unscaled), same geometry: used instead of
                                                                       // W' when all gout[g] are equal
                       const BwdFusedParams p) {
-  using Cfg = BwdCfg<TF32>;
+  using Cfg = BwdCfg<TF32, MT>;
   constexpr int BLOCK_M = Cfg::BLOCK_M, BLOCK_N = Cfg::BLOCK_N, BLOCK_K = Cfg::BLOCK_K, STAGES = Cfg::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
@@ -179,8 +186,9 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
   } else if (warp == 1) {
     // ===================== UMMA issuer (single thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc_dw = make_instr_desc(TF32 ? 2u : 1u, true, true, BLOCK_M, BLOCK_N);
-      constexpr uint32_t idesc_dx = make_instr_desc(TF32 ? 2u : 1u, false, true, BLOCK_M, BLOCK_N);
+      constexpr uint32_t idesc_dw = make_instr_desc(TF32 ? 2u : 1u, true, true, Cfg::SUB_M, BLOCK_N);
+      constexpr uint32_t idesc_dx = make_instr_desc(TF32 ? 2u : 1u, false, true, Cfg::SUB_M, BLOCK_N);
+      constexpr uint32_t SUB_A_BYTES = Cfg::SUB_M * 128;   // one 128-row sub-tile of A, in either operand layout
       constexpr uint64_t MN_LAYOUT = TF32 ? kSwizzle128B_Base32B : kSwizzle128B;
       constexpr uint32_t MN_LBO = BLOCK_K * 128, MN_SBO = TF32 ? 512 : 1024, MN_KSTEP = Cfg::UMMA_K * 128;
       int stage = 0;
@@ -192,7 +200,7 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
         const uint32_t acc_phase = (local / Cfg::ACC_STAGES) & 1u;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        const uint32_t d_tmem = tmem_base + acc * MT * BLOCK_N;
         for (int kb = un.kb0; kb < un.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -203,14 +211,18 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
           for (int k = 0; k < Cfg::K_STEPS; ++k) {
             const uint64_t bdesc = make_smem_desc(sb + k * MN_KSTEP, MN_LBO, MN_SBO, MN_LAYOUT);
             const uint32_t accum = (kb > un.kb0 || k > 0) ? 1u : 0u;
-            if (un.is_dw) {
-              const uint64_t adesc = make_smem_desc(sa + k * MN_KSTEP, MN_LBO, MN_SBO, MN_LAYOUT);
-              if (TF32) umma_tf32(d_tmem, adesc, bdesc, idesc_dw, accum);
-              else      umma_bf16(d_tmem, adesc, bdesc, idesc_dw, accum);
-            } else {
-              const uint64_t adesc = make_smem_desc(sa + k * 32, 16, 1024, kSwizzle128B);
-              if (TF32) umma_tf32(d_tmem, adesc, bdesc, idesc_dx, accum);
-              else      umma_bf16(d_tmem, adesc, bdesc, idesc_dx, accum);
+#pragma unroll
+            for (int h = 0; h < MT; ++h) {   // the sub-tiles share the B descriptor
+              const uint32_t sah = sa + h * SUB_A_BYTES;
+              if (un.is_dw) {
+                const uint64_t adesc = make_smem_desc(sah + k * MN_KSTEP, MN_LBO, MN_SBO, MN_LAYOUT);
+                if (TF32) umma_tf32(d_tmem + h * BLOCK_N, adesc, bdesc, idesc_dw, accum);
+                else      umma_bf16(d_tmem + h * BLOCK_N, adesc, bdesc, idesc_dw, accum);
+              } else {
+                const uint64_t adesc = make_smem_desc(sah + k * 32, 16, 1024, kSwizzle128B);
+                if (TF32) umma_tf32(d_tmem + h * BLOCK_N, adesc, bdesc, idesc_dx, accum);
+                else      umma_bf16(d_tmem + h * BLOCK_N, adesc, bdesc, idesc_dx, accum);
+              }
             }
           }
           umma_commit(&empty_bar[stage]);
@@ -250,12 +262,14 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
     }
     for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++local) {
       const Unit un = decode(u);
-      const int m_warp = un.m_tile * BLOCK_M + quarter * 32;
-      const int m = m_warp + lane;
       const int n0 = un.n_tile * BLOCK_N;
       const int acc = local % Cfg::ACC_STAGES;
       const uint32_t acc_phase = (local / Cfg::ACC_STAGES) & 1u;
       const int Mrows = un.is_dw ? p.C : p.Nr;
+#pragma unroll 1
+      for (int h = 0; h < MT; ++h) {
+      const int m_warp = un.m_tile * BLOCK_M + h * Cfg::SUB_M + quarter * 32;
+      const int m = m_warp + lane;
 
       float scale = dx_scale;
       if (un.is_dw) {
@@ -280,10 +294,12 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
         }
       }
 
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      if (local == 0 && warp == 2 && lane == 0) stamp(p.timing, 4);
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+      if (h == 0) {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        if (local == 0 && warp == 2 && lane == 0) stamp(p.timing, 4);
+      }
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (acc * MT + h) * BLOCK_N;
       const bool out_bf16 = (!un.is_dw) && !TF32;
       const int epi_cols = out_bf16 ? 64 : 32;
 #pragma unroll 1
@@ -338,6 +354,7 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
         }
         __syncwarp();
       }
+      }   // sub-tiles
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
