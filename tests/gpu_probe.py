@@ -259,6 +259,7 @@ def case_timeline(name):
         nat.check(nat.lib().bags_debug_set_timing(None), 'set_timing')
         off = 2048 if 'bwd_merged' in label else 0   # the merged backward stamps rows [2048, ..)
         tb = tbuf[off:off + nctas].cpu().double()
+        tb = tb[tb[:, 0] > 0]   # the grid may be smaller than nctas (e.g. 144 units of 256 x 256)
         if 'bwd_merged' in label and os.environ.get('BAGS_BWD_PAIR') == '1':
             tb = tb[0::2]   # only the leader CTA of a pair stamps the MMA slots
         t0 = tb[:, 0].min()
@@ -273,6 +274,7 @@ def case_timeline(name):
         d['cta_life_us(mean,max)'] = [round(float(((tb[:, 6] - tb[:, 0]) / 1e3).mean()), 2),
                                       round(float(((tb[:, 6] - tb[:, 0]) / 1e3).max()), 2)]
         d['distinct_sms'] = int(tb[:, 7].unique().numel())
+        d['ctas'] = int(tb.shape[0])
         if 'fused' in label:   # second stamp bank: finer epilogue phases (us after 'acc done')
             t2 = tbuf[nctas:2 * nctas].cpu().double()
             base = tb[:, 3]
@@ -361,6 +363,7 @@ def case_steptimeline(name):
         tb = s['tb'].cpu().double()
         f = tb[:128]
         bw = tb[2048:2048 + 148]
+        bw = bw[bw[:, 0] > 0]
         if t0 is None:
             t0 = f[:, 0].min()
         us = lambda v: round(float((v - t0) / 1e3), 2)
@@ -379,7 +382,7 @@ def case_steptimeline(name):
     early = []
     for i in range(POOL - 1):
         fe = sets[i + 1]['tb'][:128, 0].cpu().double()
-        be = sets[i]['tb'][2048:2048 + 148, 6].cpu().double().max()
+        be = sets[i]['tb'][2048:2048 + 148, 6].cpu().double().max()   # (unused rows are zero)
         early.append(int((fe < be).sum()))
     res['fwd_ctas_started_before_prev_bwd_end'] = early
     return res
