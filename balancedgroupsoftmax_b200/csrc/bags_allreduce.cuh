@@ -1,0 +1,142 @@
+// Gradient exchange of the fc_cls bucket over NVLink peer memory (sm_100a, NVSwitch).
+//
+// Replaces the reference's NCCL all-reduce + div of the flattened gradients
+// (mmdet/core/utils/dist_utils.py:9-41: _allreduce_coalesced -> dist.all_reduce, tensor.div_(world_size),
+// copy back) by ONE kernel working directly on the ranks' gradient buckets, which live in symmetric
+// (peer-mapped) memory:
+//
+//   barrier (all ranks' local dW / db are complete)            flag words in the peers' buffers, sys-scope CAS
+//   two-shot exchange: rank r owns vectors [r*chunk, (r+1)*chunk)
+//       NVLS   : multimem.ld_reduce.add.v4.f32 on the multicast address (the switch sums the N copies)
+//                -> * scale -> multimem.st.v4.f32 (the switch broadcasts to the N copies)
+//       peer   : ld.relaxed.sys.v4 from each rank's copy in rank order -> * scale -> st to each rank's copy
+//   barrier (every rank's slice has landed everywhere)
+//
+// Each element is reduced by exactly one rank in a fixed order, so all ranks end with bit-identical buckets.
+// 5.07 MB per head: 2 * (N-1)/N * 5.07 MB cross each GPU's links (~6-9 us at 770 GB/s) plus two flag round
+// trips; NCCL's ring/tree launch measured ~53 us per step for the same bucket (profiles/r01_bench_2gpu_v5.json).
+//
+// Flags: uint32 [blocks][world] inside every rank's buffer, zero between launches (put = CAS 0->1 on the target,
+// wait = CAS 1->0 on the own copy), so graph replays need no reset.  All spins are bounded (trap).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "bags_ptx.cuh"
+
+namespace bags {
+
+constexpr int kMaxRanks = 16;
+constexpr int kArMaxBlocks = 64;
+constexpr int kArThreads = 512;
+
+struct AllReduceParams {
+  float* peer[kMaxRanks];   // this process's mapping of every rank's bucket (peer[rank] is the local one)
+  float* mc;                // multicast mapping of the bucket (NVLS) or nullptr
+  long long flag_off;       // byte offset of the flag words inside the bucket allocation
+  long long count;          // floats to reduce (multiple of 4), starting at the bucket base
+  int rank, world;
+  float scale;              // 1/world for the mean (dist_utils.py:23), 1 for a sum
+};
+
+__device__ __forceinline__ uint32_t cas_release_sys(uint32_t* p, uint32_t cmp, uint32_t val) {
+  uint32_t old;
+  asm volatile("atom.global.release.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(cmp), "r"(val) : "memory");
+  return old;
+}
+__device__ __forceinline__ uint32_t cas_acquire_sys(uint32_t* p, uint32_t cmp, uint32_t val) {
+  uint32_t old;
+  asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(cmp), "r"(val) : "memory");
+  return old;
+}
+__device__ __forceinline__ float4 ld_relaxed_sys_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_f4(float* p, const float4 v) {
+  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+               ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 multimem_ld_reduce_f4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_f4(float* mc, const float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+               ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// Block-level barrier across ranks: block b of every rank meets block b of every other rank.
+// Thread t < world signals rank t and waits for rank t's signal.  Preceded / followed by __syncthreads() so the
+// release / acquire of the signalling threads order the whole block's accesses (PTX memory model: cumulativity).
+__device__ __forceinline__ void rank_barrier(const AllReduceParams& p) {
+  __syncthreads();
+  if (threadIdx.x < static_cast<unsigned>(p.world)) {
+    const int t = static_cast<int>(threadIdx.x);
+    uint32_t* theirs = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(p.peer[t]) + p.flag_off) +
+                       blockIdx.x * p.world + p.rank;
+    uint32_t* mine = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(p.peer[p.rank]) + p.flag_off) +
+                     blockIdx.x * p.world + t;
+    uint32_t spins = 0;
+    while (cas_release_sys(theirs, 0u, 1u) != 0u) {
+      if (++spins > (1u << 24)) { printf("bags: all-reduce put timed out (rank %d -> %d, block %d)\n", p.rank, t, (int)blockIdx.x); __trap(); }
+    }
+    spins = 0;
+    while (cas_acquire_sys(mine, 1u, 0u) != 1u) {
+      __nanosleep(32);
+      if (++spins > (1u << 24)) { printf("bags: all-reduce wait timed out (rank %d <- %d, block %d)\n", p.rank, t, (int)blockIdx.x); __trap(); }
+    }
+  }
+  __syncthreads();
+}
+
+template <bool MULTIMEM>
+__global__ void __launch_bounds__(kArThreads)
+bags_grad_allreduce_kernel(const AllReduceParams p) {
+  pdl_trigger();   // the next kernel of the stream (next step's sampler / forward mainloop) may start launching
+  pdl_wait();      // the local gradients come from the preceding backward kernel
+  rank_barrier(p);
+
+  const long long vecs = p.count >> 2;
+  const long long chunk = (vecs + p.world - 1) / p.world;
+  const long long v0 = chunk * p.rank;
+  const long long v1 = (v0 + chunk < vecs) ? (v0 + chunk) : vecs;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  constexpr int UNROLL = 4;   // loads in flight per thread: one NVLink round trip is ~2 us
+  for (long long v = v0 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < v1; v += stride * UNROLL) {
+    float4 acc[UNROLL];
+    if (MULTIMEM) {
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+        if (v + u * stride < v1) acc[u] = multimem_ld_reduce_f4(p.mc + 4 * (v + u * stride));
+    } else {
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < p.world; ++r) {
+        float4 t[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+          if (v + u * stride < v1) t[u] = ld_relaxed_sys_f4(p.peer[r] + 4 * (v + u * stride));
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+          if (v + u * stride < v1) { acc[u].x += t[u].x; acc[u].y += t[u].y; acc[u].z += t[u].z; acc[u].w += t[u].w; }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      if (v + u * stride >= v1) continue;
+      const float4 o = make_float4(acc[u].x * p.scale, acc[u].y * p.scale, acc[u].z * p.scale, acc[u].w * p.scale);
+      if (MULTIMEM) {
+        multimem_st_f4(p.mc + 4 * (v + u * stride), o);
+      } else {
+        for (int r = 0; r < p.world; ++r) st_relaxed_sys_f4(p.peer[r] + 4 * (v + u * stride), o);
+      }
+    }
+  }
+  rank_barrier(p);
+}
+
+}  // namespace bags

@@ -60,6 +60,16 @@ def peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source='fallback')
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
+        k = d.get(kernel)
+        return None if k is None else int(k['dram_read'] + k['dram_write'])
+    except Exception:
+        return None
+
+
 def make_labels(torch, n, num_classes, gen):
     """25 % positives first in every 512-block (RandomSampler num=512, pos_fraction=.25;
     mmdet/core/bbox/bbox_target.py:44-51), class ids uniform on 1..num_classes-1."""
@@ -259,8 +269,8 @@ def run_ours(args):
         last['loss'] = loss
         return loss
 
-    # sampler, fused fwd (or GEMM + grouped CE), bwd_prep, merged dW+dX GEMM
-    kernels_per_step = 5 if args.unfused else 4
+    # sampler, fused fwd (or GEMM + grouped CE), merged backward (preparation jobs + dW + dX units in one launch)
+    kernels_per_step = 4 if args.unfused else 3
 
     stream = torch.cuda.Stream(device=dev)
     use_graph = not args.no_graph
@@ -478,6 +488,7 @@ def run_ours(args):
             kernel_us['sample_others'] = graphed(lambda s: ops.sample_others(s['labels'], dt, RATIO, 7))
         except Exception as ex:  # pragma: no cover
             log('per-kernel timing failed: %r' % (ex,))
+        TF = dtype != torch.bfloat16
         flops = {'fc_cls_gemm': 2.0 * n * K_FEAT * C, 'fused_fwd': 2.0 * n * K_FEAT * C, 'dW_gemm': 2.0 * n * K_FEAT * C,
                  'dX_gemm': 2.0 * n * K_FEAT * C, 'bwd_merged(prep+dW+dX)': 4.0 * n * K_FEAT * C}
         bytes_ce = n * C * 4 + n * C * elt + n * 8 + dt.G * n   # read fp32 logits, write dz, labels, masks
@@ -487,13 +498,13 @@ def run_ours(args):
                 peak = pk['bf16_tflops_sustained'] if dtype == torch.bfloat16 else pk['bf16_tflops_sustained'] / 2.0
                 ach = flops[dom] / (kernel_us[dom] * 1e-6) / 1e12
                 roof = {'kernel': dom, 'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
-                        'frac': ach / peak, 'traffic': None,
+                        'frac': ach / peak, 'traffic': (ncu_traffic(dom) if n == N_ROIS and not TF else None),
                         'peak_source': pk['source'] + (' (sustained bf16)' if dtype == torch.bfloat16 else
                                                        ' (sustained bf16 / 2 for tf32)')}
             else:
                 ach = bytes_ce / (kernel_us[dom] * 1e-6) / 1e9
                 roof = {'kernel': dom, 'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                        'frac': ach / pk['hbm_gbs'], 'traffic': None, 'peak_source': pk['source'],
+                        'frac': ach / pk['hbm_gbs'], 'traffic': ncu_traffic(dom), 'peak_source': pk['source'],
                         'algorithmic_bytes': bytes_ce}
         step_flops = 6.0 * n * K_FEAT * C
         peak_t = pk['bf16_tflops_sustained'] if dtype == torch.bfloat16 else pk['bf16_tflops_sustained'] / 2.0
