@@ -16,6 +16,7 @@
 #include "bags_fused_fwd.cuh"
 #include "bags_bwd_fused.cuh"
 #include "bags_kernels.cuh"
+#include "bags_allreduce.cuh"
 
 using namespace bags;
 
@@ -821,6 +822,53 @@ extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long 
                 : launch_gemm_pdl<256, false, true, EPI_STORE_F32, true, 4>(ga, di, stream);
     if (rc) return rc;
   }
+  return BAGS_OK;
+}
+
+// ----------------------------------------------------------------------------
+// gradient exchange over NVLink peer memory (one kernel; see bags_allreduce.cuh)
+// ----------------------------------------------------------------------------
+extern "C" size_t bags_grad_allreduce_flag_bytes(int world) {
+  if (world < 1) world = 1;
+  return static_cast<size_t>(kArMaxBlocks) * static_cast<size_t>(world) * sizeof(uint32_t);
+}
+
+extern "C" int bags_grad_allreduce(void* const* peer_bufs_host, void* mc_buf, long long flag_off_bytes,
+                                   long long count, int rank, int world, float scale, int max_blocks,
+                                   void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BAGS_REQUIRE(peer_bufs_host != nullptr, "bags_grad_allreduce: peer_bufs_host is NULL");
+  BAGS_REQUIRE(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world,
+               "bags_grad_allreduce: bad rank %d / world %d (max %d ranks)", rank, world, kMaxRanks);
+  BAGS_REQUIRE(count >= 0 && (count % 4) == 0, "bags_grad_allreduce: count=%lld must be a multiple of 4 floats", count);
+  BAGS_REQUIRE(flag_off_bytes >= count * 4 && (flag_off_bytes % 16) == 0,
+               "bags_grad_allreduce: the flag words must follow the data (flag_off_bytes=%lld, data bytes=%lld)",
+               flag_off_bytes, count * 4);
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  AllReduceParams p{};
+  for (int r = 0; r < world; ++r) {
+    BAGS_REQUIRE(peer_bufs_host[r] != nullptr && (reinterpret_cast<uintptr_t>(peer_bufs_host[r]) & 15) == 0,
+                 "bags_grad_allreduce: peer buffer %d is NULL or not 16-byte aligned", r);
+    p.peer[r] = static_cast<float*>(peer_bufs_host[r]);
+  }
+  BAGS_REQUIRE((reinterpret_cast<uintptr_t>(mc_buf) & 15) == 0, "bags_grad_allreduce: multicast buffer not 16-byte aligned");
+  p.mc = static_cast<float*>(mc_buf);
+  p.flag_off = flag_off_bytes;
+  p.count = count;
+  p.rank = rank; p.world = world; p.scale = scale;
+  if (count == 0) return BAGS_OK;
+  // enough threads to keep one vector per thread and unroll slot in flight, at most kArMaxBlocks blocks
+  const long long per_rank = (count / 4 + world - 1) / world;
+  long long blocks = (per_rank + static_cast<long long>(kArThreads) * 4 - 1) / (static_cast<long long>(kArThreads) * 4);
+  if (blocks < 1) blocks = 1;
+  if (max_blocks <= 0 || max_blocks > kArMaxBlocks) max_blocks = kArMaxBlocks;
+  if (blocks > max_blocks) blocks = max_blocks;
+  // every rank must launch the same grid: `blocks` depends only on (count, world, max_blocks)
+  if (p.mc != nullptr && !env_int("BAGS_AR_NO_MULTIMEM", 0))
+    BAGS_CUDA(launch_pdl(bags_grad_allreduce_kernel<true>, dim3(static_cast<unsigned>(blocks)), dim3(kArThreads), 0, stream, p));
+  else
+    BAGS_CUDA(launch_pdl(bags_grad_allreduce_kernel<false>, dim3(static_cast<unsigned>(blocks)), dim3(kArThreads), 0, stream, p));
   return BAGS_OK;
 }
 

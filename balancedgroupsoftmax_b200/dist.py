@@ -1,4 +1,4 @@
-"""Data-parallel gradient exchange for the head: one NCCL all-reduce over NVLink.
+"""Data-parallel gradient exchange for the head over NVLink: one peer-memory kernel (PeerGradBucket), or NCCL.
 
 Restates mmdet/core/utils/dist_utils.py:9-58 (``_allreduce_coalesced`` /
 ``allreduce_grads``): flatten all trainable grads by dtype into one bucket,
@@ -9,8 +9,10 @@ and callers that allocate their grads as views of one flat bucket
 """
 from __future__ import annotations
 
+import ctypes as C
+import os
 from collections import OrderedDict
-from typing import Iterable, List, Tuple
+from typing import Iterable, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -63,3 +65,95 @@ def flat_grad_bucket(shapes: List[Tuple[int, ...]], device, dtype=torch.float32)
         views.append(flat[off:off + n].view(*s))
         off += n
     return flat, views
+
+
+# ---------------------------------------------------------------------------------------------------
+# NVLink peer-memory exchange (libbags_b200.so: bags_grad_allreduce) -- the B200 path
+# ---------------------------------------------------------------------------------------------------
+class PeerGradBucket(object):
+    """Flat fp32 gradient bucket in symmetric (peer-mapped) memory + its one-kernel all-reduce.
+
+    The reference flattens the grads, calls ``dist.all_reduce`` (NCCL), divides by the world size and copies back
+    (mmdet/core/utils/dist_utils.py:9-41).  Here the backward kernels write dW / db straight into ``views`` of a bucket
+    that every rank has mapped through NVLink, and ``allreduce_()`` launches ``bags_grad_allreduce``: cross-rank
+    barrier, two-shot reduction over the NVSwitch multicast mapping (``multimem.ld_reduce`` / ``multimem.st``) or,
+    without multicast support, plain peer loads / stores, cross-rank barrier -- one stream-ordered kernel that is
+    CUDA-graph capturable and needs no host synchronisation.
+
+    Allocation / rendezvous go through ``torch.distributed._symmetric_memory`` (plumbing only).  ``available()``
+    tells whether that works in this process group; callers fall back to ``allreduce_flat_`` (NCCL) otherwise.
+    """
+
+    def __init__(self, shapes: List[Tuple[int, ...]], device, group=None, mean: bool = True, max_blocks: int = 0):
+        import torch.distributed._symmetric_memory as symm
+        from . import _native
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.mean = mean
+        self.max_blocks = int(max_blocks)
+        sizes = [int(torch.Size(s).numel()) for s in shapes]
+        self.numel = sum(sizes)
+        self.count = (self.numel + 3) // 4 * 4                       # the kernel moves 16-byte vectors
+        self.flag_off = (self.count * 4 + 255) // 256 * 256
+        flag_bytes = int(_native.lib().bags_grad_allreduce_flag_bytes(self.world))
+        total_floats = (self.flag_off + flag_bytes) // 4
+        self.storage = symm.empty(total_floats, dtype=torch.float32, device=device)
+        self.storage.zero_()                                         # data + flag words (flags must start at zero)
+        torch.cuda.synchronize(device)
+        self.handle = symm.rendezvous(self.storage, self.group)      # exchanges the handles, maps the peers
+        dist.barrier(self.group)                                     # every rank's flags are zero before any kernel runs
+        off = int(getattr(self.handle, 'offset', 0) or 0)
+        self.peer_ptrs = [int(p) + off for p in self.handle.buffer_ptrs]
+        if self.peer_ptrs[self.rank] != self.storage.data_ptr():
+            raise RuntimeError('symmetric memory: local mapping %#x != tensor %#x' % (self.peer_ptrs[self.rank],
+                                                                                      self.storage.data_ptr()))
+        mc = int(getattr(self.handle, 'multicast_ptr', 0) or 0)
+        self.mc_ptr = (mc + off) if mc else 0
+        self._peer_arr = (C.c_void_p * self.world)(*self.peer_ptrs)
+        self.flat = self.storage[:self.numel]
+        self.views, o = [], 0
+        for s, n in zip(shapes, sizes):
+            self.views.append(self.flat[o:o + n].view(*s))
+            o += n
+
+    @staticmethod
+    def available() -> bool:
+        """True when the process group is NCCL on CUDA with more than one rank and symmetric memory can be used."""
+        try:
+            if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() < 2:
+                return False
+            if dist.get_backend() != 'nccl' or not torch.cuda.is_available():
+                return False
+            import torch.distributed._symmetric_memory  # noqa: F401
+            return True
+        except Exception:
+            return False
+
+    @property
+    def transport(self) -> str:
+        return 'nvls-multimem' if (self.mc_ptr and not os.environ.get('BAGS_AR_NO_MULTIMEM')) else 'peer-ldst'
+
+    def allreduce_(self, stream: Optional[int] = None) -> None:
+        """In place, on the current stream (or the given cudaStream_t): every rank ends with the mean (or sum)."""
+        from . import _native
+        if stream is None:
+            stream = torch.cuda.current_stream(self.storage.device).cuda_stream
+        scale = (1.0 / self.world) if self.mean else 1.0
+        rc = _native.lib().bags_grad_allreduce(self._peer_arr, self.mc_ptr or None, self.flag_off, self.count,
+                                               self.rank, self.world, scale, self.max_blocks, stream)
+        _native.check(rc, 'bags_grad_allreduce')
+
+
+def make_grad_bucket(shapes: List[Tuple[int, ...]], device, prefer_peer: bool = True):
+    """(bucket_or_None, flat, views, allreduce_fn): the peer-memory bucket when it can be set up, else a plain bucket
+    exchanged with NCCL (same results; the reference's path)."""
+    if prefer_peer and PeerGradBucket.available() and os.environ.get('BAGS_ALLREDUCE', 'peer') != 'nccl':
+        try:
+            b = PeerGradBucket(shapes, device)
+            return b, b.flat, b.views, b.allreduce_
+        except Exception as ex:  # symmetric memory not usable on this system
+            import warnings
+            warnings.warn('peer-memory gradient bucket unavailable (%r); using NCCL all-reduce' % (ex,))
+    flat, views = flat_grad_bucket(shapes, device)
+    return None, flat, views, (lambda: allreduce_flat_(flat))

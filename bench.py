@@ -213,6 +213,7 @@ def run_ours(args):
     import torch.distributed as dist
     from balancedgroupsoftmax_b200 import ops
     from balancedgroupsoftmax_b200.api import bags_head_loss
+    from balancedgroupsoftmax_b200.dist import make_grad_bucket
     from balancedgroupsoftmax_b200.tables import synthetic_tables
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -247,9 +248,14 @@ def run_ours(args):
         s['bias'] = torch.zeros(C, device=dev)
         s['labels'] = make_labels(torch, n, NUM_CLASSES, gen).to(dev)
         s['logits'] = torch.empty(n, C, device=dev)
-        s['grad'] = torch.empty(C * K_FEAT + C, device=dev)           # flat fc_cls gradient bucket
-        s['dW'] = s['grad'][:C * K_FEAT].view(C, K_FEAT)
-        s['db'] = s['grad'][C * K_FEAT:]
+        # flat fc_cls gradient bucket; at N > 1 it lives in NVLink peer-mapped memory (one-kernel exchange)
+        if world > 1:
+            s['bucket'], s['grad'], (s['dW'], s['db']), s['exchange'] = make_grad_bucket(
+                [(C, K_FEAT), (C,)], dev, prefer_peer=(args.allreduce == 'peer'))
+        else:
+            s['grad'] = torch.empty(C * K_FEAT + C, device=dev)
+            s['dW'] = s['grad'][:C * K_FEAT].view(C, K_FEAT)
+            s['db'] = s['grad'][C * K_FEAT:]
         s['dX'] = torch.empty(n, K_FEAT, device=dev, dtype=dtype)
         s['wscratch'] = ops.bwd_scratch(s['w'])
         sets.append(s)
@@ -265,12 +271,12 @@ def run_ours(args):
         ops.fused_bwd(dz, s['x'], s['w'], gout, dt, colsum, dW=s['dW'], dX=s['dX'], wscratch=s['wscratch'],
                       db=s['db'])
         if world > 1:
-            dist.all_reduce(s['grad'], op=dist.ReduceOp.AVG)
+            s['exchange']()     # mean over ranks of dW, db (dist_utils.py:9-41)
         last['loss'] = loss
         return loss
 
     # sampler, fused fwd (or GEMM + grouped CE), merged backward (preparation jobs + dW + dX units in one launch)
-    kernels_per_step = 4 if args.unfused else 3
+    kernels_per_step = (4 if args.unfused else 3) + (1 if world > 1 and sets[0].get('bucket') is not None else 0)
 
     stream = torch.cuda.Stream(device=dev)
     use_graph = not args.no_graph
@@ -526,8 +532,10 @@ def run_ours(args):
                 'l2': 'rotating pool of %d buffer sets (%.0f MB > 126 MB L2); no step re-reads cached inputs'
                       % (pool, pool * per_set / 1e6),
                 'launch': 'cuda-graph replay' if graph is not None else 'eager',
-                'collective': ('nccl all_reduce(avg) of %d fp32 fc_cls grads per step' % (C * K_FEAT + C))
-                if world > 1 else 'none',
+                'collective': 'none' if world == 1 else (
+                    ('bags_grad_allreduce (%s over NVLink peer memory, one kernel) of %d fp32 fc_cls grads per step'
+                     % (sets[0]['bucket'].transport, C * K_FEAT + C)) if sets[0].get('bucket') is not None else
+                    ('nccl all_reduce(avg) of %d fp32 fc_cls grads per step' % (C * K_FEAT + C))),
             },
             'clocks': clk,
             'e2e': e2e,
@@ -561,6 +569,8 @@ def main():
     ap.add_argument('--rois', type=int, default=N_ROIS)
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--allreduce', default=os.environ.get('BAGS_ALLREDUCE', 'peer'), choices=['peer', 'nccl'],
+                    help='N > 1: gradient exchange by the peer-memory kernel (default) or NCCL')
     ap.add_argument('--unfused', action='store_true', help='GEMM -> fp32 logits -> grouped CE instead of the fused kernel')
     ap.add_argument('--profile', action='store_true', help='timed loop only (for ncu): skip e2e / cpu / per-kernel legs')
     args = ap.parse_args()

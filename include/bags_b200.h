@@ -22,6 +22,8 @@
  *     triggered at mmdet/core/utils/dist_utils.py:53
  *   GSBBoxHeadWith0._merge_score                          bags_merge_scores
  *     gs_bbox_head_with0.py:239-273
+ *   allreduce_grads / _allreduce_coalesced                bags_grad_allreduce
+ *     mmdet/core/utils/dist_utils.py:9-41
  *
  * The reference's own native plugins export pybind11 `forward`/`backward`
  * functions over at::Tensor (e.g. mmdet/ops/sigmoid_focal_loss/src/
@@ -134,6 +136,23 @@ int bags_bwd(const void* dz, long long ldd, const void* x, long long ldx, const 
 int bags_merge_scores(const float* logits, long long ldz, const int32_t* slices_host,
                       const int32_t* cls2col, int N, int C, int G, int classes, float* scores,
                       long long lds, void* stream);
+
+/* Data-parallel exchange of the head's gradient bucket over NVLink peer memory -- replaces the reference's
+ * flatten + dist.all_reduce + div_(world_size) + copy-back (mmdet/core/utils/dist_utils.py:9-41) by ONE kernel:
+ * cross-rank barrier, two-shot all-reduce (rank r reduces slice r and broadcasts it), cross-rank barrier.
+ *   peer_bufs_host : HOST array [world] of this process's device mappings of every rank's bucket (symmetric /
+ *                    peer-mapped memory, same layout on every rank; entry `rank` is the local bucket)
+ *   mc_buf         : multicast (NVLS) mapping of the same bucket, or NULL -> plain peer loads / stores
+ *   count          : fp32 elements at the start of the bucket to reduce in place (multiple of 4)
+ *   flag_off_bytes : offset, inside the same allocation, of bags_grad_allreduce_flag_bytes(world) bytes of flag
+ *                    words that the caller zeroes ONCE (before the first exchange, on every rank); every call
+ *                    leaves them zero
+ *   scale          : applied to the sum (1/world = the reference's mean)
+ * Every rank must issue the call with the same (count, world, max_blocks).  Stream-ordered after the local
+ * gradients' producer; all waits are bounded (a missing rank traps instead of hanging the device). */
+size_t bags_grad_allreduce_flag_bytes(int world);
+int bags_grad_allreduce(void* const* peer_bufs_host, void* mc_buf, long long flag_off_bytes, long long count,
+                        int rank, int world, float scale, int max_blocks, void* stream);
 
 /* dst[rows, cols] (bf16, leading dim ldd) = bf16(src[rows, cols] fp32, leading dim lds); cols % 4 == 0 */
 int bags_cast_bf16(const float* src, long long lds, void* dst, long long ldd, int rows, int cols,
