@@ -32,6 +32,7 @@ SIGNATURES = {
     'bags_workspace_bytes': (_sz, []),
     'bags_linear_fwd': (_i, [_vp, _ll, _vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _vp]),
     'bags_sample_others': (_i, [_vp, _vp, _i, _i, _i, C.c_double, C.c_uint64, _vp, _vp, _vp]),
+    'bags_sample_others_step': (_i, [_vp, _vp, _i, _i, _i, C.c_double, C.c_uint64, _vp, _vp, _vp, _vp]),
     'bags_mask_avg': (_i, [_vp, _i, _i, _vp, _vp]),
     'bags_group_ce': (_i, [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _ll, _i, _vp,
                            _vp, _sz, _vp]),

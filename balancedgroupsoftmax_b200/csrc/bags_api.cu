@@ -314,19 +314,26 @@ extern "C" int bags_linear_fwd(const void* x, long long ldx, const void* w, long
                    : launch_gemm<256, false, false, EPI_STORE_F32, true, 4>(ga, di, stream);
 }
 
-extern "C" int bags_sample_others(const int64_t* labels, const int32_t* label2bin, int N, int G,
-                                  int classes, double ratio, uint64_t seed, uint8_t* wmask,
-                                  float* avg, void* stream_) {
+extern "C" int bags_sample_others_step(const int64_t* labels, const int32_t* label2bin, int N, int G,
+                                       int classes, double ratio, uint64_t seed, const uint64_t* seed_step,
+                                       uint8_t* wmask, float* avg, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BAGS_REQUIRE(labels && label2bin && wmask && avg, "bags_sample_others: NULL argument");
   BAGS_REQUIRE(G >= 1 && G <= kMaxG && classes >= 1 && N >= 0, "bags_sample_others: bad shape");
   BAGS_REQUIRE(ratio >= 0.0, "bags_sample_others: negative ratio");
   const long long* lab = reinterpret_cast<const long long*>(labels);
   const unsigned long long sd = static_cast<unsigned long long>(seed);
-  if (N <= 4096)       BAGS_CUDA(launch_pdl(sample_others_kernel<4>, dim3(G), dim3(1024), 0, stream, lab, label2bin, classes, G, N, ratio, sd, wmask, avg));
-  else if (N <= 16384) BAGS_CUDA(launch_pdl(sample_others_kernel<16>, dim3(G), dim3(1024), 0, stream, lab, label2bin, classes, G, N, ratio, sd, wmask, avg));
-  else                 BAGS_CUDA(launch_pdl(sample_others_kernel<0>, dim3(G), dim3(1024), 0, stream, lab, label2bin, classes, G, N, ratio, sd, wmask, avg));
+  const unsigned long long* st = reinterpret_cast<const unsigned long long*>(seed_step);
+  if (N <= 4096)       BAGS_CUDA(launch_pdl(sample_others_kernel<4>, dim3(G), dim3(1024), 0, stream, lab, label2bin, classes, G, N, ratio, sd, wmask, avg, st));
+  else if (N <= 16384) BAGS_CUDA(launch_pdl(sample_others_kernel<16>, dim3(G), dim3(1024), 0, stream, lab, label2bin, classes, G, N, ratio, sd, wmask, avg, st));
+  else                 BAGS_CUDA(launch_pdl(sample_others_kernel<0>, dim3(G), dim3(1024), 0, stream, lab, label2bin, classes, G, N, ratio, sd, wmask, avg, st));
   return BAGS_OK;
+}
+
+extern "C" int bags_sample_others(const int64_t* labels, const int32_t* label2bin, int N, int G,
+                                  int classes, double ratio, uint64_t seed, uint8_t* wmask,
+                                  float* avg, void* stream_) {
+  return bags_sample_others_step(labels, label2bin, N, G, classes, ratio, seed, nullptr, wmask, avg, stream_);
 }
 
 extern "C" int bags_mask_avg(const uint8_t* wmask, int N, int G, float* avg, void* stream_) {

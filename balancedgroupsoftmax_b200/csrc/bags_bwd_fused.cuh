@@ -214,6 +214,16 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
 #pragma unroll
             for (int h = 0; h < MT; ++h) {   // the sub-tiles share the B descriptor
               const uint32_t sah = sa + h * SUB_A_BYTES;
+#ifdef BAGS_X_BWD_KMAJOR   // timing experiment only (wrong results): every operand read as a K-major tile
+              {
+                constexpr uint32_t idesc_kk = make_instr_desc(TF32 ? 2u : 1u, false, false, Cfg::SUB_M, BLOCK_N);
+                const uint64_t ad = make_smem_desc(sah + k * 32, 16, 1024, kSwizzle128B);
+                const uint64_t bd = make_smem_desc(sb + k * 32, 16, 1024, kSwizzle128B);
+                if (TF32) umma_tf32(d_tmem + h * BLOCK_N, ad, bd, idesc_kk, accum);
+                else      umma_bf16(d_tmem + h * BLOCK_N, ad, bd, idesc_kk, accum);
+                continue;
+              }
+#endif
               if (un.is_dw) {
                 const uint64_t adesc = make_smem_desc(sah + k * MN_KSTEP, MN_LBO, MN_SBO, MN_LAYOUT);
                 if (TF32) umma_tf32(d_tmem + h * BLOCK_N, adesc, bdesc, idesc_dw, accum);

@@ -266,8 +266,12 @@ template <int EPT>
 __global__ void __launch_bounds__(1024)
 sample_others_kernel(const long long* __restrict__ labels, const int* __restrict__ l2b, int classes,
                      int G, int N, double ratio, unsigned long long seed,
-                     uint8_t* __restrict__ wmask, float* __restrict__ avg) {
+                     uint8_t* __restrict__ wmask, float* __restrict__ avg,
+                     const unsigned long long* __restrict__ seed_step = nullptr) {
   pdl_trigger();   // the fused forward's GEMM mainloop does not depend on the masks: let it start now
+  // optional device-resident step counter (CUDA-graph replays: the by-value seed is frozen at capture time, the
+  // counter is advanced by the caller between replays, by a kernel that is NOT this kernel's stream predecessor)
+  if (seed_step != nullptr) seed += __ldg(seed_step) * 0x9E3779B97F4A7C15ull;
   const int g = blockIdx.x;
   const int tid = threadIdx.x;
   __shared__ int s_hist[256];

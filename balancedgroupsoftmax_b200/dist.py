@@ -117,17 +117,31 @@ class PeerGradBucket(object):
             self.views.append(self.flat[o:o + n].view(*s))
             o += n
 
+    why_not = ''   # set by available(): the reason the peer path cannot be used
+
     @staticmethod
     def available() -> bool:
-        """True when the process group is NCCL on CUDA with more than one rank and symmetric memory can be used."""
+        """True when the process group runs NCCL on CUDA with more than one rank and symmetric memory is importable."""
+        cls = PeerGradBucket
         try:
-            if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() < 2:
+            if not (dist.is_available() and dist.is_initialized()):
+                cls.why_not = 'torch.distributed is not initialised'
                 return False
-            if dist.get_backend() != 'nccl' or not torch.cuda.is_available():
+            if dist.get_world_size() < 2:
+                cls.why_not = 'world size 1'
                 return False
-            import torch.distributed._symmetric_memory  # noqa: F401
+            if not torch.cuda.is_available():
+                cls.why_not = 'no CUDA device'
+                return False
+            backend = str(dist.get_backend()).lower()
+            if 'nccl' not in backend:
+                cls.why_not = 'backend %r is not NCCL' % backend
+                return False
+            import torch.distributed._symmetric_memory as _symm  # noqa: F401
+            cls.why_not = ''
             return True
-        except Exception:
+        except Exception as ex:
+            cls.why_not = repr(ex)
             return False
 
     @property
@@ -155,5 +169,8 @@ def make_grad_bucket(shapes: List[Tuple[int, ...]], device, prefer_peer: bool = 
         except Exception as ex:  # symmetric memory not usable on this system
             import warnings
             warnings.warn('peer-memory gradient bucket unavailable (%r); using NCCL all-reduce' % (ex,))
+    elif prefer_peer and dist.is_initialized() and dist.get_rank() == 0 and PeerGradBucket.why_not:
+        import warnings
+        warnings.warn('peer-memory gradient bucket not used: %s' % PeerGradBucket.why_not)
     flat, views = flat_grad_bucket(shapes, device)
     return None, flat, views, (lambda: allreduce_flat_(flat))

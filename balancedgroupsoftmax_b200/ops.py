@@ -123,18 +123,23 @@ def linear_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor],
     return out
 
 
-def sample_others(labels: torch.Tensor, dt: DeviceTables, ratio: float, seed: int
-                  ) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Device sampler: (wmask [G,N] uint8, avg [G] fp32)   (a3/a4)."""
-    _require_cuda(labels)
+def sample_others(labels: torch.Tensor, dt: DeviceTables, ratio: float, seed: int,
+                  seed_step: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Device sampler: (wmask [G,N] uint8, avg [G] fp32)   (a3/a4).
+    ``seed_step``: optional int64 device scalar added (times a odd constant) to the seed on the device, so that
+    replays of a captured CUDA graph draw different subsets (advance it between replays)."""
+    _require_cuda(labels, seed_step)
     labels = labels.contiguous()
     assert labels.dtype == torch.int64
     N = labels.numel()
     wmask = torch.empty((dt.G, N), dtype=torch.uint8, device=labels.device)
     avg = torch.empty((dt.G,), dtype=torch.float32, device=labels.device)
-    nat.check(nat.lib().bags_sample_others(labels.data_ptr(), dt.label2bin.data_ptr(), N, dt.G, dt.num_classes,
-                                           float(ratio), int(seed) & 0xFFFFFFFFFFFFFFFF, wmask.data_ptr(),
-                                           avg.data_ptr(), _stream_ptr(labels.device)), 'bags_sample_others')
+    if seed_step is not None:
+        assert seed_step.dtype == torch.int64 and seed_step.numel() == 1
+    nat.check(nat.lib().bags_sample_others_step(labels.data_ptr(), dt.label2bin.data_ptr(), N, dt.G, dt.num_classes,
+                                                float(ratio), int(seed) & 0xFFFFFFFFFFFFFFFF, nat.ptr(seed_step),
+                                                wmask.data_ptr(), avg.data_ptr(), _stream_ptr(labels.device)),
+              'bags_sample_others')
     return wmask, avg
 
 

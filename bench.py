@@ -352,34 +352,59 @@ def run_ours(args):
         e2e_steps = max(10, min(args.steps, 200))
 
         # double-buffered pipeline: the H2D copy of step i+1 (copy stream) overlaps the compute of step i; every
-        # step still pays its own H2D of features+labels and its own D2H read of the five losses
+        # step still pays its own H2D of features+labels and its own D2H read of the five losses.
+        # Compute = the public API: GraphedHeadStep (CUDA-graph replay of bags_head_loss + backward, one instance per
+        # input buffer); the eager autograd calls of the same API are timed as well (`eager_ms_per_step`).
         copy_stream = torch.cuda.Stream(device=dev)
         comp_stream = torch.cuda.current_stream(dev)
-        xd = [torch.empty(n, K_FEAT, device=dev, dtype=dtype) for _ in range(2)]
-        ld = [torch.empty(n, device=dev, dtype=torch.int64) for _ in range(2)]
         loss_hosts = [torch.empty(dt.G, dtype=torch.float32).pin_memory() for _ in range(2)]
         ev_copied = [torch.cuda.Event() for _ in range(2)]
         ev_free = [torch.cuda.Event() for _ in range(2)]
         ev_loss = [torch.cuda.Event() for _ in range(2)]
+        if world > 1:
+            _, e2e_flat, (e2e_dW, e2e_db), e2e_exchange = make_grad_bucket([(C, K_FEAT), (C,)], dev,
+                                                                           prefer_peer=(args.allreduce == 'peer'))
+
+            def exchange():
+                e2e_dW.copy_(w_param.grad)
+                e2e_db.copy_(b_param.grad)
+                e2e_exchange()
+        else:
+            exchange = None
+        graphed = []
+        if not args.e2e_eager_only:
+            from balancedgroupsoftmax_b200.api import GraphedHeadStep
+            graphed = [GraphedHeadStep(w_param, b_param, dt, n, RATIO, compute_dtype=dtype, x_dtype=dtype,
+                                       exchange=exchange) for _ in range(2)]
+            if world > 1:
+                dist.barrier()
+        xd_eager = [torch.empty(n, K_FEAT, device=dev, dtype=dtype) for _ in range(2)]
+        ld_eager = [torch.empty(n, device=dev, dtype=torch.int64) for _ in range(2)]
+        mode = {'graphed': bool(graphed)}
 
         def stage(i):
             b_ = i & 1
-            with torch.cuda.stream(copy_stream):
+            xdst = graphed[b_].x if mode['graphed'] else xd_eager[b_]
+            ldst = graphed[b_].labels if mode['graphed'] else ld_eager[b_]
+            with torch.cuda.stream(copy_stream), torch.no_grad():
                 copy_stream.wait_event(ev_free[b_])
-                xd[b_].copy_(x_host, non_blocking=True)
-                ld[b_].copy_(lab_host, non_blocking=True)
+                xdst.copy_(x_host, non_blocking=True)
+                ldst.copy_(lab_host, non_blocking=True)
                 ev_copied[b_].record(copy_stream)
 
         def compute(i):
             b_ = i & 1
             comp_stream.wait_event(ev_copied[b_])
-            xin = xd[b_].detach().requires_grad_(True)
-            w_param.grad = None
-            b_param.grad = None
-            losses = bags_head_loss(xin, w_param, b_param, ld[b_], dt, RATIO, compute_dtype=dtype)
-            losses.sum().backward()
-            if world > 1:
-                dist.all_reduce(w_param.grad, op=dist.ReduceOp.AVG)
+            if mode['graphed']:
+                losses = graphed[b_].replay()
+            else:
+                xin = xd_eager[b_].detach().requires_grad_(True)
+                w_param.grad = None
+                b_param.grad = None
+                losses = bags_head_loss(xin, w_param, b_param, ld_eager[b_], dt, RATIO, compute_dtype=dtype)
+                losses.sum().backward()
+                if exchange is not None:
+                    exchange()
             ev_free[b_].record(comp_stream)
             loss_hosts[b_].copy_(losses.detach(), non_blocking=True)
             ev_loss[b_].record(comp_stream)
@@ -396,18 +421,29 @@ def run_ours(args):
                     ev_loss[(i - 1) & 1].synchronize()   # the previous step's losses are on the host
             ev_loss[(k - 1) & 1].synchronize()
 
-        run_e2e(6)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        run_e2e(e2e_steps)
-        torch.cuda.synchronize()
-        e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
-        if world > 1:
-            t = torch.tensor([e2e_ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_ms = float(t.item())
+        def time_e2e(k):
+            run_e2e(6)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            run_e2e(k)
+            torch.cuda.synchronize()
+            ms = (time.perf_counter() - t0) / k * 1e3
+            if world > 1:
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms
+
+        eager_ms = None
+        if graphed:
+            mode['graphed'] = False
+            eager_ms = time_e2e(max(10, min(e2e_steps, 100)))
+            mode['graphed'] = True
+        e2e_ms = time_e2e(e2e_steps)
+        xd = xd_eager
+        ld = ld_eager
         # what the copies alone cost (same pinned buffers, no compute): shows how much of the e2e step is PCIe
         ca, cb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(copy_stream):
@@ -421,6 +457,9 @@ def run_ours(args):
         e2e = {'value': world * n / (e2e_ms * 1e-3), 'unit': 'RoIs/s', 'h2d_only_ms_per_step': h2d_ms,
                'h2d_bytes_per_step': int(x_host.numel() * x_host.element_size() + lab_host.numel() * 8),
                'd2h_bytes_per_step': int(loss_host.numel() * 4), 'ms_per_step': e2e_ms, 'steps': e2e_steps,
+               'api': ('balancedgroupsoftmax_b200.api.GraphedHeadStep (CUDA-graph replay of bags_head_loss + backward)'
+                       if graphed else 'balancedgroupsoftmax_b200.api.bags_head_loss + autograd backward (eager)'),
+               'eager_ms_per_step': eager_ms,
                'pipeline': 'H2D of step i+1 overlaps compute of step i (2 buffers); losses read back every step'}
     except Exception as ex:  # pragma: no cover
         log('e2e arm failed: %r' % (ex,))
@@ -571,6 +610,7 @@ def main():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--allreduce', default=os.environ.get('BAGS_ALLREDUCE', 'peer'), choices=['peer', 'nccl'],
                     help='N > 1: gradient exchange by the peer-memory kernel (default) or NCCL')
+    ap.add_argument('--e2e-eager-only', action='store_true', help='e2e leg: eager autograd calls only (no CUDA-graph step)')
     ap.add_argument('--unfused', action='store_true', help='GEMM -> fp32 logits -> grouped CE instead of the fused kernel')
     ap.add_argument('--profile', action='store_true', help='timed loop only (for ncu): skip e2e / cpu / per-kernel legs')
     args = ap.parse_args()

@@ -80,6 +80,12 @@ int bags_linear_fwd(const void* x, long long ldx, const void* w, long long ldw, 
  * _sample_others does, but on the device with a counter-based RNG keyed by `seed`. */
 int bags_sample_others(const int64_t* labels, const int32_t* label2bin, int N, int G, int classes,
                        double ratio, uint64_t seed, uint8_t* wmask, float* avg, void* stream);
+/* Same, with the effective seed = seed + (*seed_step) * 0x9E3779B97F4A7C15 read on the DEVICE (seed_step may be
+ * NULL).  For CUDA-graph replays, where by-value arguments are frozen at capture time: the caller advances the
+ * counter between replays (not with the kernel that immediately precedes this one in the stream). */
+int bags_sample_others_step(const int64_t* labels, const int32_t* label2bin, int N, int G, int classes,
+                            double ratio, uint64_t seed, const uint64_t* seed_step, uint8_t* wmask,
+                            float* avg, void* stream);
 
 /* avg[g] = max(sum_n wmask[g,n], 1) for caller-provided masks */
 int bags_mask_avg(const uint8_t* wmask, int N, int G, float* avg, void* stream);

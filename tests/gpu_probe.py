@@ -275,6 +275,19 @@ def case_timeline(name):
                                       round(float(((tb[:, 6] - tb[:, 0]) / 1e3).max()), 2)]
         d['distinct_sms'] = int(tb[:, 7].unique().numel())
         d['ctas'] = int(tb.shape[0])
+        if 'bwd_merged' in label and tb.shape[0] > 64 and os.environ.get('BAGS_BWD_PAIR') != '1':
+            # 256 x 256 units, one per CTA: the last 64 CTAs run dX units (20 k-blocks), the others dW units
+            ndw = tb.shape[0] - 64
+            for kind, sub in (('dW', tb[:ndw]), ('dX', tb[ndw:])):
+                d['%s_units' % kind] = {
+                    'ctas': int(sub.shape[0]),
+                    'start->first_data': round(float(((sub[:, 2] - sub[:, 0]) / 1e3).mean()), 2),
+                    'mainloop(first_data->acc_done)': [round(float(((sub[:, 4] - sub[:, 2]) / 1e3).mean()), 2),
+                                                       round(float(((sub[:, 4] - sub[:, 2]) / 1e3).max()), 2)],
+                    'epilogue(acc_done->epi_done)': [round(float(((sub[:, 5] - sub[:, 4]) / 1e3).mean()), 2),
+                                                     round(float(((sub[:, 5] - sub[:, 4]) / 1e3).max()), 2)],
+                    'end_after_kernel_start': [round(float(((sub[:, 6] - t0) / 1e3).mean()), 2),
+                                               round(float(((sub[:, 6] - t0) / 1e3).max()), 2)]}
         if 'fused' in label:   # second stamp bank: finer epilogue phases (us after 'acc done')
             t2 = tbuf[nctas:2 * nctas].cpu().double()
             base = tb[:, 3]

@@ -73,6 +73,14 @@ def main():
     except Exception as e:
         out['numa_err'] = repr(e)
     out['gbs_64MB_default'] = rate(64 << 20, dev, reps=10)
+    out['gbs_default_again'] = rate(nbytes + 4096 * 9, dev)
+    # does the number of host threads that first-touch / fill the pinned buffer matter?
+    nt = torch.get_num_threads()
+    out['threads_default'] = nt
+    torch.set_num_threads(1)
+    out['gbs_32MB_1thread_fill'] = rate(32 << 20, dev, reps=10)
+    torch.set_num_threads(nt)
+    out['gbs_48MB_allthreads_fill'] = rate(48 << 20, dev, reps=10)
     print(json.dumps(out))
 
 

@@ -29,7 +29,7 @@ def main():
     from balancedgroupsoftmax_b200.dist import PeerGradBucket
     out = {'world': world, 'checks': [], 'ok': True}
     shapes = [(1236, 1024), (1236,)]
-    assert PeerGradBucket.available(), 'symmetric memory / NCCL not available'
+    assert PeerGradBucket.available(), 'peer path unavailable: ' + PeerGradBucket.why_not
 
     def check(name, cond, detail=''):
         t = torch.tensor([1 if cond else 0], device=dev)

@@ -1,0 +1,59 @@
+"""GPU: the CUDA-graph step of the public API (GraphedHeadStep) reproduces the eager autograd API call for call,
+including the device-side seed counter of the sampler."""
+import pytest
+import torch
+
+from balancedgroupsoftmax_b200.tables import synthetic_tables
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize('n', [300, 1024])
+def test_graphed_step_matches_eager(n):
+    from balancedgroupsoftmax_b200 import ops
+    from balancedgroupsoftmax_b200.api import GraphedHeadStep, bags_head_loss
+    dev = torch.device('cuda', 0)
+    t = synthetic_tables(1231, seed=0)
+    dt = ops.DeviceTables.from_tables(t, dev)
+    g = torch.Generator().manual_seed(7)
+    W = torch.nn.Parameter((torch.randn(t.num_logits, 1024, generator=g) * 0.05).to(dev).bfloat16())
+    b = torch.nn.Parameter((torch.randn(t.num_logits, generator=g) * 0.1).to(dev))
+    lw = torch.tensor([1.0, 0.5, 0.5, 0.25, 2.0])
+    step = GraphedHeadStep(W, b, dt, n, others_sample_ratio=8.0, loss_weights=lw, seed=1234)
+    for it in range(3):
+        x = torch.relu(torch.randn(n, 1024, generator=g)).to(dev).bfloat16()
+        labels = torch.zeros(n, dtype=torch.int64)
+        labels[: n // 4] = torch.randint(1, t.num_classes, (n // 4,), generator=g)
+        labels = labels.to(dev)
+        losses = step(x, labels).clone()
+        gW, gb, gx = step.grad_weight.clone(), step.grad_bias.clone(), step.grad_x.clone()
+        torch.cuda.synchronize()
+        # eager call with the masks the graph's sampler drew at this replay (seed counter = it)
+        cnt = torch.tensor([it], dtype=torch.int64, device=dev)
+        wmask, avg = ops.sample_others(labels, dt, 8.0, 1234, seed_step=cnt)
+        xe = x.clone().requires_grad_(True)
+        W.grad = None
+        b.grad = None
+        le = bags_head_loss(xe, W, b, labels, dt, 8.0, wmask=wmask, avg=avg)
+        (le * lw.to(dev)).sum().backward()
+        torch.cuda.synchronize()
+        assert torch.allclose(losses, le.detach(), rtol=1e-6, atol=1e-7), (it, losses, le)
+        assert rel(gW.float(), W.grad.float()) < 1e-5          # split-K red.add order only
+        assert rel(gb, b.grad) < 1e-5
+        assert rel(gx.float(), xe.grad.float()) < 1e-5
+        # restore the graph's static grads as the parameters' grads (the eager call replaced them)
+        W.grad, b.grad = step.grad_weight, step.grad_bias
+    # the sampler really draws a different subset per replay
+    labels = torch.zeros(n, dtype=torch.int64, device=dev)
+    labels[: n // 8] = 5
+    m0, _ = ops.sample_others(labels, dt, 2.0, 1234, seed_step=torch.tensor([0], device=dev))
+    m1, _ = ops.sample_others(labels, dt, 2.0, 1234, seed_step=torch.tensor([1], device=dev))
+    mp, _ = ops.sample_others(labels, dt, 2.0, 1234)
+    assert torch.equal(m0, mp)                  # counter 0 == the plain seed
+    assert not torch.equal(m0, m1)
+    assert torch.equal(m0.sum(1), m1.sum(1))    # same subset sizes (exact-k sampling)
