@@ -17,7 +17,8 @@
 // trips; NCCL's ring/tree launch measured ~53 us per step for the same bucket (profiles/r01_bench_2gpu_v5.json).
 //
 // Flags: uint32 [blocks][world] inside every rank's buffer, zero between launches (put = CAS 0->1 on the target,
-// wait = CAS 1->0 on the own copy), so graph replays need no reset.  All spins are bounded (trap).
+// wait = CAS 1->0 on the own copy), so graph replays need no reset.  All spins are bounded; a timeout sets the
+// status word after the flags ([kArMaxBlocks*world]) instead of trapping, so a broken peer cannot kill the context.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -72,7 +73,9 @@ __device__ __forceinline__ void multimem_st_f4(float* mc, const float4 v) {
 // Block-level barrier across ranks: block b of every rank meets block b of every other rank.
 // Thread t < world signals rank t and waits for rank t's signal.  Preceded / followed by __syncthreads() so the
 // release / acquire of the signalling threads order the whole block's accesses (PTX memory model: cumulativity).
-__device__ __forceinline__ void rank_barrier(const AllReduceParams& p) {
+// A rank that never shows up does not hang the device: after ~2^22 probes the block records the failure in the
+// status word behind the flags (checked by the host-side self test) and the kernel returns without exchanging.
+__device__ __forceinline__ bool rank_barrier(const AllReduceParams& p, int* s_fail) {
   __syncthreads();
   if (threadIdx.x < static_cast<unsigned>(p.world)) {
     const int t = static_cast<int>(threadIdx.x);
@@ -81,16 +84,24 @@ __device__ __forceinline__ void rank_barrier(const AllReduceParams& p) {
     uint32_t* mine = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(p.peer[p.rank]) + p.flag_off) +
                      blockIdx.x * p.world + t;
     uint32_t spins = 0;
+    bool ok = true;
     while (cas_release_sys(theirs, 0u, 1u) != 0u) {
-      if (++spins > (1u << 24)) { printf("bags: all-reduce put timed out (rank %d -> %d, block %d)\n", p.rank, t, (int)blockIdx.x); __trap(); }
+      if (++spins > (1u << 22)) { ok = false; break; }
     }
     spins = 0;
-    while (cas_acquire_sys(mine, 1u, 0u) != 1u) {
+    while (ok && cas_acquire_sys(mine, 1u, 0u) != 1u) {
       __nanosleep(32);
-      if (++spins > (1u << 24)) { printf("bags: all-reduce wait timed out (rank %d <- %d, block %d)\n", p.rank, t, (int)blockIdx.x); __trap(); }
+      if (++spins > (1u << 22)) { ok = false; break; }
+    }
+    if (!ok) {
+      *s_fail = 1;
+      uint32_t* status = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(p.peer[p.rank]) + p.flag_off) +
+                         kArMaxBlocks * p.world;
+      atomicExch(status, 1u);
     }
   }
   __syncthreads();
+  return *s_fail == 0;
 }
 
 template <bool MULTIMEM>
@@ -98,7 +109,9 @@ __global__ void __launch_bounds__(kArThreads)
 bags_grad_allreduce_kernel(const AllReduceParams p) {
   pdl_trigger();   // the next kernel of the stream (next step's sampler / forward mainloop) may start launching
   pdl_wait();      // the local gradients come from the preceding backward kernel
-  rank_barrier(p);
+  __shared__ int s_fail;
+  if (threadIdx.x == 0) s_fail = 0;
+  if (!rank_barrier(p, &s_fail)) return;
 
   const long long vecs = p.count >> 2;
   const long long chunk = (vecs + p.world - 1) / p.world;
@@ -136,7 +149,7 @@ bags_grad_allreduce_kernel(const AllReduceParams p) {
       }
     }
   }
-  rank_barrier(p);
+  rank_barrier(p, &s_fail);
 }
 
 }  // namespace bags

@@ -144,6 +144,25 @@ class PeerGradBucket(object):
             cls.why_not = repr(ex)
             return False
 
+    def status(self) -> int:
+        """0, or 1 after an exchange in which some rank never arrived (the kernel gave up; the bucket is unusable)."""
+        word = self.flag_off // 4 + 64 * self.world
+        return int(self.storage[word:word + 1].view(torch.int32).item())
+
+    def self_test(self) -> bool:
+        """One exchange of a known pattern, verified on every rank (collective: all ranks must call it)."""
+        dev = self.storage.device
+        self.flat.fill_(float(self.rank + 1))
+        self.allreduce_()
+        torch.cuda.synchronize(dev)
+        expect = (self.world + 1) / 2.0 if self.mean else self.world * (self.world + 1) / 2.0
+        ok = self.status() == 0 and bool(((self.flat - expect).abs() <= 1e-6 * expect).all().item())
+        verdict = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(verdict, op=dist.ReduceOp.MIN, group=self.group)
+        self.flat.zero_()
+        torch.cuda.synchronize(dev)
+        return bool(verdict.item())
+
     @property
     def transport(self) -> str:
         return 'nvls-multimem' if (self.mc_ptr and not os.environ.get('BAGS_AR_NO_MULTIMEM')) else 'peer-ldst'
@@ -165,7 +184,10 @@ def make_grad_bucket(shapes: List[Tuple[int, ...]], device, prefer_peer: bool = 
     if prefer_peer and PeerGradBucket.available() and os.environ.get('BAGS_ALLREDUCE', 'peer') != 'nccl':
         try:
             b = PeerGradBucket(shapes, device)
-            return b, b.flat, b.views, b.allreduce_
+            if b.self_test():
+                return b, b.flat, b.views, b.allreduce_
+            import warnings
+            warnings.warn('peer-memory gradient exchange failed its self test; using NCCL all-reduce')
         except Exception as ex:  # symmetric memory not usable on this system
             import warnings
             warnings.warn('peer-memory gradient bucket unavailable (%r); using NCCL all-reduce' % (ex,))

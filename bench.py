@@ -344,8 +344,13 @@ def run_ours(args):
     try:
         if args.profile:
             raise RuntimeError('skipped (--profile)')
-        x_host = torch.relu(torch.randn(n, K_FEAT, generator=gen)).to(dtype).pin_memory()
-        lab_host = make_labels(torch, n, NUM_CLASSES, gen).pin_memory()
+        from balancedgroupsoftmax_b200.hostmem import pinned_like
+        if args.numa_pinned:   # staging buffers allocated / first-touched on the GPU's NUMA node (hostmem.py)
+            x_host = pinned_like(torch.relu(torch.randn(n, K_FEAT, generator=gen)).to(dtype), local_rank)
+            lab_host = pinned_like(make_labels(torch, n, NUM_CLASSES, gen), local_rank)
+        else:
+            x_host = torch.relu(torch.randn(n, K_FEAT, generator=gen)).to(dtype).pin_memory()
+            lab_host = make_labels(torch, n, NUM_CLASSES, gen).pin_memory()
         w_param = torch.nn.Parameter(W_master.to(dev).to(dtype))
         b_param = torch.nn.Parameter(torch.zeros(C, device=dev))
         loss_host = torch.empty(dt.G, dtype=torch.float32).pin_memory()
@@ -382,14 +387,23 @@ def run_ours(args):
         ld_eager = [torch.empty(n, device=dev, dtype=torch.int64) for _ in range(2)]
         mode = {'graphed': bool(graphed)}
 
+        ev_h2d0 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev_h2d1 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        h2d_in_pipe = []
+
         def stage(i):
             b_ = i & 1
             xdst = graphed[b_].x if mode['graphed'] else xd_eager[b_]
             ldst = graphed[b_].labels if mode['graphed'] else ld_eager[b_]
             with torch.cuda.stream(copy_stream), torch.no_grad():
                 copy_stream.wait_event(ev_free[b_])
+                if i >= 2 and mode.get('probe'):
+                    ev_h2d1[b_].synchronize()
+                    h2d_in_pipe.append(ev_h2d0[b_].elapsed_time(ev_h2d1[b_]))   # step i-2's copy (long finished)
+                ev_h2d0[b_].record(copy_stream)
                 xdst.copy_(x_host, non_blocking=True)
                 ldst.copy_(lab_host, non_blocking=True)
+                ev_h2d1[b_].record(copy_stream)
                 ev_copied[b_].record(copy_stream)
 
         def compute(i):
@@ -442,6 +456,10 @@ def run_ours(args):
             eager_ms = time_e2e(max(10, min(e2e_steps, 100)))
             mode['graphed'] = True
         e2e_ms = time_e2e(e2e_steps)
+        mode['probe'] = True          # untimed extra pass: how long one step's H2D takes while the pipeline runs
+        run_e2e(40)
+        torch.cuda.synchronize()
+        mode['probe'] = False
         xd = xd_eager
         ld = ld_eager
         # what the copies alone cost (same pinned buffers, no compute): shows how much of the e2e step is PCIe
@@ -460,6 +478,8 @@ def run_ours(args):
                'api': ('balancedgroupsoftmax_b200.api.GraphedHeadStep (CUDA-graph replay of bags_head_loss + backward)'
                        if graphed else 'balancedgroupsoftmax_b200.api.bags_head_loss + autograd backward (eager)'),
                'eager_ms_per_step': eager_ms,
+               'h2d_ms_inside_pipeline': (sorted(h2d_in_pipe)[len(h2d_in_pipe) // 2] if h2d_in_pipe else None),
+               'staging': 'pinned, GPU-local NUMA node' if args.numa_pinned else 'pinned',
                'pipeline': 'H2D of step i+1 overlaps compute of step i (2 buffers); losses read back every step'}
     except Exception as ex:  # pragma: no cover
         log('e2e arm failed: %r' % (ex,))
@@ -610,6 +630,8 @@ def main():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--allreduce', default=os.environ.get('BAGS_ALLREDUCE', 'peer'), choices=['peer', 'nccl'],
                     help='N > 1: gradient exchange by the peer-memory kernel (default) or NCCL')
+    ap.add_argument('--no-numa-pinned', dest='numa_pinned', action='store_false',
+                    help='e2e leg: plain pin_memory() staging buffers instead of GPU-local NUMA placement')
     ap.add_argument('--e2e-eager-only', action='store_true', help='e2e leg: eager autograd calls only (no CUDA-graph step)')
     ap.add_argument('--unfused', action='store_true', help='GEMM -> fp32 logits -> grouped CE instead of the fused kernel')
     ap.add_argument('--profile', action='store_true', help='timed loop only (for ncu): skip e2e / cpu / per-kernel legs')

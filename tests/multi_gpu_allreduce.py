@@ -69,6 +69,7 @@ def main():
             other = mine.clone()
             dist.broadcast(other, src=0)
             check('%s ranks bit-identical' % tag, bool(torch.equal(mine, other)))
+            check('%s status word clean' % tag, bucket.status() == 0)
             # views alias the bucket
             check('%s views alias bucket' % tag, bucket.views[0].data_ptr() == bucket.flat.data_ptr())
             # CUDA graph: fill (rank+1) -> allreduce, 4 times per graph, replay 3 times
