@@ -27,8 +27,10 @@
 namespace bags {
 
 constexpr int kMaxRanks = 16;
-constexpr int kArMaxBlocks = 64;
-constexpr int kArThreads = 512;
+// Small blocks with few registers: an exchange block fits on an SM next to a GEMM CTA of this library (48-55 K
+// registers), so an exchange launched on a side stream really overlaps the next step's kernels.
+constexpr int kArMaxBlocks = 256;
+constexpr int kArThreads = 256;
 
 struct AllReduceParams {
   float* peer[kMaxRanks];   // this process's mapping of every rank's bucket (peer[rank] is the local one)
@@ -105,7 +107,7 @@ __device__ __forceinline__ bool rank_barrier(const AllReduceParams& p, int* s_fa
 }
 
 template <bool MULTIMEM>
-__global__ void __launch_bounds__(kArThreads)
+__global__ void __launch_bounds__(kArThreads, 6)
 bags_grad_allreduce_kernel(const AllReduceParams p) {
   pdl_trigger();   // the next kernel of the stream (next step's sampler / forward mainloop) may start launching
   pdl_wait();      // the local gradients come from the preceding backward kernel

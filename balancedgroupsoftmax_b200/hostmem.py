@@ -29,8 +29,11 @@ def _parse_cpulist(text: str) -> Set[int]:
 
 def gpu_local_cpus(device_index: int = 0) -> Optional[Set[int]]:
     """CPUs of the NUMA node the GPU's PCIe root port hangs off, or None when the topology cannot be read."""
+    bdf = None
     try:
-        bdf = torch.cuda.get_device_properties(device_index).pci_bus_id  # type: ignore[attr-defined]
+        pr = torch.cuda.get_device_properties(device_index)
+        if all(hasattr(pr, a) for a in ('pci_domain_id', 'pci_bus_id', 'pci_device_id')):
+            bdf = '%04x:%02x:%02x.0' % (int(pr.pci_domain_id), int(pr.pci_bus_id), int(pr.pci_device_id))
     except Exception:
         bdf = None
     if not bdf:
@@ -39,6 +42,8 @@ def gpu_local_cpus(device_index: int = 0) -> Optional[Set[int]]:
                                   '--format=csv,noheader'], capture_output=True, text=True, timeout=10).stdout.strip()
         except Exception:
             return None
+    if not bdf:
+        return None
     bdf = bdf.lower()
     if len(bdf.split(':')[0]) == 8:        # nvidia-smi prints an 8-digit PCI domain, sysfs uses 4
         bdf = bdf[4:]

@@ -271,7 +271,17 @@ def run_ours(args):
         ops.fused_bwd(dz, s['x'], s['w'], gout, dt, colsum, dW=s['dW'], dX=s['dX'], wscratch=s['wscratch'],
                       db=s['db'])
         if world > 1:
-            s['exchange']()     # mean over ranks of dW, db (dist_utils.py:9-41)
+            # mean over ranks of dW, db (dist_utils.py:9-41).  'overlap': on a side stream, concurrently with the next
+            # step's kernels (which use another member of the buffer pool); every exchange still completes inside the
+            # timed region (the side stream is joined before the closing event / at the end of the graph)
+            if comm_stream is not None:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
+                comm_stream.wait_event(ev)
+                with torch.cuda.stream(comm_stream):
+                    s['exchange']()
+            else:
+                s['exchange']()
         last['loss'] = loss
         return loss
 
@@ -279,11 +289,14 @@ def run_ours(args):
     kernels_per_step = (4 if args.unfused else 3) + (1 if world > 1 and sets[0].get('bucket') is not None else 0)
 
     stream = torch.cuda.Stream(device=dev)
+    comm_stream = torch.cuda.Stream(device=dev) if (world > 1 and args.exchange == 'overlap') else None
     use_graph = not args.no_graph
     graph = None
     with torch.cuda.stream(stream):
         for s in sets[:2]:
             one_step(s)
+        if comm_stream is not None:
+            stream.wait_stream(comm_stream)
         stream.synchronize()
         if use_graph:
             try:
@@ -291,6 +304,8 @@ def run_ours(args):
                 with torch.cuda.graph(graph, stream=stream):
                     for s in sets:
                         one_step(s)
+                    if comm_stream is not None:
+                        stream.wait_stream(comm_stream)   # join: the graph ends when its last exchange has
             except Exception as e:  # pragma: no cover
                 log('graph capture failed (%s); timing eager launches' % (e,))
                 graph = None
@@ -308,6 +323,8 @@ def run_ours(args):
             else:
                 for i in range(k):
                     one_step(sets[i % pool])
+            if comm_stream is not None:
+                stream.wait_stream(comm_stream)
 
         run_steps(max(args.warmup, 3))
         stream.synchronize()
@@ -594,7 +611,9 @@ def run_ours(args):
                 'collective': 'none' if world == 1 else (
                     ('bags_grad_allreduce (%s over NVLink peer memory, one kernel) of %d fp32 fc_cls grads per step'
                      % (sets[0]['bucket'].transport, C * K_FEAT + C)) if sets[0].get('bucket') is not None else
-                    ('nccl all_reduce(avg) of %d fp32 fc_cls grads per step' % (C * K_FEAT + C))),
+                    ('nccl all_reduce(avg) of %d fp32 fc_cls grads per step' % (C * K_FEAT + C))) + (
+                    '; each exchange runs on a side stream under the next step and completes inside the timed region'
+                    if comm_stream is not None else '; in line after the backward'),
             },
             'clocks': clk,
             'e2e': e2e,
@@ -628,6 +647,8 @@ def main():
     ap.add_argument('--rois', type=int, default=N_ROIS)
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--exchange', default='overlap', choices=['overlap', 'inline'],
+                    help='N > 1: gradient exchange on a side stream under the next step (default) or in line')
     ap.add_argument('--allreduce', default=os.environ.get('BAGS_ALLREDUCE', 'peer'), choices=['peer', 'nccl'],
                     help='N > 1: gradient exchange by the peer-memory kernel (default) or NCCL')
     ap.add_argument('--no-numa-pinned', dest='numa_pinned', action='store_false',

@@ -1,14 +1,25 @@
 #!/bin/bash
-# 2-GPU evidence (run under gpurun --gpus 2): peer-memory exchange vs NCCL, bench at N=2 with both
+# multi-GPU evidence (run under gpurun --gpus N): peer-memory exchange vs NCCL, bench at N with the exchange variants
 tag=${1:-r01_v10}
+N=${2:-2}
 out=gpurun_out
 mkdir -p $out
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
-timeout 240 $TR --master-port 29511 tests/multi_gpu_allreduce.py --json $out/${tag}_allreduce_2gpu.json > $out/${tag}_allreduce_2gpu.log 2>&1; echo "allreduce probe rc=$?"
-grep -v "^\[rank1\]" $out/${tag}_allreduce_2gpu.log | grep -v "^$" | head -60
-timeout 300 $TR --master-port 29512 bench.py --gpus 2 --steps 240 --warmup 12 --allreduce peer > $out/${tag}_bench_2gpu_peer.json 2> $out/${tag}_bench_2gpu_peer.err; echo "bench peer rc=$?"
-cat $out/${tag}_bench_2gpu_peer.json; grep -i "warn\|error\|peer" $out/${tag}_bench_2gpu_peer.err | head
-if [ "$2" = "nccl" ]; then
-timeout 300 $TR --master-port 29513 bench.py --gpus 2 --steps 240 --warmup 12 --allreduce nccl > $out/${tag}_bench_2gpu_nccl.json 2> $out/${tag}_bench_2gpu_nccl.err; echo "bench nccl rc=$?"
-cat $out/${tag}_bench_2gpu_nccl.json
-fi
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+timeout 240 $TR --master-port 29511 tests/multi_gpu_allreduce.py --json $out/${tag}_allreduce_${N}gpu.json > $out/${tag}_allreduce_${N}gpu.log 2>&1; echo "allreduce probe rc=$?"
+grep -E " ok | FAIL|us per|Error|error" $out/${tag}_allreduce_${N}gpu.log | grep -v "^\[rank[1-9]" | head -40
+port=29512
+for variant in "peer overlap" "peer inline" "nccl overlap" "nccl inline"; do
+  set -- $variant
+  port=$((port+1))
+  f=$out/${tag}_bench_${N}gpu_$1_$2
+  timeout 300 $TR --master-port $port bench.py --gpus $N --steps 240 --warmup 12 --allreduce $1 --exchange $2 > $f.json 2> $f.err; echo "bench $1 $2 rc=$?"
+  python - <<PY
+import json
+try:
+    d=json.loads([l for l in open('$f.json') if l.startswith('{')][-1])
+    print('  ms_per_step %.4f  value %.3e  e2e %s  collective: %s' % (d['ms_per_step'], d['value'], (d.get('e2e') or {}).get('value'), d['config']['collective'][:60]))
+except Exception as e:
+    print('  no result', e)
+PY
+  grep -i "warn\|error\|failed" $f.err | grep -v "OMP_NUM\|destroy_process" | head -5
+done
