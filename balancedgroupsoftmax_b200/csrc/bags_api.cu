@@ -880,6 +880,19 @@ extern "C" int bags_grad_allreduce(void* const* peer_bufs_host, void* mc_buf, lo
   return BAGS_OK;
 }
 
+// test hook: a kernel of `blocks` x `threads` that only waits `micros` microseconds (stands in for a latency-bound
+// collective when probing how side-stream work co-schedules with the GEMM kernels)
+__global__ void bags_debug_spin_kernel(long long ns) {
+  const long long t0 = global_timer_ns();
+  while (global_timer_ns() - t0 < ns) __nanosleep(200);
+}
+extern "C" int bags_debug_spin(int blocks, int threads, int micros, void* stream_) {
+  BAGS_REQUIRE(blocks >= 1 && threads >= 32 && threads <= 1024 && micros >= 0, "bags_debug_spin: bad arguments");
+  bags_debug_spin_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream_)>>>(1000LL * micros);
+  BAGS_CUDA(cudaGetLastError());
+  return BAGS_OK;
+}
+
 extern "C" int bags_merge_scores(const float* logits, long long ldz, const int32_t* slices_host,
                                  const int32_t* cls2col, int N, int C, int G, int classes,
                                  float* scores, long long lds, void* stream_) {

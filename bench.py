@@ -282,6 +282,11 @@ def run_ours(args):
                     s['exchange']()
             else:
                 s['exchange']()
+        elif fake is not None:   # scheduling probe (N = 1): a side-stream kernel that only waits
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            comm_stream.wait_event(ev)
+            nat.check(nat.lib().bags_debug_spin(fake[0], fake[1], fake[2], comm_stream.cuda_stream), 'bags_debug_spin')
         last['loss'] = loss
         return loss
 
@@ -290,6 +295,11 @@ def run_ours(args):
 
     stream = torch.cuda.Stream(device=dev)
     comm_stream = torch.cuda.Stream(device=dev) if (world > 1 and args.exchange == 'overlap') else None
+    fake = None
+    if world == 1 and args.fake_exchange:
+        from balancedgroupsoftmax_b200 import _native as nat
+        fake = [int(v) for v in args.fake_exchange.split(',')]    # blocks,threads,microseconds
+        comm_stream = torch.cuda.Stream(device=dev)
     use_graph = not args.no_graph
     graph = None
     with torch.cuda.stream(stream):
@@ -647,6 +657,7 @@ def main():
     ap.add_argument('--rois', type=int, default=N_ROIS)
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--fake-exchange', default='', help='probe (N = 1): blocks,threads,microseconds of a side-stream wait kernel per step')
     ap.add_argument('--exchange', default='overlap', choices=['overlap', 'inline'],
                     help='N > 1: gradient exchange on a side stream under the next step (default) or in line')
     ap.add_argument('--allreduce', default=os.environ.get('BAGS_ALLREDUCE', 'peer'), choices=['peer', 'nccl'],

@@ -161,6 +161,9 @@ size_t bags_grad_allreduce_flag_bytes(int world);
 int bags_grad_allreduce(void* const* peer_bufs_host, void* mc_buf, long long flag_off_bytes, long long count,
                         int rank, int world, float scale, int max_blocks, void* stream);
 
+/* test hook: launch `blocks` x `threads` threads that wait `micros` microseconds and exit */
+int bags_debug_spin(int blocks, int threads, int micros, void* stream);
+
 /* dst[rows, cols] (bf16, leading dim ldd) = bf16(src[rows, cols] fp32, leading dim lds); cols % 4 == 0 */
 int bags_cast_bf16(const float* src, long long lds, void* dst, long long ldd, int rows, int cols,
                    void* stream);
