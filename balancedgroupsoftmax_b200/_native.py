@@ -44,6 +44,7 @@ SIGNATURES = {
                       _i, _i, _i, _vp]),
     'bags_merge_scores': (_i, [_vp, _ll, _vp, _vp, _i, _i, _i, _i, _vp, _ll, _vp]),
     'bags_grad_allreduce_flag_bytes': (_sz, [_i]),
+    'bags_grad_allreduce_status_offset': (_ll, [_i]),
     'bags_grad_allreduce': (_i, [_vp, _vp, _ll, _ll, _i, _i, C.c_float, _i, _vp]),
     'bags_debug_spin': (_i, [_i, _i, _i, _vp]),
     'bags_cast_bf16': (_i, [_vp, _ll, _vp, _ll, _i, _i, _vp]),

@@ -16,9 +16,13 @@
 // 5.07 MB per head: 2 * (N-1)/N * 5.07 MB cross each GPU's links (~6-9 us at 770 GB/s) plus two flag round
 // trips; NCCL's ring/tree launch measured ~53 us per step for the same bucket (profiles/r01_bench_2gpu_v5.json).
 //
-// Flags: uint32 [blocks][world] inside every rank's buffer, zero between launches (put = CAS 0->1 on the target,
-// wait = CAS 1->0 on the own copy), so graph replays need no reset.  All spins are bounded; a timeout sets the
-// status word after the flags ([kArMaxBlocks*world]) instead of trapping, so a broken peer cannot kill the context.
+// Flags (inside every rank's bucket allocation, zeroed once by the caller):
+//   slot[b][r]  written by rank r's block b with an EPOCH number (st.release.sys, fire and forget), polled locally by
+//               this rank's block b (ld.relaxed.sys until it reaches the expected epoch, then one acquire fence);
+//   epoch[b]    this rank's block b's own count of barriers so far (all ranks run the same launches, so they agree);
+//   status      set to 1 when a wait timed out (bounded spins; nothing traps, nothing hangs the device).
+// Epochs only grow, so nothing is reset and CUDA-graph replays need no host work; a sender may be one barrier ahead
+// of a slow receiver, hence the >= comparison (on the wrapped difference).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -29,8 +33,8 @@ namespace bags {
 constexpr int kMaxRanks = 16;
 // Small blocks with few registers: an exchange block fits on an SM next to a GEMM CTA of this library (48-55 K
 // registers), so an exchange launched on a side stream really overlaps the next step's kernels.
-constexpr int kArMaxBlocks = 256;
-constexpr int kArThreads = 256;
+constexpr int kArMaxBlocks = 320;
+constexpr int kArThreads = 128;
 
 struct AllReduceParams {
   float* peer[kMaxRanks];   // this process's mapping of every rank's bucket (peer[rank] is the local one)
@@ -41,16 +45,15 @@ struct AllReduceParams {
   float scale;              // 1/world for the mean (dist_utils.py:23), 1 for a sum
 };
 
-__device__ __forceinline__ uint32_t cas_release_sys(uint32_t* p, uint32_t cmp, uint32_t val) {
-  uint32_t old;
-  asm volatile("atom.global.release.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(cmp), "r"(val) : "memory");
-  return old;
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ uint32_t cas_acquire_sys(uint32_t* p, uint32_t cmp, uint32_t val) {
-  uint32_t old;
-  asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(cmp), "r"(val) : "memory");
-  return old;
+__device__ __forceinline__ uint32_t ld_relaxed_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ float4 ld_relaxed_sys_f4(const float* p) {
   float4 v;
   asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -73,47 +76,46 @@ __device__ __forceinline__ void multimem_st_f4(float* mc, const float4 v) {
 }
 
 // Block-level barrier across ranks: block b of every rank meets block b of every other rank.
-// Thread t < world signals rank t and waits for rank t's signal.  Preceded / followed by __syncthreads() so the
-// release / acquire of the signalling threads order the whole block's accesses (PTX memory model: cumulativity).
+// Thread t < world publishes `epoch` in rank t's slot for (block, this rank) and polls its own slot for (block, t).
+// Preceded / followed by __syncthreads() so that the release store / acquire fence of the signalling threads order
+// the whole block's accesses (PTX memory model: cumulativity through the CTA barrier).
 // A rank that never shows up does not hang the device: after ~2^22 probes the block records the failure in the
-// status word behind the flags (checked by the host-side self test) and the kernel returns without exchanging.
-__device__ __forceinline__ bool rank_barrier(const AllReduceParams& p, int* s_fail) {
+// status word (checked by the host-side self test) and the kernel returns without exchanging.
+__device__ __forceinline__ uint32_t* ar_flags(const AllReduceParams& p, int rank) {
+  return reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(p.peer[rank]) + p.flag_off);
+}
+__device__ __forceinline__ bool rank_barrier(const AllReduceParams& p, uint32_t epoch, int* s_fail) {
   __syncthreads();
   if (threadIdx.x < static_cast<unsigned>(p.world)) {
     const int t = static_cast<int>(threadIdx.x);
-    uint32_t* theirs = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(p.peer[t]) + p.flag_off) +
-                       blockIdx.x * p.world + p.rank;
-    uint32_t* mine = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(p.peer[p.rank]) + p.flag_off) +
-                     blockIdx.x * p.world + t;
+    st_release_sys_u32(ar_flags(p, t) + blockIdx.x * p.world + p.rank, epoch);
+    const uint32_t* mine = ar_flags(p, p.rank) + blockIdx.x * p.world + t;
     uint32_t spins = 0;
-    bool ok = true;
-    while (cas_release_sys(theirs, 0u, 1u) != 0u) {
-      if (++spins > (1u << 22)) { ok = false; break; }
+    while (static_cast<int32_t>(ld_relaxed_sys_u32(mine) - epoch) < 0) {
+      __nanosleep(40);
+      if (++spins > (1u << 22)) {
+        *s_fail = 1;
+        atomicExch(ar_flags(p, p.rank) + kArMaxBlocks * p.world + kArMaxBlocks, 1u);
+        break;
+      }
     }
-    spins = 0;
-    while (ok && cas_acquire_sys(mine, 1u, 0u) != 1u) {
-      __nanosleep(32);
-      if (++spins > (1u << 22)) { ok = false; break; }
-    }
-    if (!ok) {
-      *s_fail = 1;
-      uint32_t* status = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(p.peer[p.rank]) + p.flag_off) +
-                         kArMaxBlocks * p.world;
-      atomicExch(status, 1u);
-    }
+    fence_acq_rel_sys();
   }
   __syncthreads();
   return *s_fail == 0;
 }
 
 template <bool MULTIMEM>
-__global__ void __launch_bounds__(kArThreads, 6)
+__global__ void __launch_bounds__(kArThreads, 12)
 bags_grad_allreduce_kernel(const AllReduceParams p) {
   pdl_trigger();   // the next kernel of the stream (next step's sampler / forward mainloop) may start launching
   pdl_wait();      // the local gradients come from the preceding backward kernel
   __shared__ int s_fail;
   if (threadIdx.x == 0) s_fail = 0;
-  if (!rank_barrier(p, &s_fail)) return;
+  // this block's barrier count so far (same on every rank); two more after this launch
+  uint32_t* my_epoch = ar_flags(p, p.rank) + kArMaxBlocks * p.world + blockIdx.x;
+  const uint32_t epoch = *my_epoch;
+  if (!rank_barrier(p, epoch + 1u, &s_fail)) return;
 
   const long long vecs = p.count >> 2;
   const long long chunk = (vecs + p.world - 1) / p.world;
@@ -151,7 +153,8 @@ bags_grad_allreduce_kernel(const AllReduceParams p) {
       }
     }
   }
-  rank_barrier(p, &s_fail);
+  rank_barrier(p, epoch + 2u, &s_fail);
+  if (threadIdx.x == 0) *my_epoch = epoch + 2u;
 }
 
 }  // namespace bags

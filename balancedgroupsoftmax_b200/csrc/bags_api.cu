@@ -837,8 +837,13 @@ extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long 
 // ----------------------------------------------------------------------------
 extern "C" size_t bags_grad_allreduce_flag_bytes(int world) {
   if (world < 1) world = 1;
-  // flags [kArMaxBlocks][world] + one status word (non-zero after a timed-out exchange), padded to 64 bytes
-  return (static_cast<size_t>(kArMaxBlocks) * static_cast<size_t>(world) + 16) * sizeof(uint32_t);
+  // slots [kArMaxBlocks][world] + epochs [kArMaxBlocks] + one status word, padded to 64 bytes
+  return (static_cast<size_t>(kArMaxBlocks) * static_cast<size_t>(world) + kArMaxBlocks + 16) * sizeof(uint32_t);
+}
+
+extern "C" long long bags_grad_allreduce_status_offset(int world) {
+  if (world < 1) world = 1;
+  return (static_cast<long long>(kArMaxBlocks) * world + kArMaxBlocks) * static_cast<long long>(sizeof(uint32_t));
 }
 
 extern "C" int bags_grad_allreduce(void* const* peer_bufs_host, void* mc_buf, long long flag_off_bytes,

@@ -146,7 +146,8 @@ class PeerGradBucket(object):
 
     def status(self) -> int:
         """0, or 1 after an exchange in which some rank never arrived (the kernel gave up; the bucket is unusable)."""
-        word = self.flag_off // 4 + 256 * self.world   # kArMaxBlocks * world
+        from . import _native
+        word = (self.flag_off + int(_native.lib().bags_grad_allreduce_status_offset(self.world))) // 4
         return int(self.storage[word:word + 1].view(torch.int32).item())
 
     def self_test(self) -> bool:

@@ -239,6 +239,12 @@ def run_ours(args):
     ldd = ops.pad_cols(C)
     per_set = n * K_FEAT * elt * 2 + n * C * 4 + n * ldd * elt + C * K_FEAT * 4 + C * K_FEAT * elt * 2
     pool = max(2, int(np.ceil(2.2 * 126e6 / per_set)))
+    if args.pool:
+        pool = max(2, args.pool)
+    elif world > 1 and args.exchange == 'overlap':
+        # one CUDA graph spans the pool; its last exchange cannot hide under a following step, so a longer graph
+        # amortises that tail (each set is used once per graph: no exchange ever races a later step on its bucket)
+        pool = 20
     sets = []
     W_master = (torch.randn(C, K_FEAT, generator=gen) * 0.01)
     for i in range(pool):
@@ -657,6 +663,7 @@ def main():
     ap.add_argument('--rois', type=int, default=N_ROIS)
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--pool', type=int, default=0, help='number of rotating buffer sets (= steps per CUDA graph)')
     ap.add_argument('--fake-exchange', default='', help='probe (N = 1): blocks,threads,microseconds of a side-stream wait kernel per step')
     ap.add_argument('--exchange', default='overlap', choices=['overlap', 'inline'],
                     help='N > 1: gradient exchange on a side stream under the next step (default) or in line')

@@ -156,8 +156,10 @@ int bags_merge_scores(const float* logits, long long ldz, const int32_t* slices_
  *   scale          : applied to the sum (1/world = the reference's mean)
  * Every rank must issue the call with the same (count, world, max_blocks).  Stream-ordered after the local
  * gradients' producer; all waits are bounded: if a rank never arrives the kernel gives up, leaves the bucket
- * unreduced and sets the uint32 status word at flag_off_bytes + 256 * world * 4 to 1 (0 otherwise). */
+ * unreduced and sets the uint32 status word at flag_off_bytes + bags_grad_allreduce_status_offset(world) to 1
+ * (0 otherwise). */
 size_t bags_grad_allreduce_flag_bytes(int world);
+long long bags_grad_allreduce_status_offset(int world);
 int bags_grad_allreduce(void* const* peer_bufs_host, void* mc_buf, long long flag_off_bytes, long long count,
                         int rank, int world, float scale, int max_blocks, void* stream);
 

@@ -172,3 +172,18 @@ def test_loss_modules_semantics():
     assert torch.allclose(ce(z, y, reduction_override='none'), 2.0 * per)
     with pytest.raises(ValueError):
         ce(z, y, w, avg_factor=2.0, reduction_override='sum')
+
+
+def test_hostmem_cpulist_and_affinity_restore():
+    """NUMA staging helpers: cpulist parsing; the affinity / thread-count context always restores the caller's state
+    (and degrades to a no-op when the GPU topology cannot be read, as in this container)."""
+    import os
+    import torch
+    from balancedgroupsoftmax_b200 import hostmem
+    assert hostmem._parse_cpulist('0-3,8,10-11\n') == {0, 1, 2, 3, 8, 10, 11}
+    assert hostmem._parse_cpulist('') == set()
+    aff, nt = os.sched_getaffinity(0), torch.get_num_threads()
+    with hostmem.gpu_local_affinity(0) as cpus:
+        assert cpus is None or cpus <= aff
+        assert torch.get_num_threads() == 1
+    assert os.sched_getaffinity(0) == aff and torch.get_num_threads() == nt
