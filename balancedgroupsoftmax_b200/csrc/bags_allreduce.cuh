@@ -18,7 +18,8 @@
 //
 // Flags (inside every rank's bucket allocation, zeroed once by the caller):
 //   slot[b][r]  written by rank r's block b with an EPOCH number (st.release.sys, fire and forget), polled locally by
-//               this rank's block b (ld.relaxed.sys until it reaches the expected epoch, then one acquire fence);
+//               this rank's block b (ld.acquire.sys until it reaches the expected epoch);
+//               or, protocol "cas": toggled 0 -> 1 by the sender (CAS on the target) and 1 -> 0 by the receiver;
 //   epoch[b]    this rank's block b's own count of barriers so far (all ranks run the same launches, so they agree);
 //   status      set to 1 when a wait timed out (bounded spins; nothing traps, nothing hangs the device).
 // Epochs only grow, so nothing is reset and CUDA-graph replays need no host work; a sender may be one barrier ahead
@@ -34,7 +35,7 @@ constexpr int kMaxRanks = 16;
 // Small blocks with few registers: an exchange block fits on an SM next to a GEMM CTA of this library (48-55 K
 // registers), so an exchange launched on a side stream really overlaps the next step's kernels.
 constexpr int kArMaxBlocks = 320;
-constexpr int kArThreads = 128;
+constexpr int kArThreads = 256;   // upper bound; the launch may use fewer (BAGS_AR_THREADS)
 
 struct AllReduceParams {
   float* peer[kMaxRanks];   // this process's mapping of every rank's bucket (peer[rank] is the local one)
@@ -53,7 +54,21 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys_u32(const uint32_t* p) {
   asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t cas_release_sys(uint32_t* p, uint32_t cmp, uint32_t val) {
+  uint32_t old;
+  asm volatile("atom.global.release.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(cmp), "r"(val) : "memory");
+  return old;
+}
+__device__ __forceinline__ uint32_t cas_acquire_sys(uint32_t* p, uint32_t cmp, uint32_t val) {
+  uint32_t old;
+  asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(cmp), "r"(val) : "memory");
+  return old;
+}
 __device__ __forceinline__ float4 ld_relaxed_sys_f4(const float* p) {
   float4 v;
   asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -84,29 +99,44 @@ __device__ __forceinline__ void multimem_st_f4(float* mc, const float4 v) {
 __device__ __forceinline__ uint32_t* ar_flags(const AllReduceParams& p, int rank) {
   return reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(p.peer[rank]) + p.flag_off);
 }
+// EPOCH = true : slots carry monotonically growing epoch numbers (release store, local acquire-load polling).
+// EPOCH = false: slots toggle 0 -> 1 -> 0 (put = CAS 0->1 on the target, wait = CAS 1->0 on the own copy).
+template <bool EPOCH>
 __device__ __forceinline__ bool rank_barrier(const AllReduceParams& p, uint32_t epoch, int* s_fail) {
   __syncthreads();
   if (threadIdx.x < static_cast<unsigned>(p.world)) {
     const int t = static_cast<int>(threadIdx.x);
-    st_release_sys_u32(ar_flags(p, t) + blockIdx.x * p.world + p.rank, epoch);
-    const uint32_t* mine = ar_flags(p, p.rank) + blockIdx.x * p.world + t;
+    uint32_t* theirs = ar_flags(p, t) + blockIdx.x * p.world + p.rank;
+    uint32_t* mine = ar_flags(p, p.rank) + blockIdx.x * p.world + t;
     uint32_t spins = 0;
-    while (static_cast<int32_t>(ld_relaxed_sys_u32(mine) - epoch) < 0) {
-      __nanosleep(40);
-      if (++spins > (1u << 22)) {
-        *s_fail = 1;
-        atomicExch(ar_flags(p, p.rank) + kArMaxBlocks * p.world + kArMaxBlocks, 1u);
-        break;
+    bool ok = true;
+    if (EPOCH) {
+      st_release_sys_u32(theirs, epoch);
+      while (static_cast<int32_t>(ld_acquire_sys_u32(mine) - epoch) < 0) {
+        __nanosleep(20);
+        if (++spins > (1u << 22)) { ok = false; break; }
+      }
+    } else {
+      while (cas_release_sys(theirs, 0u, 1u) != 0u) {
+        if (++spins > (1u << 22)) { ok = false; break; }
+      }
+      spins = 0;
+      while (ok && cas_acquire_sys(mine, 1u, 0u) != 1u) {
+        __nanosleep(20);
+        if (++spins > (1u << 22)) { ok = false; break; }
       }
     }
-    fence_acq_rel_sys();
+    if (!ok) {
+      *s_fail = 1;
+      atomicExch(ar_flags(p, p.rank) + kArMaxBlocks * p.world + kArMaxBlocks, 1u);
+    }
   }
   __syncthreads();
   return *s_fail == 0;
 }
 
-template <bool MULTIMEM>
-__global__ void __launch_bounds__(kArThreads, 12)
+template <bool MULTIMEM, bool EPOCH>
+__global__ void __launch_bounds__(kArThreads, 6)
 bags_grad_allreduce_kernel(const AllReduceParams p) {
   pdl_trigger();   // the next kernel of the stream (next step's sampler / forward mainloop) may start launching
   pdl_wait();      // the local gradients come from the preceding backward kernel
@@ -115,7 +145,7 @@ bags_grad_allreduce_kernel(const AllReduceParams p) {
   // this block's barrier count so far (same on every rank); two more after this launch
   uint32_t* my_epoch = ar_flags(p, p.rank) + kArMaxBlocks * p.world + blockIdx.x;
   const uint32_t epoch = *my_epoch;
-  if (!rank_barrier(p, epoch + 1u, &s_fail)) return;
+  if (!rank_barrier<EPOCH>(p, epoch + 1u, &s_fail)) return;
 
   const long long vecs = p.count >> 2;
   const long long chunk = (vecs + p.world - 1) / p.world;
@@ -153,7 +183,7 @@ bags_grad_allreduce_kernel(const AllReduceParams p) {
       }
     }
   }
-  rank_barrier(p, epoch + 2u, &s_fail);
+  rank_barrier<EPOCH>(p, epoch + 2u, &s_fail);
   if (threadIdx.x == 0) *my_epoch = epoch + 2u;
 }
 

@@ -871,17 +871,22 @@ extern "C" int bags_grad_allreduce(void* const* peer_bufs_host, void* mc_buf, lo
   p.count = count;
   p.rank = rank; p.world = world; p.scale = scale;
   if (count == 0) return BAGS_OK;
-  // enough threads to keep one vector per thread and unroll slot in flight, at most kArMaxBlocks blocks
+  // enough threads to keep one vector per thread and unroll slot in flight, at most kArMaxBlocks blocks;
+  // every rank must launch the same grid: it depends only on (count, world, max_blocks) and the environment
+  int threads = env_int("BAGS_AR_THREADS", 256);
+  if (threads != 128 && threads != 256) threads = 256;
   const long long per_rank = (count / 4 + world - 1) / world;
-  long long blocks = (per_rank + static_cast<long long>(kArThreads) * 4 - 1) / (static_cast<long long>(kArThreads) * 4);
+  long long blocks = (per_rank + static_cast<long long>(threads) * 4 - 1) / (static_cast<long long>(threads) * 4);
   if (blocks < 1) blocks = 1;
   if (max_blocks <= 0 || max_blocks > kArMaxBlocks) max_blocks = kArMaxBlocks;
   if (blocks > max_blocks) blocks = max_blocks;
-  // every rank must launch the same grid: `blocks` depends only on (count, world, max_blocks)
-  if (p.mc != nullptr && !env_int("BAGS_AR_NO_MULTIMEM", 0))
-    BAGS_CUDA(launch_pdl(bags_grad_allreduce_kernel<true>, dim3(static_cast<unsigned>(blocks)), dim3(kArThreads), 0, stream, p));
-  else
-    BAGS_CUDA(launch_pdl(bags_grad_allreduce_kernel<false>, dim3(static_cast<unsigned>(blocks)), dim3(kArThreads), 0, stream, p));
+  const bool mm = p.mc != nullptr && !env_int("BAGS_AR_NO_MULTIMEM", 0);
+  const bool epoch = env_int("BAGS_AR_EPOCH", 1) != 0;
+  const dim3 grid(static_cast<unsigned>(blocks)), block(static_cast<unsigned>(threads));
+  if (mm && epoch)       BAGS_CUDA(launch_pdl(bags_grad_allreduce_kernel<true, true>, grid, block, 0, stream, p));
+  else if (mm)           BAGS_CUDA(launch_pdl(bags_grad_allreduce_kernel<true, false>, grid, block, 0, stream, p));
+  else if (epoch)        BAGS_CUDA(launch_pdl(bags_grad_allreduce_kernel<false, true>, grid, block, 0, stream, p));
+  else                   BAGS_CUDA(launch_pdl(bags_grad_allreduce_kernel<false, false>, grid, block, 0, stream, p));
   return BAGS_OK;
 }
 

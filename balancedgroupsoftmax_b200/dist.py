@@ -35,10 +35,48 @@ def allreduce_flat_(flat: torch.Tensor, async_op: bool = False):
     return None
 
 
+_peer_buckets = {}   # (device index, numel) -> PeerGradBucket | None (None: tried, unavailable)
+
+
+def _peer_bucket_for(numel: int, device) -> Optional['PeerGradBucket']:
+    """Cached peer-memory staging bucket for fp32 gradient sets of `numel` elements (None -> use NCCL)."""
+    if os.environ.get('BAGS_ALLREDUCE', 'peer') == 'nccl' or not PeerGradBucket.available():
+        return None
+    key = (torch.device(device).index, int(numel))
+    if key not in _peer_buckets:
+        try:
+            b = PeerGradBucket([(int(numel),)], device)
+            _peer_buckets[key] = b if b.self_test() else None
+        except Exception:
+            _peer_buckets[key] = None
+    return _peer_buckets[key]
+
+
 def allreduce_grads(params: Iterable[torch.nn.Parameter], coalesce: bool = True) -> None:
+    """Mean of the gradients over ranks (mmdet/core/utils/dist_utils.py:31-41).  fp32 CUDA gradients travel through
+    the NVLink peer-memory kernel when it is available (flatten into the symmetric bucket -> bags_grad_allreduce ->
+    copy back: the reference's flatten / all_reduce / div / unflatten with the collective replaced); anything else
+    takes the reference's NCCL / gloo route."""
     grads = [p.grad.data for p in params if p.requires_grad and p.grad is not None]
     if not grads:
         return
+    if coalesce:
+        f32 = [g for g in grads if g.dtype == torch.float32 and g.is_cuda]
+        if f32:
+            bucket = _peer_bucket_for(sum(g.numel() for g in f32), f32[0].device)
+            if bucket is not None:
+                off = 0
+                for g in f32:
+                    bucket.flat[off:off + g.numel()].view_as(g).copy_(g)
+                    off += g.numel()
+                bucket.allreduce_()
+                off = 0
+                for g in f32:
+                    g.copy_(bucket.flat[off:off + g.numel()].view_as(g))
+                    off += g.numel()
+                grads = [g for g in grads if not (g.dtype == torch.float32 and g.is_cuda)]
+                if not grads:
+                    return
     if not coalesce:
         for g in grads:
             allreduce_flat_(g)

@@ -108,6 +108,34 @@ def main():
                 print('%s: %.2f us per exchange of %.2f MB' % (tag, float(t.item()), bucket.numel * 4 / 1e6), flush=True)
         del graph, tg
 
+    quick = '--quick' in sys.argv
+    if quick:
+        if rank == 0:
+            print(json.dumps(out), flush=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0 if out['ok'] else 1)
+    # the reference-shaped entry point (dist_utils.py:31-41): grads of a parameter list, through the peer bucket
+    os.environ.pop('BAGS_AR_NO_MULTIMEM', None)
+    from balancedgroupsoftmax_b200.dist import allreduce_grads, _peer_buckets
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    params = [torch.nn.Parameter(torch.zeros(1236, 1024, device=dev)), torch.nn.Parameter(torch.zeros(1236, device=dev)),
+              torch.nn.Parameter(torch.zeros(7, device=dev, dtype=torch.float64)),
+              torch.nn.Parameter(torch.zeros(3, device=dev), requires_grad=False)]
+    for p_ in params[:3]:
+        p_.grad = torch.randn(p_.shape, device=dev, generator=g, dtype=p_.dtype)
+    refs = []
+    for p_ in params[:3]:
+        r_ = p_.grad.clone()
+        dist.all_reduce(r_)
+        refs.append(r_ / world)
+    allreduce_grads(params)
+    torch.cuda.synchronize()
+    err = max(((p_.grad - r_).abs().max().item() for p_, r_ in zip(params[:3], refs)))
+    used = any(b is not None for b in _peer_buckets.values())
+    check('allreduce_grads(params) via peer bucket == NCCL mean', err <= 1e-6 and used, 'err %.2e, peer bucket used: %s' % (err, used))
+
     # NCCL reference timing (graph of 50 all-reduces on the same bucket size)
     flat = torch.zeros(sum(torch.Size(s).numel() for s in shapes), device=dev)
     stream = torch.cuda.Stream(device=dev)
