@@ -878,6 +878,7 @@ extern "C" int bags_grad_allreduce(void* const* peer_bufs_host, void* mc_buf, lo
   const long long per_rank = (count / 4 + world - 1) / world;
   long long blocks = (per_rank + static_cast<long long>(threads) * 4 - 1) / (static_cast<long long>(threads) * 4);
   if (blocks < 1) blocks = 1;
+  if (max_blocks <= 0) max_blocks = env_int("BAGS_AR_MAX_BLOCKS", kArMaxBlocks);
   if (max_blocks <= 0 || max_blocks > kArMaxBlocks) max_blocks = kArMaxBlocks;
   if (blocks > max_blocks) blocks = max_blocks;
   const bool mm = p.mc != nullptr && !env_int("BAGS_AR_NO_MULTIMEM", 0);

@@ -520,8 +520,15 @@ def run_ours(args):
     # ---- per-kernel durations (CUDA events, rotating sets) for the roofline ------------------
     roof = None
     kernel_us = {}
-    if rank == 0 and args.profile:
-        print(json.dumps({'profile_run': True, 'ms_per_step': ms_step, 'value': value}), flush=True)
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({'profile_run': True, 'ms_per_step': ms_step, 'value': value}), flush=True)
+        if world > 1:
+            graph = None
+            torch.cuda.synchronize()
+            dist.barrier()
+            sys.stdout.flush()
+            os._exit(0)
         return 0
     if rank == 0:
         pk = peaks()
