@@ -407,6 +407,28 @@ class GSBBoxHeadWith0(SharedFCBBoxHead):
         self._sample_calls = 0
         self.last_sample = None  # (wmask [G,N] uint8, avg [G]) of the latest loss() call, for inspection
 
+    # ---- reference checkpoints -----------------------------------------------------------
+    def load_reference_checkpoint(self, checkpoint, prefix: str = 'bbox_head.', strict: bool = True):
+        """Load this head's parameters from a reference detector checkpoint (mmcv format: a dict with a
+        ``'state_dict'`` entry, keys such as ``bbox_head.fc_cls.weight`` [1236,1024]; cascade / HTC checkpoints use
+        ``bbox_head.<stage>.`` -- pass that as ``prefix``).  ``checkpoint`` is a path or an already loaded dict.
+        Returns the (missing, unexpected) key lists of ``load_state_dict``."""
+        if isinstance(checkpoint, (str, os.PathLike)):
+            checkpoint = torch.load(checkpoint, map_location='cpu')
+        sd = checkpoint.get('state_dict', checkpoint)
+        if any(k.startswith('module.') for k in sd):      # saved from (Distributed)DataParallel
+            sd = {(k[7:] if k.startswith('module.') else k): v for k, v in sd.items()}
+        own = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)} if prefix else dict(sd)
+        if not own:
+            raise KeyError('no key with prefix %r in the checkpoint' % prefix)
+        want = self.state_dict()
+        for k, v in own.items():
+            if k in want and tuple(v.shape) != tuple(want[k].shape):
+                raise ValueError('%s%s has shape %s, this head expects %s' % (prefix, k, tuple(v.shape),
+                                                                             tuple(want[k].shape)))
+        res = self.load_state_dict(own, strict=strict)
+        return list(res.missing_keys), list(res.unexpected_keys)
+
     # ---- device-side tables -------------------------------------------------------------
     def device_tables(self, device) -> ops.DeviceTables:
         device = torch.device(device)

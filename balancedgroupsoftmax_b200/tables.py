@@ -148,3 +148,53 @@ def load_reference_files(label2binlabel: str, pred_slice: str, fg_split: str) ->
     else:
         fg = [np.asarray(split['bin%d' % (i + 1)], dtype=np.int64) for i in range(num_bins - 1)]
     return GroupTables(l2b, ps, fg)
+
+
+def instance_counts_from_annotations(ann_file: str) -> Dict[int, int]:
+    """Per-category training instance counts from an LVIS-style annotation json: what ``LVIS(ann).cats`` gives
+    tools/lvis_analyse.py:13-15 (``categories[*].id`` -> ``categories[*].instance_count``), in file order (the
+    reference iterates the dict in insertion order, and local bin indices follow that order, :23-36).  When a
+    category carries no ``instance_count`` the annotations are counted instead."""
+    import json
+    with open(ann_file) as f:
+        data = json.load(f)
+    cats = data['categories']
+    if all('instance_count' in c for c in cats):
+        return {int(c['id']): int(c['instance_count']) for c in cats}
+    counts = {int(c['id']): 0 for c in cats}
+    for a in data.get('annotations', []):
+        counts[int(a['category_id'])] += 1
+    return counts
+
+
+def main(argv=None) -> int:
+    """python -m balancedgroupsoftmax_b200.tables --ann lvis_v0.5_train.json --out data/lvis
+    Writes label2binlabel.pt, pred_slice_with0.pt and valsplit.pkl in the reference's formats
+    (tools/lvis_analyse.py: get_cate_gs + get_split; --thresholds generalises the 5-bin split)."""
+    import argparse
+    ap = argparse.ArgumentParser(description=main.__doc__)
+    ap.add_argument('--ann', help='LVIS-style training annotation json (categories with instance_count)')
+    ap.add_argument('--synthetic', type=int, default=None, metavar='SEED',
+                    help='no annotation file: seeded long-tailed synthetic counts')
+    ap.add_argument('--num-classes', type=int, default=None, help='labels incl. background (default: max id + 1)')
+    ap.add_argument('--thresholds', type=int, nargs='+', default=list(DEFAULT_THRESHOLDS))
+    ap.add_argument('--out', required=True)
+    args = ap.parse_args(argv)
+    if args.ann:
+        counts = instance_counts_from_annotations(args.ann)
+    elif args.synthetic is not None:
+        counts = synthetic_instance_counts((args.num_classes or 1231) - 1, args.synthetic)
+    else:
+        ap.error('give --ann or --synthetic')
+    num_classes = args.num_classes or (max(counts) + 1)
+    tables = build_group_tables(counts, num_classes, args.thresholds)
+    paths = save_reference_files(tables, args.out)
+    print('bins: %s' % ', '.join('%d+1' % len(s) if i else '2' for i, s in enumerate([None] + tables.fg_splits)))
+    print('pred_slice:', tables.pred_slice.tolist())
+    for k, v in paths.items():
+        print('%s -> %s' % (k, v))
+    return 0
+
+
+if __name__ == '__main__':
+    raise SystemExit(main())

@@ -187,3 +187,35 @@ def test_hostmem_cpulist_and_affinity_restore():
         assert cpus is None or cpus <= aff
         assert torch.get_num_threads() == 1
     assert os.sched_getaffinity(0) == aff and torch.get_num_threads() == nt
+
+
+def test_load_reference_checkpoint_roundtrip(tmp_path):
+    """A checkpoint laid out like the reference's (mmcv dict, 'bbox_head.' prefix, optional 'module.') loads into the
+    head; shape mismatches and missing prefixes are refused."""
+    import torch
+    from balancedgroupsoftmax_b200.head import GSBBoxHeadWith0
+    from balancedgroupsoftmax_b200.tables import synthetic_tables
+    t = synthetic_tables()
+    mk = lambda: GSBBoxHeadWith0(num_fcs=2, in_channels=4, fc_out_channels=32, roi_feat_size=2, num_classes=t.num_classes,
+                                 gs_config=dict(tables=t, others_sample_ratio=8.0, num_bins=5,
+                                                loss_bin=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0)))
+    src, dst = mk(), mk()
+    src.init_weights()
+    with torch.no_grad():
+        src.fc_cls.bias.uniform_(-1, 1)
+    sd = {'module.bbox_head.' + k: v.clone() for k, v in src.state_dict().items()}
+    sd['module.backbone.conv1.weight'] = torch.zeros(3)
+    path = tmp_path / 'epoch_12.pth'
+    torch.save({'meta': {}, 'state_dict': sd}, str(path))
+    missing, unexpected = dst.load_reference_checkpoint(str(path))
+    assert not missing and not unexpected
+    assert dst.fc_cls.weight.shape == (t.num_logits, 32)
+    for k, v in src.state_dict().items():
+        assert torch.equal(dst.state_dict()[k], v)
+    import pytest
+    with pytest.raises(KeyError):
+        dst.load_reference_checkpoint({'state_dict': sd}, prefix='bbox_head.2.')
+    bad = dict(sd)
+    bad['module.bbox_head.fc_cls.weight'] = torch.zeros(1231, 32)
+    with pytest.raises(ValueError):
+        dst.load_reference_checkpoint({'state_dict': bad})

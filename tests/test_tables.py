@@ -64,3 +64,29 @@ def test_other_bin_counts():
         build_group_tables(counts, thresholds=(5, 10, 50, 100, 500, 1000))
     assert t2.num_bins == 3 and t2.num_logits == 1231 + 3
     assert t8.num_bins == 8 and t8.num_logits == 1231 + 8
+
+
+def test_cli_from_annotation_json(tmp_path):
+    """tools/lvis_analyse.py get_cate_gs + get_split from a categories list: file order defines the local indices,
+    the written files load back through the head's own loader."""
+    import json
+    from balancedgroupsoftmax_b200 import tables as T
+    cats = [dict(id=3, instance_count=5), dict(id=1, instance_count=50000), dict(id=2, instance_count=12),
+            dict(id=5, instance_count=999), dict(id=4, instance_count=7)]
+    ann = tmp_path / 'ann.json'
+    ann.write_text(json.dumps(dict(categories=cats, annotations=[])))
+    assert T.main(['--ann', str(ann), '--out', str(tmp_path / 'out')]) == 0
+    t = T.load_reference_files(str(tmp_path / 'out' / 'label2binlabel.pt'), str(tmp_path / 'out' / 'pred_slice_with0.pt'),
+                               str(tmp_path / 'out' / 'valsplit.pkl'))
+    assert t.pred_slice.tolist() == [[0, 2], [2, 3], [5, 2], [7, 2], [9, 2]]
+    assert t.label2binlabel[0].tolist() == [0, 1, 1, 1, 1, 1]
+    assert t.label2binlabel[1].tolist() == [0, 0, 0, 1, 2, 0]      # ids 3 then 4, in file order
+    assert t.label2binlabel[2].tolist() == [0, 0, 1, 0, 0, 0]
+    assert t.label2binlabel[3].tolist() == [0, 0, 0, 0, 0, 1]
+    assert t.label2binlabel[4].tolist() == [0, 1, 0, 0, 0, 0]
+    assert [s.tolist() for s in t.fg_splits] == [[3, 4], [2], [5], [1]]
+    # counted from annotations when the categories carry no instance_count
+    ann2 = tmp_path / 'ann2.json'
+    ann2.write_text(json.dumps(dict(categories=[dict(id=1), dict(id=2)],
+                                    annotations=[dict(category_id=2)] * 11 + [dict(category_id=1)] * 3)))
+    assert T.instance_counts_from_annotations(str(ann2)) == {1: 3, 2: 11}
