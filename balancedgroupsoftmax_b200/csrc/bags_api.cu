@@ -878,10 +878,14 @@ extern "C" int bags_grad_allreduce(void* const* peer_bufs_host, void* mc_buf, lo
   const long long per_rank = (count / 4 + world - 1) / world;
   long long blocks = (per_rank + static_cast<long long>(threads) * 4 - 1) / (static_cast<long long>(threads) * 4);
   if (blocks < 1) blocks = 1;
-  if (max_blocks <= 0) max_blocks = env_int("BAGS_AR_MAX_BLOCKS", kArMaxBlocks);
+  const bool mm = p.mc != nullptr && !env_int("BAGS_AR_NO_MULTIMEM", 0);
+  // Default grid: the multimem path runs on few blocks -- its system-scope fences and switch round trips disturb
+  // co-resident GEMM CTAs, and an exchange that overlaps the next step is not latency-critical (N = 2, overlapped:
+  // 16 blocks 60.5 us/step, 155 blocks 64.2; profiles/r01_bench_2gpu_v18_variants.log); plain peer ld/st keeps one
+  // vector per thread in flight (16 blocks: 73.1 us/step, 155 blocks: 64.8).
+  if (max_blocks <= 0) max_blocks = env_int("BAGS_AR_MAX_BLOCKS", mm ? 16 : kArMaxBlocks);
   if (max_blocks <= 0 || max_blocks > kArMaxBlocks) max_blocks = kArMaxBlocks;
   if (blocks > max_blocks) blocks = max_blocks;
-  const bool mm = p.mc != nullptr && !env_int("BAGS_AR_NO_MULTIMEM", 0);
   const bool epoch = env_int("BAGS_AR_EPOCH", 1) != 0;
   const dim3 grid(static_cast<unsigned>(blocks)), block(static_cast<unsigned>(threads));
   if (mm && epoch)       BAGS_CUDA(launch_pdl(bags_grad_allreduce_kernel<true, true>, grid, block, 0, stream, p));

@@ -371,6 +371,11 @@ def run_ours(args):
         stream.synchronize()
         clk = clocks.stop()
     value = world * n / (ms_step * 1e-3)
+    if world > 1:
+        # every exchange of the run completed: no bucket recorded a timed-out rank barrier
+        bad = [i for i, s in enumerate(sets) if s.get('bucket') is not None and s['bucket'].status() != 0]
+        if bad:
+            raise SystemExit('gradient exchange timed out on buffer sets %s (rank %d)' % (bad, rank))
 
     # ---- e2e: public API, host buffers, H2D + D2H inside the timed region -------------------
     e2e = None
