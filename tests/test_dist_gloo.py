@@ -46,6 +46,15 @@ def _worker(rank, world, port, q):
         allreduce_flat_(flat)
         ok = ok and torch.allclose(dW, torch.full((12, 8), 1.0)) and torch.allclose(db, torch.full((12,), 2.0))
         ok = ok and dW.data_ptr() == flat.data_ptr()
+        # make_grad_bucket: no NVLink peer memory under gloo -> plain bucket + the reference's collective, same result
+        from balancedgroupsoftmax_b200.dist import PeerGradBucket, make_grad_bucket
+        ok = ok and not PeerGradBucket.available() and bool(PeerGradBucket.why_not)   # (no CUDA / not NCCL)
+        bucket, flat2, (gW, gb), exchange = make_grad_bucket([(6, 4), (6,)], 'cpu')
+        gW.fill_(float(rank + 1))
+        gb.fill_(10.0 * rank)
+        exchange()
+        ok = ok and bucket is None and torch.allclose(gW, torch.full((6, 4), 1.5)) and \
+            torch.allclose(gb, torch.full((6,), 5.0)) and gW.data_ptr() == flat2.data_ptr()
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
