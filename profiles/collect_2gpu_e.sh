@@ -7,7 +7,7 @@ mkdir -p $out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 port=29560
 i=0
-for cfg in "BAGS_AR_THREADS=128 BAGS_AR_MAX_BLOCKS=32" "BAGS_AR_THREADS=256 BAGS_AR_MAX_BLOCKS=32" "BAGS_AR_THREADS=256 BAGS_AR_MAX_BLOCKS=8"; do
+for cfg in "BAGS_AR_THREADS=128 BAGS_AR_MAX_BLOCKS=32" "BAGS_AR_THREADS=256 BAGS_AR_MAX_BLOCKS=32"; do
   port=$((port+1)); i=$((i+1))
   f=$out/${tag}_bench_${N}gpu_cfg$i
   env $cfg timeout 100 $TR --master-port $port bench.py --gpus $N --steps 240 --warmup 12 --allreduce peer --exchange overlap --profile > $f.json 2> $f.err; echo "bench [$cfg] rc=$?"
