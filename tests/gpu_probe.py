@@ -440,6 +440,35 @@ def case_timing(name):
     res['fwd_fused_us'] = timeit(lambda: ops.fused_fwd(xc, wc, bc, lc, dt, wmask, avg))
     # torch reference pieces on the same device for scale
     res['torch_matmul_bf16_us'] = timeit(lambda: torch.matmul(xc, wc.t()))
+    # library yardstick: the three plain GEMMs of a step (no softmax, no loss) through cuBLAS, replayed from a CUDA
+    # graph so that host launch gaps do not count
+    try:
+        dzc = dz[:, :t.num_logits].contiguous()
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            def three():
+                z = torch.matmul(xc, wc.t())
+                gw = torch.matmul(dzc.t(), xc)
+                gx = torch.matmul(dzc, wc)
+                return z, gw, gx
+            for _ in range(3):
+                three()
+            st.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=st):
+                for _ in range(10):
+                    three()
+            g.replay()
+            st.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            for _ in range(10):
+                g.replay()
+            e1.record(st)
+            st.synchronize()
+        res['cublas_three_gemms_graph_us'] = e0.elapsed_time(e1) / 100 * 1e3
+    except Exception as ex:  # pragma: no cover
+        res['cublas_three_gemms_graph_us'] = repr(ex)
     return res
 
 
