@@ -14,6 +14,7 @@
 #include "../../include/bags_b200.h"
 #include "bags_gemm.cuh"
 #include "bags_fused_fwd.cuh"
+#include "bags_fused_fwd_pair.cuh"
 #include "bags_bwd_fused.cuh"
 #include "bags_kernels.cuh"
 #include "bags_allreduce.cuh"
@@ -487,6 +488,45 @@ static int launch_fused_fwd(const void* x, long long ldx, const void* w, long lo
   return BAGS_OK;
 }
 
+// EXPERIMENTAL (BAGS_FWD_PAIR=1): the CTA-pair forward, bags_fused_fwd_pair.cuh.  Same parameters and outputs.
+template <bool TF32>
+static int launch_fused_fwd_pair(const void* x, long long ldx, const void* w, long long ldw, const FusedFwdParams& p0,
+                                 void* dz, long long ldd, cudaStream_t stream) {
+  using Cfg = FusedPairCfg<TF32>;
+  const int dtype = TF32 ? BAGS_DTYPE_F32 : BAGS_DTYPE_BF16;
+  CUtensorMap tx, tw;
+  int rc = make_tmap(&tx, x, dtype, p0.K, p0.N, ldx, Cfg::BLOCK_K, Cfg::BLOCK_M);
+  if (rc) return rc;
+  rc = make_tmap(&tw, w, dtype, p0.K, p0.C, ldw, Cfg::BLOCK_K, Cfg::HALF_N);   // each CTA stages 80 of 160 W rows
+  if (rc) return rc;
+  if (dz != nullptr && (reinterpret_cast<uintptr_t>(dz) & 15) != 0)
+    return fail(BAGS_ERR_INVALID, "bags_fwd: dz must be 16-byte aligned");
+  FusedFwdParams p = p0;
+  p.dz = dz;
+  p.ldd = ldd;
+  p.kblocks = (p.K + Cfg::BLOCK_K - 1) / Cfg::BLOCK_K;
+  p.want_dz = dz != nullptr ? 1 : 0;
+  p.timing = g_timing;
+  p.dbg = g_timing ? g_dbg : 0;
+  auto kernel = bags_fwd_pair_kernel<TF32>;
+  BAGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  const int row_tiles = (p.N + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
+  const int grid = Cfg::CLUSTER * ((row_tiles + 1) / 2);   // an 8-CTA cluster owns two row tiles (the last may be empty)
+  if (grid > 4096) return fail(BAGS_ERR_INVALID, "bags_fwd: N=%d too large for the fused path's loss workspace", p.N);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(Cfg::NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = env_int("BAGS_PDL", 1) ? 1 : 0;
+  BAGS_CUDA(cudaLaunchKernelEx(&cfg, kernel, tx, tw, p));
+  return BAGS_OK;
+}
+
 extern "C" int bags_fwd(const void* x, long long ldx, const void* w, long long ldw,
                         const float* bias, const int64_t* labels, const int32_t* label2bin,
                         const int32_t* slices_host, const uint8_t* wmask, const float* avg, int N,
@@ -535,6 +575,9 @@ extern "C" int bags_fwd(const void* x, long long ldx, const void* w, long long l
   p.counter = reinterpret_cast<unsigned int*>(workspace);
   p.part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
   if (N == 0) dz = nullptr;
+  if (env_int("BAGS_FWD_PAIR", 0))
+    return dtype == BAGS_DTYPE_BF16 ? launch_fused_fwd_pair<false>(x, ldx, w, ldw, p, dz, ldd, stream)
+                                    : launch_fused_fwd_pair<true>(x, ldx, w, ldw, p, dz, ldd, stream);
   return dtype == BAGS_DTYPE_BF16 ? launch_fused_fwd<false>(x, ldx, w, ldw, p, dz, ldd, di, stream)
                                   : launch_fused_fwd<true>(x, ldx, w, ldw, p, dz, ldd, di, stream);
 }
