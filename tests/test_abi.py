@@ -77,3 +77,32 @@ def test_product_does_not_import_oracle():
         if fn.endswith('.py'):
             src = open(os.path.join(pkg, fn)).read()
             assert 'oracle' not in src.replace('# oracle', ''), '%s references the oracle' % fn
+
+
+def test_grad_allreduce_argument_validation():
+    """bags_grad_allreduce: layout / rank / alignment errors are reported before anything touches a device."""
+    lib = nat.lib()
+    assert lib.bags_grad_allreduce_flag_bytes(2) > lib.bags_grad_allreduce_status_offset(2) > 0
+    assert lib.bags_grad_allreduce_flag_bytes(8) > lib.bags_grad_allreduce_flag_bytes(2)
+    assert lib.bags_grad_allreduce_flag_bytes(8) % 4 == 0
+    buf = (C.c_char * 4096)()
+    base = (C.addressof(buf) + 255) // 256 * 256
+    peers = (C.c_void_p * 2)(base, base + 1024)
+    # NULL peer table
+    rc = lib.bags_grad_allreduce(None, None, 1024, 16, 0, 2, 0.5, 0, None)
+    assert rc == -1 and b'peer_bufs_host' in lib.bags_last_error()
+    # rank outside the world / too many ranks
+    assert lib.bags_grad_allreduce(peers, None, 1024, 16, 2, 2, 0.5, 0, None) == -1
+    assert lib.bags_grad_allreduce(peers, None, 1024, 16, 0, 17, 0.5, 0, None) == -1
+    # count not a multiple of 4 floats
+    rc = lib.bags_grad_allreduce(peers, None, 1024, 10, 0, 2, 0.5, 0, None)
+    assert rc == -1 and b'multiple of 4' in lib.bags_last_error()
+    # flags overlapping the data
+    rc = lib.bags_grad_allreduce(peers, None, 32, 16, 0, 2, 0.5, 0, None)
+    assert rc == -1 and b'flag' in lib.bags_last_error()
+    # misaligned peer mapping
+    bad = (C.c_void_p * 2)(base, base + 1028)
+    rc = lib.bags_grad_allreduce(bad, None, 1024, 16, 0, 2, 0.5, 0, None)
+    assert rc != 0
+    with pytest.raises(nat.BagsNativeError):
+        nat.check(rc, 'bags_grad_allreduce')
