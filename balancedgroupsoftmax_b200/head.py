@@ -50,6 +50,54 @@ def _mmdet_core(name):
         return None
 
 
+def bbox2delta(proposals, gt, means=(0, 0, 0, 0), stds=(1, 1, 1, 1)):
+    """Box encoding of the regression targets; same maths as mmdet/core/bbox/transforms.py:6-31 (legacy "+1" widths)."""
+    assert proposals.size() == gt.size()
+    proposals, gt = proposals.float(), gt.float()
+    px = (proposals[..., 0] + proposals[..., 2]) * 0.5
+    py = (proposals[..., 1] + proposals[..., 3]) * 0.5
+    pw = proposals[..., 2] - proposals[..., 0] + 1.0
+    ph = proposals[..., 3] - proposals[..., 1] + 1.0
+    gx = (gt[..., 0] + gt[..., 2]) * 0.5
+    gy = (gt[..., 1] + gt[..., 3]) * 0.5
+    gw = gt[..., 2] - gt[..., 0] + 1.0
+    gh = gt[..., 3] - gt[..., 1] + 1.0
+    deltas = torch.stack([(gx - px) / pw, (gy - py) / ph, torch.log(gw / pw), torch.log(gh / ph)], dim=-1)
+    means = deltas.new_tensor(means).unsqueeze(0)
+    stds = deltas.new_tensor(stds).unsqueeze(0)
+    return deltas.sub_(means).div_(stds)
+
+
+def bbox_target(pos_bboxes_list, neg_bboxes_list, pos_gt_bboxes_list, pos_gt_labels_list, cfg, reg_classes=1,
+                target_means=(.0, .0, .0, .0), target_stds=(1.0, 1.0, 1.0, 1.0), concat=True):
+    """Per-image RoI targets, restating mmdet/core/bbox/bbox_target.py:7-63: positives first (their gt label, weight
+    ``cfg.pos_weight`` or 1, encoded box target, box weight 1), negatives after (label 0, weight 1).  This is the
+    producer of the ``labels`` vector the BAGS path consumes (its layout -- positives first in every image's block --
+    is what bench.py's synthetic labels imitate).  ``reg_classes`` is accepted and unused, as in the reference."""
+    pw = cfg['pos_weight'] if isinstance(cfg, dict) else cfg.pos_weight
+    outs = ([], [], [], [])
+    for pos_bboxes, neg_bboxes, pos_gt_bboxes, pos_gt_labels in zip(pos_bboxes_list, neg_bboxes_list,
+                                                                      pos_gt_bboxes_list, pos_gt_labels_list):
+        num_pos, num_neg = pos_bboxes.size(0), neg_bboxes.size(0)
+        n = num_pos + num_neg
+        labels = pos_bboxes.new_zeros(n, dtype=torch.long)
+        label_weights = pos_bboxes.new_zeros(n)
+        bbox_targets = pos_bboxes.new_zeros(n, 4)
+        bbox_weights = pos_bboxes.new_zeros(n, 4)
+        if num_pos > 0:
+            labels[:num_pos] = pos_gt_labels
+            label_weights[:num_pos] = 1.0 if pw <= 0 else pw
+            bbox_targets[:num_pos, :] = bbox2delta(pos_bboxes, pos_gt_bboxes, target_means, target_stds)
+            bbox_weights[:num_pos, :] = 1
+        if num_neg > 0:
+            label_weights[-num_neg:] = 1.0
+        for o, v in zip(outs, (labels, label_weights, bbox_targets, bbox_weights)):
+            o.append(v)
+    if concat:
+        return tuple(torch.cat(o, 0) for o in outs)
+    return outs
+
+
 def delta2bbox(rois, deltas, means=(0, 0, 0, 0), stds=(1, 1, 1, 1), max_shape=None, wh_ratio_clip=16 / 1000):
     """Box decoding used by get_det_bboxes / regress_by_class; same maths as
     mmdet/core/bbox/transforms.py:34-111 (consumer of the path, plain PyTorch)."""
@@ -204,16 +252,13 @@ class BBoxHead(nn.Module):
             nn.init.constant_(self.fc_reg.bias, 0)
 
     def get_target(self, sampling_results, gt_bboxes, gt_labels, rcnn_train_cfg):
-        bbox_target = _mmdet_core('bbox_target')
-        if bbox_target is None:
-            raise NotImplementedError(
-                'get_target needs mmdet.core.bbox_target (the target generator is upstream of the BAGS '
-                'hot path and is not re-implemented here); install mmdetection v1.x to use it')
+        """(labels, label_weights, bbox_targets, bbox_weights) of the sampled RoIs (bbox_head.py:80-96).  Uses
+        mmdet's ``bbox_target`` inside an mmdetection checkout, the restatement above otherwise (identical results)."""
+        fn = _mmdet_core('bbox_target') or bbox_target
         reg_classes = 1 if self.reg_class_agnostic else self.num_classes
-        return bbox_target([r.pos_bboxes for r in sampling_results], [r.neg_bboxes for r in sampling_results],
-                           [r.pos_gt_bboxes for r in sampling_results],
-                           [r.pos_gt_labels for r in sampling_results], rcnn_train_cfg, reg_classes,
-                           target_means=self.target_means, target_stds=self.target_stds)
+        return fn([r.pos_bboxes for r in sampling_results], [r.neg_bboxes for r in sampling_results],
+                  [r.pos_gt_bboxes for r in sampling_results], [r.pos_gt_labels for r in sampling_results],
+                  rcnn_train_cfg, reg_classes, target_means=self.target_means, target_stds=self.target_stds)
 
     def _bbox_loss(self, bbox_pred, labels, bbox_targets, bbox_weights, reduction_override):
         pos_inds = labels > 0

@@ -113,6 +113,26 @@ def load():
     return ns
 
 
+def load_bbox_target():
+    """The reference's own ``bbox_target`` (mmdet/core/bbox/bbox_target.py) and ``bbox2delta`` (transforms.py),
+    executed in place: the producer of the head's ``labels`` / box targets."""
+    load()
+    root = reference_dir()
+    md = os.path.join(root, 'mmdet')
+    import functools
+    if 'mmdet.core.utils' not in sys.modules or not hasattr(sys.modules['mmdet.core.utils'], 'multi_apply'):
+        cu = _shell('mmdet.core.utils', os.path.join(md, 'core', 'utils'))
+
+        def multi_apply(func, *args, **kwargs):   # mmdet/core/utils/misc.py:22-25 (its module imports six / mmcv.im*)
+            pfunc = functools.partial(func, **kwargs) if kwargs else func
+            return tuple(map(list, zip(*map(pfunc, *args))))
+        cu.multi_apply = multi_apply
+    _shell('mmdet.core.bbox', os.path.join(md, 'core', 'bbox'))
+    tr = _exec('mmdet.core.bbox.transforms', os.path.join(md, 'core', 'bbox', 'transforms.py'))
+    bt = _exec('mmdet.core.bbox.bbox_target', os.path.join(md, 'core', 'bbox', 'bbox_target.py'))
+    return bt.bbox_target, tr.bbox2delta
+
+
 def build_reference_head(tables, others_sample_ratio: float = 8.0, fc_out_channels: int = 1024,
                          in_channels: int = 256, roi_feat_size: int = 7, num_fcs: int = 2,
                          reg_class_agnostic: bool = False, tmpdir: Optional[str] = None):

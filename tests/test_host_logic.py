@@ -219,3 +219,30 @@ def test_load_reference_checkpoint_roundtrip(tmp_path):
     bad['module.bbox_head.fc_cls.weight'] = torch.zeros(1231, 32)
     with pytest.raises(ValueError):
         dst.load_reference_checkpoint({'state_dict': bad})
+
+
+def test_get_target_known_values():
+    """bbox_target / bbox2delta restatement on hand-checkable boxes (mmdet/core/bbox/bbox_target.py:36-63,
+    transforms.py:6-31): positives first with their labels, negatives label 0, '+1' box widths."""
+    import math
+    from types import SimpleNamespace
+    import torch
+    from balancedgroupsoftmax_b200.head import bbox2delta, bbox_target
+    p = torch.tensor([[0., 0., 9., 9.]])          # 10 x 10, centre 4.5
+    gt = torch.tensor([[2., 0., 21., 9.]])        # 20 x 10, centre (11.5, 4.5)
+    d = bbox2delta(p, gt, (0, 0, 0, 0), (0.1, 0.1, 0.2, 0.2))
+    assert torch.allclose(d, torch.tensor([[7.0, 0.0, math.log(2.0) / 0.2, 0.0]]), atol=1e-6)
+    neg = torch.tensor([[1., 1., 2., 2.], [3., 3., 4., 4.]])
+    labels, lw, bt, bw = bbox_target([p], [neg], [gt], [torch.tensor([17])], dict(pos_weight=-1),
+                                     target_stds=(0.1, 0.1, 0.2, 0.2))
+    assert labels.tolist() == [17, 0, 0] and labels.dtype == torch.long
+    assert lw.tolist() == [1.0, 1.0, 1.0]
+    assert torch.allclose(bt[0], d[0]) and bt[1:].abs().sum() == 0
+    assert bw.tolist() == [[1, 1, 1, 1], [0, 0, 0, 0], [0, 0, 0, 0]]
+    _, lw2, _, _ = bbox_target([p], [neg], [gt], [torch.tensor([17])], SimpleNamespace(pos_weight=3.0))
+    assert lw2.tolist() == [3.0, 1.0, 1.0]
+    # an image without positives, one without negatives
+    e = torch.zeros(0, 4)
+    labels, lw, bt, bw = bbox_target([e, p], [neg, e], [e, gt], [torch.zeros(0, dtype=torch.long), torch.tensor([5])],
+                                     dict(pos_weight=-1))
+    assert labels.tolist() == [0, 0, 5] and lw.tolist() == [1.0, 1.0, 1.0] and bw[:, 0].tolist() == [0, 0, 1]

@@ -88,3 +88,49 @@ def test_host_mirror_numpy_sampler_is_the_reference_sampler(ref):
     for g in range(1, 5):
         w = mine._sample_others_numpy(mine.label2binlabel[g][labels])
         assert torch.equal(w, ref_w[g])
+
+
+def test_get_target_matches_reference_bbox_target():
+    """The head's standalone target generator against the reference's bbox_target.py / transforms.py run in place."""
+    from types import SimpleNamespace
+    from balancedgroupsoftmax_b200.head import GSBBoxHeadWith0, bbox2delta, bbox_target
+    ref_bbox_target, ref_bbox2delta = ref_shim.load_bbox_target()
+    g = torch.Generator().manual_seed(11)
+
+    def boxes(n):
+        xy = torch.rand(n, 2, generator=g) * 600
+        wh = torch.rand(n, 2, generator=g) * 200 + 1
+        return torch.cat([xy, xy + wh], 1)
+
+    imgs = []
+    for npos, nneg in ((5, 20), (0, 12), (7, 0), (1, 1)):
+        imgs.append(SimpleNamespace(pos_bboxes=boxes(npos), neg_bboxes=boxes(nneg), pos_gt_bboxes=boxes(npos),
+                                    pos_gt_labels=torch.randint(1, 1231, (npos,), generator=g)))
+    means, stds = [0., 0., 0., 0.], [0.1, 0.1, 0.2, 0.2]
+    assert torch.equal(bbox2delta(imgs[0].pos_bboxes, imgs[0].pos_gt_bboxes, means, stds),
+                       ref_bbox2delta(imgs[0].pos_bboxes, imgs[0].pos_gt_bboxes, means, stds))
+    for pos_weight in (-1, 2.5):
+        cfg = ref_shim.AttrDict(pos_weight=pos_weight)
+        args = ([r.pos_bboxes for r in imgs], [r.neg_bboxes for r in imgs], [r.pos_gt_bboxes for r in imgs],
+                [r.pos_gt_labels for r in imgs], cfg)
+        want = ref_bbox_target(*args, reg_classes=1231, target_means=means, target_stds=stds)
+        got = bbox_target(*args, reg_classes=1231, target_means=means, target_stds=stds)
+        for a, b in zip(got, want):
+            assert a.dtype == b.dtype and torch.equal(a, b)
+        # not concatenated
+        want = ref_bbox_target(*args, target_means=means, target_stds=stds, concat=False)
+        got = bbox_target(*args, target_means=means, target_stds=stds, concat=False)
+        for la, lb in zip(got, want):
+            assert len(la) == len(lb) and all(torch.equal(a, b) for a, b in zip(la, lb))
+    # through the head method
+    t = synthetic_tables()
+    head = GSBBoxHeadWith0(num_fcs=1, in_channels=4, fc_out_channels=16, roi_feat_size=1, num_classes=t.num_classes,
+                           target_means=means, target_stds=stds,
+                           gs_config=dict(tables=t, others_sample_ratio=8.0, num_bins=5,
+                                          loss_bin=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0)))
+    cfg = ref_shim.AttrDict(pos_weight=-1)
+    got = head.get_target(imgs, None, None, cfg)
+    want = ref_bbox_target([r.pos_bboxes for r in imgs], [r.neg_bboxes for r in imgs], [r.pos_gt_bboxes for r in imgs],
+                           [r.pos_gt_labels for r in imgs], cfg, 1231, target_means=means, target_stds=stds)
+    assert all(torch.equal(a, b) for a, b in zip(got, want))
+    assert got[0].dtype == torch.long and got[0][:5].tolist() == imgs[0].pos_gt_labels.tolist() and got[0][5:25].sum() == 0
