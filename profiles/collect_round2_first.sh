@@ -1,0 +1,14 @@
+#!/bin/bash
+# First GPU call of the next round (1 GPU, ~3 min): state of the tree + the experiments prepared at the end of round 1.
+#   gpurun --timeout 1200 -- 'bash profiles/collect_round2_first.sh r02_v0'
+tag=${1:-r02_v0}
+out=gpurun_out
+mkdir -p $out
+timeout 600 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $out/${tag}_pytest.log
+timeout 400 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench rc=$?"; cut -c1-400 $out/${tag}_bench.json
+# 1. CTA-pair forward (BAGS_FWD_PAIR=1): parity vs the default fused forward + kernel timing A/B
+timeout 300 python tests/gpu_probe.py --case fwdpair.bf16 > $out/${tag}_fwdpair.log 2>&1; echo "fwdpair rc=$?"; tail -3 $out/${tag}_fwdpair.log | cut -c1-1500
+# 2. whole step with the pair forward
+for v in 0 1 0 1; do echo -n "BAGS_FWD_PAIR=$v "; BAGS_FWD_PAIR=$v timeout 200 python bench.py --profile --steps 480 --warmup 20 2>/dev/null | tail -1; done | tee $out/${tag}_fwdpair_step_ab.log
+# 3. library yardstick: the three plain GEMMs through cuBLAS from a CUDA graph (gpu_probe 'timing': cublas_three_gemms_graph_us)
+timeout 200 python tests/gpu_probe.py --case timing > $out/${tag}_timing.log 2>&1; grep RESULT $out/${tag}_timing.log | cut -c1-900
