@@ -611,7 +611,9 @@ static int launch_bwd_merged(const void* dz, long long ldd, const void* x, long 
   if ((rc = make_tmap(&t_wT, wb, dtype, p0.Kf, p0.C, ldw, Cfg::SLAB, Cfg::BLOCK_K, TF32))) return rc;
   BwdFusedParams p = p0;
   p.timing = g_timing ? g_timing + 2048 * 8 : nullptr;   // rows [2048, ..): the forward of the same step uses [0, 2048)
-  auto kernel = bags_bwd_fused_kernel<TF32, MT>;
+  // BAGS_BWD_TICKET=1 (experimental): preparation jobs handed out by an atomic ticket (no co-residency requirement)
+  auto kernel = (p.prep_jobs > 0 && env_int("BAGS_BWD_TICKET", 0)) ? bags_bwd_fused_kernel<TF32, MT, true>
+                                                                  : bags_bwd_fused_kernel<TF32, MT, false>;
   BAGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int units = p.dw_units + p.dx_units;
   const int grid = units < di.num_sms ? units : di.num_sms;

@@ -68,7 +68,10 @@ struct BwdCfg {
   static_assert(SMEM_BYTES <= 232448, "exceeds shared memory");
 };
 
-template <bool TF32, int MT>
+// TICKET = false: preparation job j runs on CTA j % gridDim.x (all CTAs must be resident together before the grid
+// counter reaches its target).  TICKET = true (BAGS_BWD_TICKET=1, experimental): jobs are handed out through an atomic
+// ticket and counted one by one, so whichever CTAs are resident finish them all -- no co-residency requirement.
+template <bool TF32, int MT, bool TICKET = false>
 __global__ void __launch_bounds__(64 + 32 * 8, 1)
 bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as MN-major A of dW  (box SLAB x BLOCK_K)
                       const __grid_constant__ CUtensorMap tmap_xT,    // x  as MN-major B of dW  (box SLAB x BLOCK_K)
@@ -155,7 +158,7 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
         const Unit un = decode(u);
         const int m0 = un.m_tile * BLOCK_M, n0 = un.n_tile * BLOCK_N;
         if (!un.is_dw && !waited && !plain_w) {   // W' is written by bwd_prep / by the preparation jobs of all CTAs
-          if (inkernel) { wait_grid_jobs(p.sync, gridDim.x); asm volatile("fence.proxy.async;" ::: "memory"); }
+          if (inkernel) { wait_grid_jobs(p.sync, TICKET ? static_cast<unsigned int>(p.prep_jobs) : gridDim.x); asm volatile("fence.proxy.async;" ::: "memory"); }
           else pdl_wait();
           waited = true;
         }
@@ -261,6 +264,20 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
       const int tid = static_cast<int>(threadIdx.x) - 64;
       float (*s_part)[64] = reinterpret_cast<float (*)[64]>(smem_epi);
       pdl_wait();   // dW / W' may still be in use by whatever ran before the forward kernel; dz comes from it
+      if constexpr (TICKET) {
+        __shared__ int s_job;
+        for (;;) {
+          if (tid == 0) s_job = static_cast<int>(atomicAdd(p.sync + 2, 1u));
+          asm volatile("bar.sync 5, 256;" ::: "memory");
+          const int j = s_job;
+          if (j >= p.prep_jobs) break;
+          bwd_prep_job<TF32, 5>(p.prep, j, tid, s_part);
+          asm volatile("fence.proxy.async;" ::: "memory");   // W' is read through TMA (async proxy) by other CTAs
+          __threadfence();
+          asm volatile("bar.sync 5, 256;" ::: "memory");     // the job's writes are fenced; s_job / s_part may be reused
+          if (tid == 0) atomicAdd(p.sync, 1u);               // one count per finished job
+        }
+      } else {
       for (int j = blockIdx.x; j < p.prep_jobs; j += gridDim.x) {
         bwd_prep_job<TF32, 5>(p.prep, j, tid, s_part);
         asm volatile("bar.sync 5, 256;" ::: "memory");   // s_part is reused by the next job
@@ -269,6 +286,7 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
       __threadfence();
       asm volatile("bar.sync 5, 256;" ::: "memory");
       if (tid == 0) atomicAdd(p.sync, 1u);
+      }
     }
     for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++local) {
       const Unit un = decode(u);
@@ -284,7 +302,7 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
       float scale = dx_scale;
       if (un.is_dw) {
         if (!waited) {   // dW was zeroed / column-sum partials were made by bwd_prep or by every CTA's jobs
-          if (inkernel) { if (lane == 0) wait_grid_jobs(p.sync, gridDim.x); __syncwarp(); __threadfence(); }
+          if (inkernel) { if (lane == 0) wait_grid_jobs(p.sync, TICKET ? static_cast<unsigned int>(p.prep_jobs) : gridDim.x); __syncwarp(); __threadfence(); }
           else pdl_wait();
           waited = true;
         }
@@ -381,7 +399,7 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
   }
   if (threadIdx.x == 0 && p.prep_jobs > 0) {
     // the last CTA to get here re-arms the counters for the next launch (nobody is waiting on them any more)
-    if (atomicAdd(p.sync + 1, 1u) == gridDim.x - 1) { p.sync[0] = 0u; p.sync[1] = 0u; __threadfence(); }
+    if (atomicAdd(p.sync + 1, 1u) == gridDim.x - 1) { p.sync[0] = 0u; p.sync[1] = 0u; if (TICKET) p.sync[2] = 0u; __threadfence(); }
   }
   if (threadIdx.x == 0) stamp(p.timing, 6);
 }

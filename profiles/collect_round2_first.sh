@@ -12,3 +12,6 @@ timeout 300 python tests/gpu_probe.py --case fwdpair.bf16 > $out/${tag}_fwdpair.
 for v in 0 1 0 1; do echo -n "BAGS_FWD_PAIR=$v "; BAGS_FWD_PAIR=$v timeout 200 python bench.py --profile --steps 480 --warmup 20 2>/dev/null | tail -1; done | tee $out/${tag}_fwdpair_step_ab.log
 # 3. library yardstick: the three plain GEMMs through cuBLAS from a CUDA graph (gpu_probe 'timing': cublas_three_gemms_graph_us)
 timeout 200 python tests/gpu_probe.py --case timing > $out/${tag}_timing.log 2>&1; grep RESULT $out/${tag}_timing.log | cut -c1-900
+# 4. ticket-based preparation jobs in the merged backward (BAGS_BWD_TICKET=1): parity suite under the flag + step A/B
+BAGS_BWD_TICKET=1 timeout 600 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest_ticket.log 2>&1; echo "pytest (ticket) rc=$?"; tail -2 $out/${tag}_pytest_ticket.log
+for v in 0 1 0 1; do echo -n "BAGS_BWD_TICKET=$v "; BAGS_BWD_TICKET=$v timeout 200 python bench.py --profile --steps 480 --warmup 20 2>/dev/null | tail -1; done | tee $out/${tag}_ticket_step_ab.log
