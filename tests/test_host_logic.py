@@ -246,3 +246,15 @@ def test_get_target_known_values():
     labels, lw, bt, bw = bbox_target([e, p], [neg, e], [e, gt], [torch.zeros(0, dtype=torch.long), torch.tensor([5])],
                                      dict(pos_weight=-1))
     assert labels.tolist() == [0, 0, 5] and lw.tolist() == [1.0, 1.0, 1.0] and bw[:, 0].tolist() == [0, 0, 1]
+
+
+def test_graphed_step_refuses_cpu_parameters():
+    """No CPU fallback for the graph-captured step either."""
+    import pytest
+    import torch
+    from balancedgroupsoftmax_b200._native import BagsNativeError
+    from balancedgroupsoftmax_b200.api import GraphedHeadStep
+    from balancedgroupsoftmax_b200.tables import synthetic_tables
+    w = torch.nn.Parameter(torch.zeros(1236, 64))
+    with pytest.raises(BagsNativeError):
+        GraphedHeadStep(w, None, synthetic_tables(), 32)
