@@ -15,3 +15,6 @@ timeout 200 python tests/gpu_probe.py --case timing > $out/${tag}_timing.log 2>&
 # 4. ticket-based preparation jobs in the merged backward (BAGS_BWD_TICKET=1): parity suite under the flag + step A/B
 BAGS_BWD_TICKET=1 timeout 600 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest_ticket.log 2>&1; echo "pytest (ticket) rc=$?"; tail -2 $out/${tag}_pytest_ticket.log
 for v in 0 1 0 1; do echo -n "BAGS_BWD_TICKET=$v "; BAGS_BWD_TICKET=$v timeout 200 python bench.py --profile --steps 480 --warmup 20 2>/dev/null | tail -1; done | tee $out/${tag}_ticket_step_ab.log
+# 5. detector harness: frozen torchvision trunk + BAGS head(s), synthetic 1333x800 images
+timeout 300 python tools/bench_detector.py --stages 1 --steps 10 --warmup 3 > $out/${tag}_detector_s1.json 2> $out/${tag}_detector_s1.err; echo "detector s1 rc=$?"; cat $out/${tag}_detector_s1.json; tail -3 $out/${tag}_detector_s1.err
+timeout 300 python tools/bench_detector.py --stages 3 --steps 10 --warmup 3 > $out/${tag}_detector_s3.json 2> $out/${tag}_detector_s3.err; echo "detector s3 rc=$?"; cat $out/${tag}_detector_s3.json; tail -3 $out/${tag}_detector_s3.err
