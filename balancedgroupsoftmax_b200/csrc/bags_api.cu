@@ -18,6 +18,7 @@
 #include "bags_bwd_fused.cuh"
 #include "bags_kernels.cuh"
 #include "bags_allreduce.cuh"
+#include "bags_nms.cuh"
 
 using namespace bags;
 
@@ -937,6 +938,27 @@ extern "C" int bags_grad_allreduce(void* const* peer_bufs_host, void* mc_buf, lo
   else if (mm)           BAGS_CUDA(launch_pdl(bags_grad_allreduce_kernel<true, false>, grid, block, 0, stream, p));
   else if (epoch)        BAGS_CUDA(launch_pdl(bags_grad_allreduce_kernel<false, true>, grid, block, 0, stream, p));
   else                   BAGS_CUDA(launch_pdl(bags_grad_allreduce_kernel<false, false>, grid, block, 0, stream, p));
+  return BAGS_OK;
+}
+
+// ----------------------------------------------------------------------------
+// class-aware batched NMS (experimental; see bags_nms.cuh)
+// ----------------------------------------------------------------------------
+extern "C" int bags_class_nms(const float* boxes, const int32_t* seg_off, int num_segments, int max_segment,
+                              float iou_thr, uint8_t* keep, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BAGS_REQUIRE(num_segments >= 0 && max_segment >= 0, "bags_class_nms: bad sizes");
+  if (num_segments == 0 || max_segment == 0) return BAGS_OK;
+  BAGS_REQUIRE(boxes && seg_off && keep, "bags_class_nms: NULL argument");
+  BAGS_REQUIRE((reinterpret_cast<uintptr_t>(boxes) & 15) == 0, "bags_class_nms: boxes must be 16-byte aligned");
+  BAGS_REQUIRE(max_segment <= kNmsMaxSeg, "bags_class_nms: a class holds %d candidates, more than the %d one CTA handles",
+               max_segment, kNmsMaxSeg);
+  const int words = (max_segment + 31) / 32;
+  const size_t smem = static_cast<size_t>((max_segment + 1) & ~1) * sizeof(float4) +
+                      static_cast<size_t>(max_segment) * words * sizeof(uint32_t);
+  BAGS_CUDA(cudaFuncSetAttribute(class_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  class_nms_kernel<<<num_segments, kNmsThreads, smem, stream>>>(reinterpret_cast<const float4*>(boxes), seg_off, iou_thr, keep);
+  BAGS_CUDA(cudaGetLastError());
   return BAGS_OK;
 }
 

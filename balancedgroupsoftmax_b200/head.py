@@ -599,8 +599,15 @@ class GSBBoxHeadWith0(SharedFCBBoxHead):
             return bboxes, scores
         multiclass_nms = _mmdet_core('multiclass_nms')
         if multiclass_nms is None:
+            if os.environ.get('BAGS_NMS_NATIVE') == '1':    # experimental one-launch class-aware NMS (ops.multiclass_nms)
+                nms_cfg = _cfg_get(cfg, 'nms')
+                if _cfg_get(nms_cfg, 'type', 'nms') != 'nms':
+                    raise NotImplementedError('only hard NMS is implemented natively (got %r)' % _cfg_get(nms_cfg, 'type'))
+                return ops.multiclass_nms(bboxes, scores, float(_cfg_get(cfg, 'score_thr')),
+                                          float(_cfg_get(nms_cfg, 'iou_thr')), int(_cfg_get(cfg, 'max_per_img')))
             raise NotImplementedError('multiclass_nms is downstream of the BAGS path (SURVEY.md §8f-2); '
-                                      'call with cfg=None or install mmdetection v1.x')
+                                      'install mmdetection v1.x, or set BAGS_NMS_NATIVE=1 for the experimental '
+                                      'one-launch class-aware NMS (ops.multiclass_nms)')
         return multiclass_nms(bboxes, scores, cfg.score_thr, cfg.nms, cfg.max_per_img)
 
 

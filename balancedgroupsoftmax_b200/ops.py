@@ -280,6 +280,47 @@ def merge_scores(logits: torch.Tensor, dt: DeviceTables) -> torch.Tensor:
     return scores
 
 
+def multiclass_nms(multi_bboxes: torch.Tensor, multi_scores: torch.Tensor, score_thr: float, iou_thr: float,
+                   max_num: int = -1) -> Tuple[torch.Tensor, torch.Tensor]:
+    """EXPERIMENTAL (bags_class_nms has not run on a GPU yet).  mmdet/core/post_processing/bbox_nms.py:6-66 with the
+    per-class Python loop replaced by ONE launch: candidates (score > score_thr, background column ignored) are sorted
+    by (class, score descending) with torch, every class segment is suppressed by its own CTA, then the reference's
+    top-``max_num`` rule is applied.  Returns (dets [k,5], labels [k] 0-based)."""
+    _require_cuda(multi_bboxes, multi_scores)
+    n, num_classes = multi_scores.shape
+    dev = multi_scores.device
+    fg = multi_scores[:, 1:]
+    cand = torch.nonzero(fg > score_thr, as_tuple=False)          # host sync: the output size is data dependent
+    if cand.shape[0] == 0:
+        return multi_bboxes.new_zeros((0, 5)), multi_bboxes.new_zeros((0,), dtype=torch.long)
+    rows, cls = cand[:, 0], cand[:, 1]
+    sc = fg[rows, cls]
+    by_score = torch.argsort(sc, descending=True, stable=True)
+    by_class = torch.argsort(cls[by_score], stable=True)          # stable: score order survives inside a class
+    idx = by_score[by_class]
+    rows, cls, sc = rows[idx], cls[idx], sc[idx]
+    if multi_bboxes.shape[1] == 4:
+        boxes = multi_bboxes[rows]
+    else:
+        boxes = multi_bboxes.view(n, -1, 4)[rows, cls + 1]
+    boxes = boxes.float().contiguous()
+    counts = torch.bincount(cls, minlength=num_classes - 1)
+    seg_off = torch.zeros(num_classes, dtype=torch.int32, device=dev)
+    seg_off[1:] = torch.cumsum(counts, 0).to(torch.int32)
+    max_seg = int(counts.max().item())
+    keep = torch.empty(boxes.shape[0], dtype=torch.uint8, device=dev)
+    nat.check(nat.lib().bags_class_nms(boxes.data_ptr(), seg_off.data_ptr(), num_classes - 1, max_seg, float(iou_thr),
+                                       keep.data_ptr(), _stream_ptr(dev)), 'bags_class_nms')
+    k = keep.bool()
+    dets = torch.cat([boxes[k], sc[k].float()[:, None]], 1)
+    labels = cls[k]
+    if dets.shape[0] > max_num:          # (as in the reference, max_num = -1 drops the lowest-scored detection)
+        _, inds = dets[:, -1].sort(descending=True)
+        inds = inds[:max_num]
+        dets, labels = dets[inds], labels[inds]
+    return dets, labels
+
+
 def gemm_probe(a, a_mn: bool, b, b_mn: bool, M: int, N: int, K: int, block_n: int = 256, splits: int = 1,
                epi: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Test hook for one tcgen05 GEMM (see bags_gemm_probe)."""

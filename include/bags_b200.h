@@ -163,6 +163,14 @@ long long bags_grad_allreduce_status_offset(int world);
 int bags_grad_allreduce(void* const* peer_bufs_host, void* mc_buf, long long flag_off_bytes, long long count,
                         int rank, int world, float scale, int max_blocks, void* stream);
 
+/* EXPERIMENTAL (not yet run on a GPU): per-class greedy NMS of candidates sorted by (class, score descending), the
+ * test-time consumer of bags_merge_scores -- one launch instead of the reference's Python loop over 1230 classes
+ * (mmdet/core/post_processing/bbox_nms.py:34-54, IoU convention of mmdet/ops/nms/src/nms_kernel.cu:13-21).
+ * boxes [M,4] fp32; seg_off [num_segments+1] int32 (device); max_segment = longest segment (<= 1024);
+ * keep [M] uint8 out (1 = kept).  A box is suppressed when IoU("+1" widths) with a kept higher-score box > iou_thr. */
+int bags_class_nms(const float* boxes, const int32_t* seg_off, int num_segments, int max_segment, float iou_thr,
+                   uint8_t* keep, void* stream);
+
 /* test hook: launch `blocks` x `threads` threads that wait `micros` microseconds and exit */
 int bags_debug_spin(int blocks, int threads, int micros, void* stream);
 

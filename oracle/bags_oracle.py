@@ -188,3 +188,58 @@ def head_step(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, labels:
     total = sum(losses.values())
     total.backward()
     return losses, w.grad, b.grad, (x.grad if need_dx else None)
+
+
+# ---------------------------------------------------------------------------------------------------
+# test-time consumer of the merged scores: per-class NMS
+# ---------------------------------------------------------------------------------------------------
+def nms_plus1(dets: torch.Tensor, iou_thr: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Greedy NMS with the reference op's conventions (mmdet/ops/nms/src/nms_kernel.cu:13-21,60,76-78): boxes visited
+    in descending score order, IoU with "+1" widths, a box is dropped when IoU with a kept box > iou_thr.
+    dets [n,5] (x1,y1,x2,y2,score) -> (kept dets in score order, their indices)."""
+    if dets.shape[0] == 0:
+        return dets, dets.new_zeros(0, dtype=torch.long)
+    d = dets.detach().double().cpu().numpy()
+    order = np.argsort(-d[:, 4], kind='stable')
+    x1, y1, x2, y2 = d[:, 0], d[:, 1], d[:, 2], d[:, 3]
+    area = (x2 - x1 + 1) * (y2 - y1 + 1)
+    removed = np.zeros(len(d), dtype=bool)
+    keep = []
+    for a, i in enumerate(order):
+        if removed[i]:
+            continue
+        keep.append(i)
+        rest = order[a + 1:]
+        w = np.maximum(np.minimum(x2[i], x2[rest]) - np.maximum(x1[i], x1[rest]) + 1, 0)
+        h = np.maximum(np.minimum(y2[i], y2[rest]) - np.maximum(y1[i], y1[rest]) + 1, 0)
+        inter = w * h
+        iou = inter / (area[i] + area[rest] - inter)
+        removed[rest[iou.astype(np.float32) > np.float32(iou_thr)]] = True
+    inds = torch.as_tensor(np.array(keep, dtype=np.int64))
+    return dets[inds], inds
+
+
+def multiclass_nms(multi_bboxes: torch.Tensor, multi_scores: torch.Tensor, score_thr: float, iou_thr: float,
+                   max_num: int = -1) -> Tuple[torch.Tensor, torch.Tensor]:
+    """mmdet/core/post_processing/bbox_nms.py:6-66 restated (nms_cfg = dict(type='nms', iou_thr=...)): column 0 of the
+    scores is background and ignored; per class keep score > score_thr, NMS, label = class - 1; concatenate in class
+    order; ``if n > max_num`` sort by score and keep ``[:max_num]`` -- including the reference's behaviour for
+    max_num = -1 (n > -1 always holds, so the lowest-scored detection is dropped)."""
+    num_classes = multi_scores.shape[1]
+    bboxes, labels = [], []
+    for i in range(1, num_classes):
+        cls_inds = multi_scores[:, i] > score_thr
+        if not cls_inds.any():
+            continue
+        _b = multi_bboxes[cls_inds, :] if multi_bboxes.shape[1] == 4 else multi_bboxes[cls_inds, i * 4:(i + 1) * 4]
+        cls_dets, _ = nms_plus1(torch.cat([_b, multi_scores[cls_inds, i][:, None]], 1), iou_thr)
+        bboxes.append(cls_dets)
+        labels.append(torch.full((cls_dets.shape[0],), i - 1, dtype=torch.long))
+    if not bboxes:
+        return multi_bboxes.new_zeros((0, 5)), multi_bboxes.new_zeros((0,), dtype=torch.long)
+    bboxes, labels = torch.cat(bboxes), torch.cat(labels)
+    if bboxes.shape[0] > max_num:
+        _, inds = bboxes[:, -1].sort(descending=True)
+        inds = inds[:max_num]
+        bboxes, labels = bboxes[inds], labels[inds]
+    return bboxes, labels

@@ -133,6 +133,23 @@ def load_bbox_target():
     return bt.bbox_target, tr.bbox2delta
 
 
+def load_multiclass_nms(nms_op):
+    """The reference's own ``multiclass_nms`` loop (mmdet/core/post_processing/bbox_nms.py) executed in place, with
+    ``nms_op(dets, iou_thr) -> (dets, inds)`` standing in for its compiled NMS extension (mmdet/ops/nms)."""
+    load()
+    root = reference_dir()
+    md = os.path.join(root, 'mmdet')
+    _shell('mmdet.ops', os.path.join(md, 'ops'))
+    nms_pkg = _shell('mmdet.ops.nms', os.path.join(md, 'ops', 'nms'))
+    wrapper = types.ModuleType('mmdet.ops.nms.nms_wrapper')
+    wrapper.nms = nms_op
+    sys.modules['mmdet.ops.nms.nms_wrapper'] = wrapper
+    nms_pkg.nms_wrapper = wrapper
+    _shell('mmdet.core.post_processing', os.path.join(md, 'core', 'post_processing'))
+    mod = _exec('mmdet.core.post_processing.bbox_nms', os.path.join(md, 'core', 'post_processing', 'bbox_nms.py'))
+    return mod.multiclass_nms
+
+
 def build_reference_head(tables, others_sample_ratio: float = 8.0, fc_out_channels: int = 1024,
                          in_channels: int = 256, roi_feat_size: int = 7, num_fcs: int = 2,
                          reg_class_agnostic: bool = False, tmpdir: Optional[str] = None):

@@ -18,3 +18,5 @@ for v in 0 1 0 1; do echo -n "BAGS_BWD_TICKET=$v "; BAGS_BWD_TICKET=$v timeout 2
 # 5. detector harness: frozen torchvision trunk + BAGS head(s), synthetic 1333x800 images
 timeout 300 python tools/bench_detector.py --stages 1 --steps 10 --warmup 3 > $out/${tag}_detector_s1.json 2> $out/${tag}_detector_s1.err; echo "detector s1 rc=$?"; cat $out/${tag}_detector_s1.json; tail -3 $out/${tag}_detector_s1.err
 timeout 300 python tools/bench_detector.py --stages 3 --steps 10 --warmup 3 > $out/${tag}_detector_s3.json 2> $out/${tag}_detector_s3.err; echo "detector s3 rc=$?"; cat $out/${tag}_detector_s3.json; tail -3 $out/${tag}_detector_s3.err
+# 6. experimental one-launch class-aware NMS against the oracle
+BAGS_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_nms.py -q -m gpu > $out/${tag}_pytest_nms.log 2>&1; echo "nms rc=$?"; tail -3 $out/${tag}_pytest_nms.log

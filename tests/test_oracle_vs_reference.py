@@ -134,3 +134,21 @@ def test_get_target_matches_reference_bbox_target():
                            [r.pos_gt_labels for r in imgs], cfg, 1231, target_means=means, target_stds=stds)
     assert all(torch.equal(a, b) for a, b in zip(got, want))
     assert got[0].dtype == torch.long and got[0][:5].tolist() == imgs[0].pos_gt_labels.tolist() and got[0][5:25].sum() == 0
+
+
+def test_multiclass_nms_oracle_matches_reference_loop():
+    """The oracle's multiclass_nms against the reference's bbox_nms.py run in place (its compiled NMS op replaced by
+    the oracle's greedy "+1" NMS): thresholds, labels, class order and the top-k rule."""
+    ref_mc_nms = ref_shim.load_multiclass_nms(O.nms_plus1)
+    g = torch.Generator().manual_seed(5)
+    n, classes = 60, 9
+    xy = torch.rand(n, 2, generator=g) * 80
+    wh = torch.rand(n, 2, generator=g) * 40 + 2
+    boxes4 = torch.cat([xy, xy + wh], 1)
+    boxes_pc = (boxes4[:, None, :] + torch.rand(n, classes, 4, generator=g)).reshape(n, classes * 4)
+    scores = torch.rand(n, classes, generator=g) ** 3
+    for mb in (boxes4, boxes_pc):
+        for thr, iou, k in ((0.05, 0.5, 20), (0.0, 0.3, 1000), (0.9999, 0.5, 10), (0.2, 0.5, -1)):
+            want = ref_mc_nms(mb, scores.clone(), thr, dict(type='nms', iou_thr=iou), k)
+            got = O.multiclass_nms(mb, scores.clone(), thr, iou, k)
+            assert got[0].shape == want[0].shape and torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
