@@ -29,6 +29,7 @@ def main() -> int:
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--no-amp', dest='amp', action='store_false', help='shared FCs / fc_reg in fp32 instead of bf16 autocast')
     args = ap.parse_args()
 
     import torch
@@ -48,7 +49,7 @@ def main() -> int:
         dist.init_process_group('nccl', device_id=dev)
     tables = synthetic_tables(1231, seed=0)
     weights = (1.0,) if args.stages == 1 else (1.0, 0.5, 0.25)
-    model = BagsDetectorHarness(tables, num_stages=args.stages, stage_loss_weights=weights, compute_dtype=args.dtype,
+    model = BagsDetectorHarness(tables, num_stages=args.stages, stage_loss_weights=weights, compute_dtype=args.dtype, amp=args.amp,
                                 min_size=args.height, max_size=args.width).to(dev)
     model.train()
     params = model.head_parameters()
@@ -69,7 +70,7 @@ def main() -> int:
         rois = proposals
         for si, head in enumerate(model.heads):
             x, sampling, boxes = model.head_inputs(feats, rois, gbs, gl, sizes, si)
-            cls_score, bbox_pred = head(x)
+            cls_score, bbox_pred = model.run_head(head, x)
             targets = head.get_target(sampling, gbs, gl, model.rcnn_cfg)
             for k, v in head.loss(cls_score, bbox_pred, *targets).items():
                 losses['s%d.%s' % (si, k)] = v * weights[si]
@@ -112,7 +113,7 @@ def main() -> int:
                       % (args.width, args.height, args.stages),
             'value': world * args.imgs_per_gpu / (ms * 1e-3), 'unit': 'img/s', 'n_gpus': world, 'ms_per_step': ms,
             'head_ms_per_step': head, 'head_share': head / ms, 'steps': args.steps, 'warmup': args.warmup,
-            'dtype': args.dtype, 'data': 'synthetic', 'loss': float(last.detach().float().item()),
+            'dtype': args.dtype, 'amp_trunk_fcs': bool(args.amp), 'data': 'synthetic', 'loss': float(last.detach().float().item()),
             'config': {'imgs_per_gpu': args.imgs_per_gpu, 'rois_per_image': 512, 'stages': args.stages,
                        'trunk': 'torchvision fasterrcnn_resnet50_fpn (frozen, random init)'}}), flush=True)
     if world > 1:
