@@ -352,7 +352,7 @@ static int launch_group_ce(const float* logits, long long ldz, const int64_t* la
                            const int32_t* label2bin, const GroupTable& gt, const uint8_t* wmask,
                            const float* avg, int N, int C, int classes, float* loss, float* lse,
                            void* dz, long long ldd, int dz_dtype, float* colsum, void* workspace,
-                           int num_sms, cudaStream_t stream) {
+                           int num_sms, cudaStream_t stream, bool wf = false) {
   const int smem = 8 * NV * 128 * (int)sizeof(float);
   // persistent CTAs (2 per SM: 126 regs x 256 threads): every CTA walks several row octets so the
   // bias-gradient column sums are reduced in registers/smem and hit global atomics once per CTA
@@ -366,7 +366,12 @@ static int launch_group_ce(const float* logits, long long ldz, const int64_t* la
   unsigned int* counter = reinterpret_cast<unsigned int*>(workspace);
   float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
   const long long* lab = reinterpret_cast<const long long*>(labels);
-  if (dz_dtype == BAGS_DTYPE_F32) {
+  if (wf) {   // fp32 per-RoI weights (reweight head variant)
+    auto k = (dz_dtype == BAGS_DTYPE_F32) ? group_ce_kernel<NV, true, true> : group_ce_kernel<NV, false, true>;
+    BAGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k<<<grid, 256, smem, stream>>>(logits, ldz, lab, label2bin, classes, gt, wmask, avg, N, C, loss, lse, dz, ldd,
+                                   colsum, part, counter);
+  } else if (dz_dtype == BAGS_DTYPE_F32) {
     auto k = group_ce_kernel<NV, true>;
     BAGS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     k<<<grid, 256, smem, stream>>>(logits, ldz, lab, label2bin, classes, gt, wmask, avg, N, C, loss, lse, dz, ldd,
@@ -381,12 +386,12 @@ static int launch_group_ce(const float* logits, long long ldz, const int64_t* la
   return BAGS_OK;
 }
 
-extern "C" int bags_group_ce(const float* logits, long long ldz, const int64_t* labels,
-                             const int32_t* label2bin, const int32_t* slices_host,
-                             const uint8_t* wmask, const float* avg, int N, int C, int G,
-                             int classes, float* loss, float* lse, void* dz, long long ldd,
-                             int dz_dtype, float* colsum, void* workspace, size_t workspace_bytes,
-                             void* stream_) {
+static int group_ce_impl(const float* logits, long long ldz, const int64_t* labels,
+                         const int32_t* label2bin, const int32_t* slices_host,
+                         const uint8_t* wmask, bool wf, const float* avg, int N, int C, int G,
+                         int classes, float* loss, float* lse, void* dz, long long ldd,
+                         int dz_dtype, float* colsum, void* workspace, size_t workspace_bytes,
+                         void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   BAGS_REQUIRE(label2bin && loss && workspace && (N == 0 || (logits && labels)), "bags_group_ce: NULL argument");
   BAGS_REQUIRE(workspace_bytes >= bags_workspace_bytes(), "bags_group_ce: workspace too small (%zu < %zu)",
@@ -414,12 +419,33 @@ extern "C" int bags_group_ce(const float* logits, long long ldz, const int64_t* 
   const int nv = (C / 4 + 31) / 32;
   if (nv <= 10)
     return launch_group_ce<10>(logits, ldz, labels, label2bin, gt, wmask, avg, N, C, classes, loss, lse, dz, ldd,
-                               dz_dtype, colsum, workspace, di.num_sms, stream);
+                               dz_dtype, colsum, workspace, di.num_sms, stream, wf);
   if (nv <= 16)
     return launch_group_ce<16>(logits, ldz, labels, label2bin, gt, wmask, avg, N, C, classes, loss, lse, dz, ldd,
-                               dz_dtype, colsum, workspace, di.num_sms, stream);
+                               dz_dtype, colsum, workspace, di.num_sms, stream, wf);
   return launch_group_ce<32>(logits, ldz, labels, label2bin, gt, wmask, avg, N, C, classes, loss, lse, dz, ldd,
-                             dz_dtype, colsum, workspace, di.num_sms, stream);
+                             dz_dtype, colsum, workspace, di.num_sms, stream, wf);
+}
+
+extern "C" int bags_group_ce(const float* logits, long long ldz, const int64_t* labels,
+                             const int32_t* label2bin, const int32_t* slices_host,
+                             const uint8_t* wmask, const float* avg, int N, int C, int G,
+                             int classes, float* loss, float* lse, void* dz, long long ldd,
+                             int dz_dtype, float* colsum, void* workspace, size_t workspace_bytes,
+                             void* stream_) {
+  return group_ce_impl(logits, ldz, labels, label2bin, slices_host, wmask, false, avg, N, C, G, classes, loss, lse, dz,
+                       ldd, dz_dtype, colsum, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int bags_group_ce_w(const float* logits, long long ldz, const int64_t* labels,
+                               const int32_t* label2bin, const int32_t* slices_host,
+                               const float* wfloat, const float* avg, int N, int C, int G,
+                               int classes, float* loss, float* lse, void* dz, long long ldd,
+                               int dz_dtype, float* colsum, void* workspace, size_t workspace_bytes,
+                               void* stream_) {
+  return group_ce_impl(logits, ldz, labels, label2bin, slices_host, reinterpret_cast<const uint8_t*>(wfloat),
+                       wfloat != nullptr, avg, N, C, G, classes, loss, lse, dz, ldd, dz_dtype, colsum, workspace,
+                       workspace_bytes, stream_);
 }
 
 
@@ -454,7 +480,7 @@ extern "C" int bags_fused_eligible(const int32_t* slices_host, int G, int C) {
 
 template <bool TF32>
 static int launch_fused_fwd(const void* x, long long ldx, const void* w, long long ldw, const FusedFwdParams& p0,
-                            void* dz, long long ldd, const DeviceInfo& di, cudaStream_t stream) {
+                            void* dz, long long ldd, const DeviceInfo& di, cudaStream_t stream, bool wf = false) {
   using Cfg = FusedCfg<TF32>;
   const int dtype = TF32 ? BAGS_DTYPE_F32 : BAGS_DTYPE_BF16;
   CUtensorMap tx, tw;
@@ -471,7 +497,7 @@ static int launch_fused_fwd(const void* x, long long ldx, const void* w, long lo
   p.want_dz = dz != nullptr ? 1 : 0;
   p.timing = g_timing;
   p.dbg = g_timing ? g_dbg : 0;
-  auto kernel = bags_fwd_fused_kernel<TF32>;
+  auto kernel = wf ? bags_fwd_fused_kernel<TF32, true> : bags_fwd_fused_kernel<TF32, false>;
   BAGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int grid = Cfg::CLUSTER * ((p.N + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M);
   (void)di;
@@ -528,9 +554,9 @@ static int launch_fused_fwd_pair(const void* x, long long ldx, const void* w, lo
   return BAGS_OK;
 }
 
-extern "C" int bags_fwd(const void* x, long long ldx, const void* w, long long ldw,
-                        const float* bias, const int64_t* labels, const int32_t* label2bin,
-                        const int32_t* slices_host, const uint8_t* wmask, const float* avg, int N,
+static int fwd_impl(const void* x, long long ldx, const void* w, long long ldw,
+                    const float* bias, const int64_t* labels, const int32_t* label2bin,
+                    const int32_t* slices_host, const uint8_t* wmask, bool wf, const float* avg, int N,
                         int K, int C, int G, int classes, int dtype, float* logits, long long ldz,
                         float* loss, float* lse, void* dz, long long ldd, float* colsum,
                         int colsum_tiles, void* workspace, size_t workspace_bytes, void* stream_) {
@@ -543,7 +569,7 @@ extern "C" int bags_fwd(const void* x, long long ldx, const void* w, long long l
     if (colsum != nullptr && colsum_tiles > 1)
       BAGS_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * C * colsum_tiles, static_cast<cudaStream_t>(stream_)));
     if (int rc = bags_linear_fwd(x, ldx, w, ldw, bias, logits, ldz, N, K, C, dtype, stream_)) return rc;
-    return bags_group_ce(logits, ldz, labels, label2bin, slices_host, wmask, avg, N, C, G, classes, loss,
+    return group_ce_impl(logits, ldz, labels, label2bin, slices_host, wmask, wf, avg, N, C, G, classes, loss,
                          lse, dz, ldd, dtype, colsum, workspace, workspace_bytes, stream_);
   }
   // fused path: logits stay in TMEM
@@ -576,11 +602,44 @@ extern "C" int bags_fwd(const void* x, long long ldx, const void* w, long long l
   p.counter = reinterpret_cast<unsigned int*>(workspace);
   p.part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
   if (N == 0) dz = nullptr;
-  if (env_int("BAGS_FWD_PAIR", 0))
+  if (!wf && env_int("BAGS_FWD_PAIR", 0))
     return dtype == BAGS_DTYPE_BF16 ? launch_fused_fwd_pair<false>(x, ldx, w, ldw, p, dz, ldd, stream)
                                     : launch_fused_fwd_pair<true>(x, ldx, w, ldw, p, dz, ldd, stream);
-  return dtype == BAGS_DTYPE_BF16 ? launch_fused_fwd<false>(x, ldx, w, ldw, p, dz, ldd, di, stream)
-                                  : launch_fused_fwd<true>(x, ldx, w, ldw, p, dz, ldd, di, stream);
+  return dtype == BAGS_DTYPE_BF16 ? launch_fused_fwd<false>(x, ldx, w, ldw, p, dz, ldd, di, stream, wf)
+                                  : launch_fused_fwd<true>(x, ldx, w, ldw, p, dz, ldd, di, stream, wf);
+}
+
+extern "C" int bags_fwd(const void* x, long long ldx, const void* w, long long ldw,
+                        const float* bias, const int64_t* labels, const int32_t* label2bin,
+                        const int32_t* slices_host, const uint8_t* wmask, const float* avg, int N,
+                        int K, int C, int G, int classes, int dtype, float* logits, long long ldz,
+                        float* loss, float* lse, void* dz, long long ldd, float* colsum,
+                        int colsum_tiles, void* workspace, size_t workspace_bytes, void* stream_) {
+  return fwd_impl(x, ldx, w, ldw, bias, labels, label2bin, slices_host, wmask, false, avg, N, K, C, G, classes, dtype,
+                  logits, ldz, loss, lse, dz, ldd, colsum, colsum_tiles, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int bags_fwd_w(const void* x, long long ldx, const void* w, long long ldw,
+                          const float* bias, const int64_t* labels, const int32_t* label2bin,
+                          const int32_t* slices_host, const float* wfloat, const float* avg, int N,
+                          int K, int C, int G, int classes, int dtype, float* logits, long long ldz,
+                          float* loss, float* lse, void* dz, long long ldd, float* colsum,
+                          int colsum_tiles, void* workspace, size_t workspace_bytes, void* stream_) {
+  return fwd_impl(x, ldx, w, ldw, bias, labels, label2bin, slices_host, reinterpret_cast<const uint8_t*>(wfloat),
+                  wfloat != nullptr, avg, N, K, C, G, classes, dtype, logits, ldz, loss, lse, dz, ldd, colsum,
+                  colsum_tiles, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int bags_reweight(const int64_t* labels, const int32_t* label2bin, const uint8_t* wmask,
+                             const float* cls_weight, int wstride, int N, int G, int classes, float* wfloat,
+                             float* avg, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BAGS_REQUIRE(label2bin && cls_weight && wfloat && avg && (N == 0 || labels), "bags_reweight: NULL argument");
+  BAGS_REQUIRE(G >= 1 && G <= kMaxG && classes >= 1 && N >= 0 && wstride >= 1, "bags_reweight: bad shape");
+  reweight_kernel<<<G, 256, 0, stream>>>(reinterpret_cast<const long long*>(labels), label2bin, classes, N, wmask,
+                                         cls_weight, wstride, wfloat, avg);
+  BAGS_CUDA(cudaGetLastError());
+  return BAGS_OK;
 }
 
 __global__ void __launch_bounds__(256)

@@ -43,7 +43,7 @@ struct FusedFwdParams {
   const long long* labels;  // [N]
   const int* l2b;           // [G, classes]
   int classes;
-  const uint8_t* wmask;     // [G, N] or nullptr (all ones)
+  const uint8_t* wmask;     // [G, N] 0/1 bytes (or fp32 weights when the kernel is instantiated with WF) or nullptr (all ones)
   const float* avg;         // [G] or nullptr (N)
   float* loss;              // [G]
   float* lse;               // [N, G] or nullptr
@@ -160,7 +160,9 @@ __device__ __forceinline__ unsigned int atom_add_release_gpu(unsigned int* addr,
   return old;
 }
 
-template <bool TF32>
+// WF = true: p.wmask points at fp32 per-(bin, RoI) weights instead of 0/1 bytes (the reweight head variant,
+// gs_bbox_head_with0_reweight.py:57-85)
+template <bool TF32, bool WF = false>
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FusedCfg<TF32>::NUM_THREADS, 1)
 bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                       const FusedFwdParams p) {
@@ -377,7 +379,11 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         int t = lab_ok ? __ldg(p.l2b + g * p.classes + static_cast<int>(lab)) : 0;
         t = (t >= 0 && t < s_ge[g] - s_gs[g]) ? t : 0;
         float w = 0.f;
-        if (row < p.N) w = (p.wmask != nullptr) ? static_cast<float>(__ldg(p.wmask + static_cast<long long>(g) * p.N + row)) : 1.0f;
+        if (row < p.N)
+          w = (p.wmask != nullptr)
+                  ? (WF ? __ldg(reinterpret_cast<const float*>(p.wmask) + static_cast<long long>(g) * p.N + row)
+                        : static_cast<float>(__ldg(p.wmask + static_cast<long long>(g) * p.N + row)))
+                  : 1.0f;
         const float inv_avg = 1.0f / (p.avg != nullptr ? __ldg(p.avg + g) : fmaxf(static_cast<float>(p.N), 1.0f));
         s_tcol[g * BLOCK_M + row_l] = s_gs[g] + t;
         s_coef[g * BLOCK_M + row_l] = w * inv_avg;

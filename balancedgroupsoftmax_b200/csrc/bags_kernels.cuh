@@ -53,7 +53,7 @@ constexpr float kLn2 = 0.6931471805599453f;
 //   dz       [N, ldd] bf16 (DZ_F32 = false) or fp32 (true), optional
 //   colsum   [C] fp32, += sum_n dz~[n, c]  (optional; caller zeroes)
 //   part     [gridDim.x, kMaxG] fp32 scratch ; counter: 1 uint32 (zero on entry, reset on exit)
-template <int NV, bool DZ_F32>
+template <int NV, bool DZ_F32, bool WF = false>   // WF: wmask points at fp32 weights (reweight head variant)
 __global__ void __launch_bounds__(256)
 group_ce_kernel(const float* __restrict__ z, long long ldz, const long long* __restrict__ labels,
                 const int* __restrict__ l2b, int classes, GroupTable gt,
@@ -112,7 +112,9 @@ group_ce_kernel(const float* __restrict__ z, long long ldz, const long long* __r
       const int s = gt.start[g], len = gt.len[g];
       int t = lab_ok ? __ldg(l2b + g * classes + (int)lab) : 0;
       t = (t >= 0 && t < len) ? t : 0;
-      const float w = (wmask != nullptr) ? (float)__ldg(wmask + (long long)g * N + n) : 1.0f;
+      const float w = (wmask != nullptr) ? (WF ? __ldg(reinterpret_cast<const float*>(wmask) + (long long)g * N + n)
+                                               : (float)__ldg(wmask + (long long)g * N + n))
+                                         : 1.0f;
       // pass 1: max
       float m = -INFINITY;
 #pragma unroll 4
@@ -436,6 +438,38 @@ sample_others_kernel(const long long* __restrict__ labels, const int* __restrict
     __syncthreads();
     if (tid == 0) s_base += tot;
     __syncthreads();
+  }
+}
+
+// Reweight head variant (gs_bbox_head_with0_reweight.py:57-85,101-109): the sampled 0/1 weight of every RoI is
+// multiplied by a per-class weight looked up with the RoI's in-bin label (bin 0 keeps plain ones), and the
+// normaliser becomes max(sum of the products, 1).  One CTA per bin.
+//   cls_weight [G, wstride] fp32: row g holds the len_g weights of bin g (index 0 = "others"); row 0 is unused
+__global__ void __launch_bounds__(256)
+reweight_kernel(const long long* __restrict__ labels, const int* __restrict__ l2b, int classes, int N,
+                const uint8_t* __restrict__ wmask, const float* __restrict__ cls_weight, int wstride,
+                float* __restrict__ wfloat, float* __restrict__ avg) {
+  const int g = blockIdx.x;
+  __shared__ float s_part[8];
+  float acc = 0.f;
+  for (int n = threadIdx.x; n < N; n += 256) {
+    float w = (wmask != nullptr) ? static_cast<float>(wmask[(long long)g * N + n]) : 1.0f;
+    if (g > 0) {
+      const long long lab = labels[n];
+      int t = (lab >= 0 && lab < classes) ? l2b[g * classes + (int)lab] : 0;
+      t = (t >= 0 && t < wstride) ? t : 0;
+      w *= cls_weight[(long long)g * wstride + t];
+    }
+    wfloat[(long long)g * N + n] = w;
+    acc += w;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += s_part[i];
+    avg[g] = fmaxf(t, 1.0f);
   }
 }
 

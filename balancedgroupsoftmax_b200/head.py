@@ -616,5 +616,44 @@ class GSBBoxHead(GSBBoxHeadWith0):
     (configs/ablations/gs_faster_rcnn_r50_fpn_1x_lvis.py:35)."""
 
 
-for _cls in (BBoxHead, ConvFCBBoxHead, SharedFCBBoxHead, GSBBoxHeadWith0, GSBBoxHead):
+class GSBBoxHeadWith0Reweight(GSBBoxHeadWith0):
+    """BAGS head with per-class loss weights inside the bins (gs_bbox_head_with0_reweight.py:14-109; used by
+    configs/ablations/gs_faster_rcnn_r50_fpn_1x_lvis_with0_reweight.py).  EXPERIMENTAL: its device ops have not run on a
+    GPU yet.  Differences from ``GSBBoxHeadWith0``: ``gs_config.bin_cls_weight`` names a pickle holding one weight
+    vector per foreground bin (length = the bin's logit count, index 0 = "others"); the sampled 0/1 weight of every
+    RoI is multiplied by the weight of its in-bin label and the per-bin normaliser is the sum of the products
+    (``_sample_others`` :57-85, ``_remap_labels`` :87-109).  ``gs_config['cls_weights']`` may pass the vectors directly."""
+
+    def __init__(self, *args, gs_config=None, **kwargs):
+        super().__init__(*args, gs_config=gs_config, **kwargs)
+        weights = _cfg_get(gs_config, 'cls_weights')
+        if weights is None:
+            import pickle
+            with open(_cfg_get(gs_config, 'bin_cls_weight'), 'rb') as fin:
+                weights = pickle.load(fin)
+        weights = [torch.as_tensor(np.asarray(w), dtype=torch.float32) for w in weights]
+        G = self.tables.num_bins
+        assert len(weights) == G - 1, 'one weight vector per foreground bin'
+        for g, w in enumerate(weights, start=1):
+            assert w.numel() == int(self.tables.pred_slice[g, 1]), 'bin %d: %d weights for %d logits' % (
+                g, w.numel(), int(self.tables.pred_slice[g, 1]))
+        self.cls_weights = weights
+        stride = max(int(w.numel()) for w in weights)
+        table = torch.ones(G, stride, dtype=torch.float32)
+        for g, w in enumerate(weights, start=1):
+            table[g, :w.numel()] = w
+        self._cls_weight_table = table
+        self._cls_weight_dev: Dict[int, torch.Tensor] = {}
+
+    def _remap_labels(self, labels):
+        """(wfloat [G,N] fp32, avg [G] fp32): the base class's sampled masks times the per-class weights."""
+        wmask, _ = super()._remap_labels(labels)
+        dev = labels.device
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        if idx not in self._cls_weight_dev:
+            self._cls_weight_dev[idx] = self._cls_weight_table.to(dev)
+        return ops.reweight(labels, self.device_tables(dev), wmask, self._cls_weight_dev[idx])
+
+
+for _cls in (BBoxHead, ConvFCBBoxHead, SharedFCBBoxHead, GSBBoxHeadWith0, GSBBoxHead, GSBBoxHeadWith0Reweight):
     register(HEADS, _cls)

@@ -143,6 +143,24 @@ def sample_others(labels: torch.Tensor, dt: DeviceTables, ratio: float, seed: in
     return wmask, avg
 
 
+def reweight(labels: torch.Tensor, dt: DeviceTables, wmask: Optional[torch.Tensor], cls_weight: torch.Tensor
+             ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """EXPERIMENTAL (reweight head variant, gs_bbox_head_with0_reweight.py:57-109): (wfloat [G,N] fp32, avg [G]) with
+    wfloat[g,n] = wmask[g,n] * cls_weight[g, in-bin label of n] for g >= 1 and avg[g] = max(sum_n wfloat[g,n], 1).
+    ``cls_weight`` is [G, stride] fp32 on the device (row 0 unused; index 0 of a row is the "others" weight)."""
+    _require_cuda(labels, wmask, cls_weight)
+    labels = labels.contiguous()
+    assert cls_weight.dtype == torch.float32 and cls_weight.dim() == 2 and cls_weight.shape[0] == dt.G
+    cls_weight = cls_weight.contiguous()
+    N = labels.numel()
+    wfloat = torch.empty((dt.G, N), dtype=torch.float32, device=labels.device)
+    avg = torch.empty((dt.G,), dtype=torch.float32, device=labels.device)
+    nat.check(nat.lib().bags_reweight(labels.data_ptr(), dt.label2bin.data_ptr(), nat.ptr(wmask), cls_weight.data_ptr(),
+                                      cls_weight.shape[1], N, dt.G, dt.num_classes, wfloat.data_ptr(), avg.data_ptr(),
+                                      _stream_ptr(labels.device)), 'bags_reweight')
+    return wfloat, avg
+
+
 def mask_avg(wmask: torch.Tensor) -> torch.Tensor:
     _require_cuda(wmask)
     wmask = wmask.contiguous()
@@ -172,7 +190,10 @@ def group_ce(logits: torch.Tensor, labels: torch.Tensor, dt: DeviceTables,
         dz = torch.empty((N, ldd), dtype=dz_dtype, device=dev)
         colsum = torch.empty((1, Cc), dtype=torch.float32, device=dev)
     ws = _workspace(dev)
-    nat.check(nat.lib().bags_group_ce(
+    entry = nat.lib().bags_group_ce_w if (wmask is not None and wmask.dtype == torch.float32) else nat.lib().bags_group_ce
+    if wmask is not None:
+        assert wmask.dtype in (torch.uint8, torch.float32) and wmask.is_contiguous()
+    nat.check(entry(
         logits.data_ptr(), logits.stride(0), labels.data_ptr(), dt.label2bin.data_ptr(), dt.slices_host,
         nat.ptr(wmask), nat.ptr(avg), N, Cc, dt.G, dt.num_classes, loss.data_ptr(), nat.ptr(lse), nat.ptr(dz), ldd,
         _dtype_code(dz_dtype), nat.ptr(colsum), ws.data_ptr(), ws.numel(), _stream_ptr(dev)), 'bags_group_ce')
@@ -218,7 +239,10 @@ def fused_fwd(x, w, bias, labels, dt: DeviceTables, wmask, avg, logits: Optional
         if want_colsum:   # per-row-tile partials; by default the backward recomputes them from dz instead
             colsum = torch.empty((max((N + 127) // 128, 1), Cc), dtype=torch.float32, device=dev)
     ws = _workspace(dev)
-    nat.check(nat.lib().bags_fwd(
+    entry = nat.lib().bags_fwd_w if (wmask is not None and wmask.dtype == torch.float32) else nat.lib().bags_fwd
+    if wmask is not None:
+        assert wmask.dtype in (torch.uint8, torch.float32) and wmask.is_contiguous()
+    nat.check(entry(
         x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), nat.ptr(bias), labels.data_ptr(),
         dt.label2bin.data_ptr(), dt.slices_host, nat.ptr(wmask), nat.ptr(avg), N, K, Cc, dt.G, dt.num_classes,
         _dtype_code(x.dtype), nat.ptr(logits), logits.stride(0) if logits is not None else 0, loss.data_ptr(),

@@ -120,6 +120,25 @@ int bags_fwd(const void* x, long long ldx, const void* w, long long ldw, const f
              long long ldd, float* colsum, int colsum_tiles, void* workspace, size_t workspace_bytes,
              void* stream);
 
+/* ---- reweight head variant (GSBBoxHeadWith0Reweight, mmdet/models/bbox_heads/gs_bbox_head_with0_reweight.py:57-109):
+ * per-(bin, RoI) fp32 weights instead of 0/1 masks.  EXPERIMENTAL: not yet run on a GPU. ----
+ * bags_reweight: wfloat[g,n] = wmask[g,n] * cls_weight[g, label2bin[g, labels[n]]] for g >= 1 (bin 0: wmask as is),
+ *                avg[g] = max(sum_n wfloat[g,n], 1).  cls_weight is [G, wstride] fp32 (row 0 unused, index 0 = "others").
+ * bags_fwd_w / bags_group_ce_w: bags_fwd / bags_group_ce with `wfloat` [G,N] fp32 in place of the byte mask. */
+int bags_reweight(const int64_t* labels, const int32_t* label2bin, const uint8_t* wmask, const float* cls_weight,
+                  int wstride, int N, int G, int classes, float* wfloat, float* avg, void* stream);
+int bags_fwd_w(const void* x, long long ldx, const void* w, long long ldw, const float* bias,
+               const int64_t* labels, const int32_t* label2bin, const int32_t* slices_host,
+               const float* wfloat, const float* avg, int N, int K, int C, int G, int classes,
+               int dtype, float* logits, long long ldz, float* loss, float* lse, void* dz,
+               long long ldd, float* colsum, int colsum_tiles, void* workspace, size_t workspace_bytes,
+               void* stream);
+int bags_group_ce_w(const float* logits, long long ldz, const int64_t* labels,
+                    const int32_t* label2bin, const int32_t* slices_host, const float* wfloat,
+                    const float* avg, int N, int C, int G, int classes, float* loss, float* lse,
+                    void* dz, long long ldd, int dz_dtype, float* colsum, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
 /* bytes of `wscratch` bags_bwd needs (row-scaled copy of w + bias-gradient partials) */
 size_t bags_bwd_scratch_bytes(int C, long long ldw, int dtype);
 

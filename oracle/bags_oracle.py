@@ -79,6 +79,27 @@ def remap_labels(labels: torch.Tensor, label2binlabel: torch.Tensor, ratio: floa
     return new_labels, new_weights, new_avg
 
 
+def remap_labels_reweight(labels: torch.Tensor, label2binlabel: torch.Tensor, ratio: float,
+                          cls_weights: Sequence[torch.Tensor]
+                          ) -> Tuple[List[torch.Tensor], List[torch.Tensor], List[float]]:
+    """Reweight head variant, gs_bbox_head_with0_reweight.py:57-109: like ``remap_labels``, but the sampled 0/1 weight
+    of a foreground bin is multiplied by ``cls_weights[bin-1][in-bin label]`` (all zeros when the bin has no
+    foreground RoI, :66-67), and the normaliser is max(sum of the products, 1)."""
+    new_labels, new_weights, new_avg = [], [], []
+    for i in range(label2binlabel.shape[0]):
+        new_bin_label = label2binlabel[i][labels]
+        if i < 1:
+            weight = torch.ones_like(new_bin_label)
+        else:
+            weight = sample_others(new_bin_label, ratio)
+            if (new_bin_label > 0).any():          # (the reference returns integer zeros before the multiply otherwise)
+                weight = weight * cls_weights[i - 1][new_bin_label]
+        new_labels.append(new_bin_label)
+        new_weights.append(weight)
+        new_avg.append(max(torch.sum(weight).float().item(), 1.))
+    return new_labels, new_weights, new_avg
+
+
 def slice_preds(cls_score: torch.Tensor, pred_slice: torch.Tensor) -> List[torch.Tensor]:
     """gs_bbox_head_with0.py:134-145."""
     return [cls_score.narrow(1, int(pred_slice[i, 0]), int(pred_slice[i, 1]))

@@ -113,6 +113,37 @@ def load():
     return ns
 
 
+def build_reference_reweight_head(tables, cls_weights, others_sample_ratio: float = 8.0, fc_out_channels: int = 1024,
+                                  tmpdir: Optional[str] = None):
+    """The reference's GSBBoxHeadWith0Reweight (mmdet/models/bbox_heads/gs_bbox_head_with0_reweight.py) on CPU, its
+    per-bin class weights written to a pickle like the file its config names (``bin_cls_weight``)."""
+    import pickle
+    import numpy as np
+    from balancedgroupsoftmax_b200.tables import save_reference_files
+    load()
+    root = reference_dir()
+    md = os.path.join(root, 'mmdet')
+    # this repository's drop-in registers itself under the same name when an `mmdet` package is importable
+    sys.modules['mmdet.models.registry'].HEADS._module_dict.pop('GSBBoxHeadWith0Reweight', None)
+    mod = _exec('mmdet.models.bbox_heads.gs_bbox_head_with0_reweight',
+                os.path.join(md, 'models', 'bbox_heads', 'gs_bbox_head_with0_reweight.py'))
+    d = tmpdir or tempfile.mkdtemp(prefix='bags_tables_rw_')
+    paths = save_reference_files(tables, d)
+    wpath = os.path.join(d, 'bin_cls_weight.pkl')
+    with open(wpath, 'wb') as f:
+        pickle.dump([np.asarray(w, dtype=np.float32) for w in cls_weights], f)
+    gs_config = AttrDict(
+        label2binlabel=paths['label2binlabel'], pred_slice=paths['pred_slice'], fg_split=paths['fg_split'],
+        others_sample_ratio=others_sample_ratio, bin_cls_weight=wpath,
+        loss_bg=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0), num_bins=tables.num_bins,
+        loss_bin=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0))
+    return mod.GSBBoxHeadWith0Reweight(
+        num_fcs=2, in_channels=256, fc_out_channels=fc_out_channels, gs_config=gs_config, roi_feat_size=7,
+        num_classes=tables.num_classes, target_means=[0., 0., 0., 0.], target_stds=[0.1, 0.1, 0.2, 0.2],
+        reg_class_agnostic=False, loss_cls=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0),
+        loss_bbox=dict(type='SmoothL1Loss', beta=1.0, loss_weight=1.0))
+
+
 def load_bbox_target():
     """The reference's own ``bbox_target`` (mmdet/core/bbox/bbox_target.py) and ``bbox2delta`` (transforms.py),
     executed in place: the producer of the head's ``labels`` / box targets."""

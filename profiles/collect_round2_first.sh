@@ -20,3 +20,5 @@ timeout 300 python tools/bench_detector.py --stages 1 --steps 10 --warmup 3 > $o
 timeout 300 python tools/bench_detector.py --stages 3 --steps 10 --warmup 3 > $out/${tag}_detector_s3.json 2> $out/${tag}_detector_s3.err; echo "detector s3 rc=$?"; cat $out/${tag}_detector_s3.json; tail -3 $out/${tag}_detector_s3.err
 # 6. experimental one-launch class-aware NMS against the oracle
 BAGS_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_nms.py -q -m gpu > $out/${tag}_pytest_nms.log 2>&1; echo "nms rc=$?"; tail -3 $out/${tag}_pytest_nms.log
+# 7. experimental reweight head variant (fp32 per-RoI weights through bags_fwd_w / bags_group_ce_w)
+BAGS_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_reweight.py -q -m gpu > $out/${tag}_pytest_reweight.log 2>&1; echo "reweight rc=$?"; tail -3 $out/${tag}_pytest_reweight.log

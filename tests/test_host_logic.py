@@ -258,3 +258,36 @@ def test_graphed_step_refuses_cpu_parameters():
     w = torch.nn.Parameter(torch.zeros(1236, 64))
     with pytest.raises(BagsNativeError):
         GraphedHeadStep(w, None, synthetic_tables(), 32)
+
+
+def test_reweight_head_variant_construction(tmp_path):
+    """GSBBoxHeadWith0Reweight: registered, reads bin_cls_weight in the reference's pickle format, validates lengths."""
+    import pickle
+    import numpy as np
+    import pytest
+    import torch
+    from balancedgroupsoftmax_b200.head import GSBBoxHeadWith0Reweight
+    from balancedgroupsoftmax_b200.registry import HEADS, build_from_cfg
+    from balancedgroupsoftmax_b200.tables import save_reference_files, synthetic_tables
+    t = synthetic_tables()
+    paths = save_reference_files(t, str(tmp_path))
+    ws = [np.linspace(0.5, 1.5, int(t.pred_slice[g, 1])).astype(np.float32) for g in range(1, 5)]
+    wfile = tmp_path / 'bin_cls_weight.pkl'
+    with open(wfile, 'wb') as f:
+        pickle.dump(ws, f)
+    cfg = dict(type='GSBBoxHeadWith0Reweight', num_fcs=2, in_channels=4, fc_out_channels=32, roi_feat_size=2,
+               num_classes=1231,
+               gs_config=dict(label2binlabel=paths['label2binlabel'], pred_slice=paths['pred_slice'],
+                              fg_split=paths['fg_split'], others_sample_ratio=8.0, num_bins=5,
+                              bin_cls_weight=str(wfile),
+                              loss_bin=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0)))
+    head = build_from_cfg(cfg, HEADS)
+    assert isinstance(head, GSBBoxHeadWith0Reweight) and len(head.cls_weights) == 4
+    tab = head._cls_weight_table
+    assert tab.shape == (5, max(len(w) for w in ws)) and torch.all(tab[0] == 1)
+    for g, w in enumerate(ws, start=1):
+        assert torch.allclose(tab[g, :len(w)], torch.from_numpy(w)) and torch.all(tab[g, len(w):] == 1)
+    bad = dict(cfg)
+    bad['gs_config'] = dict(cfg['gs_config'], cls_weights=[w[:-1] for w in ws])
+    with pytest.raises(AssertionError):
+        build_from_cfg(bad, HEADS)

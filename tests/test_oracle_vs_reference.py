@@ -152,3 +152,35 @@ def test_multiclass_nms_oracle_matches_reference_loop():
             want = ref_mc_nms(mb, scores.clone(), thr, dict(type='nms', iou_thr=iou), k)
             got = O.multiclass_nms(mb, scores.clone(), thr, iou, k)
             assert got[0].shape == want[0].shape and torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+
+
+def test_reweight_variant_matches_reference():
+    """Reweight head variant (gs_bbox_head_with0_reweight.py): the oracle's weights / normalisers / per-bin losses
+    against the reference class run in place."""
+    t = synthetic_tables(1231, seed=0)
+    g = torch.Generator().manual_seed(21)
+    cls_weights = [torch.rand(int(t.pred_slice[b, 1]), generator=g) * 2 + 0.1 for b in range(1, t.num_bins)]
+    head = ref_shim.build_reference_reweight_head(t, cls_weights, fc_out_channels=64)
+    head.init_weights()
+    l2b, ps = torch.from_numpy(t.label2binlabel), torch.from_numpy(t.pred_slice)
+    for N, npos, seed in ((300, 75, 1), (64, 0, 2), (40, 40, 3), (512, 128, 4)):
+        torch.manual_seed(seed)
+        with torch.no_grad():
+            head.fc_cls.weight.normal_(0, 0.2)
+            head.fc_cls.bias.normal_(0, 0.1)
+        x = torch.relu(torch.randn(N, 64))
+        labels = torch.zeros(N, dtype=torch.long)
+        labels[:npos] = torch.randint(1, 1231, (npos,))
+        z = head.fc_cls(x).detach()
+        np.random.seed(seed)
+        want = head.loss(z, None, labels, None, None, None)
+        np.random.seed(seed)
+        rl, rw, ra = head._remap_labels(labels)
+        np.random.seed(seed)
+        remapped = O.remap_labels_reweight(labels, l2b, 8.0, cls_weights)
+        for a, b in zip(remapped[1], rw):
+            assert torch.allclose(a.float(), b.float(), rtol=0, atol=0)
+        assert remapped[2] == ra
+        got = O.bags_loss(z, labels, l2b, ps, remapped=remapped)
+        for k in want:
+            assert abs(got[k].item() - want[k].item()) <= 1e-6 * max(1.0, abs(want[k].item())), (k, got[k], want[k])
