@@ -550,6 +550,14 @@ static int launch_fused_fwd_pair(const void* x, long long ldx, const void* w, lo
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = env_int("BAGS_PDL", 1) ? 1 : 0;
+  if (env_int("BAGS_DBG_OCC", 0)) {   // how many 8-CTA clusters fit at once (16 are needed for one wave at N = 4096)
+    int nclusters = -1;
+    cudaLaunchConfig_t q = cfg;
+    q.numAttrs = 0;
+    const cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, kernel, &q);
+    fprintf(stderr, "bags: pair forward: %d clusters of %d CTAs requested, max active clusters = %d (%s)\n",
+            grid / Cfg::CLUSTER, Cfg::CLUSTER, nclusters, cudaGetErrorString(e));
+  }
   BAGS_CUDA(cudaLaunchKernelEx(&cfg, kernel, tx, tw, p));
   return BAGS_OK;
 }

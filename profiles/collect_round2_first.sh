@@ -7,7 +7,7 @@ mkdir -p $out
 timeout 600 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $out/${tag}_pytest.log
 timeout 400 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench rc=$?"; cut -c1-400 $out/${tag}_bench.json
 # 1. CTA-pair forward (BAGS_FWD_PAIR=1): parity vs the default fused forward + kernel timing A/B
-timeout 300 python tests/gpu_probe.py --case fwdpair.bf16 > $out/${tag}_fwdpair.log 2>&1; echo "fwdpair rc=$?"; tail -3 $out/${tag}_fwdpair.log | cut -c1-1500
+BAGS_DBG_OCC=1 timeout 300 python tests/gpu_probe.py --case fwdpair.bf16 > $out/${tag}_fwdpair.log 2>&1; echo "fwdpair rc=$?"; grep -m1 'max active clusters' $out/${tag}_fwdpair.log; tail -3 $out/${tag}_fwdpair.log | cut -c1-1500
 # 2. whole step with the pair forward
 for v in 0 1 0 1; do echo -n "BAGS_FWD_PAIR=$v "; BAGS_FWD_PAIR=$v timeout 200 python bench.py --profile --steps 480 --warmup 20 2>/dev/null | tail -1; done | tee $out/${tag}_fwdpair_step_ab.log
 # 3. library yardstick: the three plain GEMMs through cuBLAS from a CUDA graph (gpu_probe 'timing': cublas_three_gemms_graph_us)
