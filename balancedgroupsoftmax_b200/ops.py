@@ -54,6 +54,18 @@ def _row_major(t: torch.Tensor) -> torch.Tensor:
 _workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
 
 
+def _weights_arg(wmask: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """[G,N] sample weights as the kernels read them: contiguous 0/1 bytes (bool is the same storage), or fp32
+    (reweight head variant); other dtypes are cast to fp32."""
+    if wmask is None:
+        return None
+    if wmask.dtype == torch.bool:
+        wmask = wmask.view(torch.uint8)
+    elif wmask.dtype not in (torch.uint8, torch.float32):
+        wmask = wmask.to(torch.float32)
+    return wmask.contiguous()
+
+
 def _workspace(device: torch.device) -> torch.Tensor:
     key = (device.index if device.index is not None else torch.cuda.current_device(), _stream_ptr(device))
     ws = _workspaces.get(key)
@@ -190,9 +202,8 @@ def group_ce(logits: torch.Tensor, labels: torch.Tensor, dt: DeviceTables,
         dz = torch.empty((N, ldd), dtype=dz_dtype, device=dev)
         colsum = torch.empty((1, Cc), dtype=torch.float32, device=dev)
     ws = _workspace(dev)
+    wmask = _weights_arg(wmask)
     entry = nat.lib().bags_group_ce_w if (wmask is not None and wmask.dtype == torch.float32) else nat.lib().bags_group_ce
-    if wmask is not None:
-        assert wmask.dtype in (torch.uint8, torch.float32) and wmask.is_contiguous()
     nat.check(entry(
         logits.data_ptr(), logits.stride(0), labels.data_ptr(), dt.label2bin.data_ptr(), dt.slices_host,
         nat.ptr(wmask), nat.ptr(avg), N, Cc, dt.G, dt.num_classes, loss.data_ptr(), nat.ptr(lse), nat.ptr(dz), ldd,
@@ -239,9 +250,8 @@ def fused_fwd(x, w, bias, labels, dt: DeviceTables, wmask, avg, logits: Optional
         if want_colsum:   # per-row-tile partials; by default the backward recomputes them from dz instead
             colsum = torch.empty((max((N + 127) // 128, 1), Cc), dtype=torch.float32, device=dev)
     ws = _workspace(dev)
+    wmask = _weights_arg(wmask)
     entry = nat.lib().bags_fwd_w if (wmask is not None and wmask.dtype == torch.float32) else nat.lib().bags_fwd
-    if wmask is not None:
-        assert wmask.dtype in (torch.uint8, torch.float32) and wmask.is_contiguous()
     nat.check(entry(
         x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), nat.ptr(bias), labels.data_ptr(),
         dt.label2bin.data_ptr(), dt.slices_host, nat.ptr(wmask), nat.ptr(avg), N, K, Cc, dt.G, dt.num_classes,
