@@ -55,6 +55,7 @@ SIGNATURES = {
     'bags_debug_spin': (_i, [_i, _i, _i, _vp]),
     'bags_cast_bf16': (_i, [_vp, _ll, _vp, _ll, _i, _i, _vp]),
     'bags_debug_set_timing': (_i, [_vp]),
+    'bags_reload_env': (_i, []),
     'bags_gemm_probe': (_i, [_vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }
 
@@ -85,6 +86,11 @@ def lib():
             raise BagsNativeError('libbags_b200.so ABI version %d != expected %d' % (ver, ABI_VERSION))
         _lib = handle
         return _lib
+
+
+def reload_env() -> None:
+    """Make the library re-read its BAGS_* environment switches (they are cached after first use)."""
+    lib().bags_reload_env()
 
 
 def check(rc: int, what: str) -> None:

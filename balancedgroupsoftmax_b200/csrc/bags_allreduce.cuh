@@ -21,7 +21,7 @@
 //               this rank's block b (ld.acquire.sys until it reaches the expected epoch);
 //               or, protocol "cas": toggled 0 -> 1 by the sender (CAS on the target) and 1 -> 0 by the receiver;
 //   epoch[b]    this rank's block b's own count of barriers so far (all ranks run the same launches, so they agree);
-//   status      set to 1 when a wait timed out (bounded spins; nothing traps, nothing hangs the device).
+//   status      set to 1 when a wait timed out (bounded in time; the kernel then traps -- see rank_barrier).
 // Epochs only grow, so nothing is reset and CUDA-graph replays need no host work; a sender may be one barrier ahead
 // of a slow receiver, hence the >= comparison (on the wrapped difference).
 #pragma once
@@ -44,6 +44,11 @@ struct AllReduceParams {
   long long count;          // floats to reduce (multiple of 4), starting at the bucket base
   int rank, world;
   float scale;              // 1/world for the mean (dist_utils.py:23), 1 for a sum
+  long long timeout_ns;     // how long a rank barrier waits for a missing peer before it gives up
+  int trap_on_timeout;      // 1: a peer that never arrives kills the kernel (__trap: sticky error, the process fails
+                            //    loudly -- NCCL would hang); 0 (construction-time self test only): set the status word,
+                            //    skip the exchange and let the host fall back to NCCL
+  long long* timing;        // debug timeline [grid][8] (%globaltimer) or nullptr
 };
 
 __device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
@@ -94,8 +99,10 @@ __device__ __forceinline__ void multimem_st_f4(float* mc, const float4 v) {
 // Thread t < world publishes `epoch` in rank t's slot for (block, this rank) and polls its own slot for (block, t).
 // Preceded / followed by __syncthreads() so that the release store / acquire fence of the signalling threads order
 // the whole block's accesses (PTX memory model: cumulativity through the CTA barrier).
-// A rank that never shows up does not hang the device: after ~2^22 probes the block records the failure in the
-// status word (checked by the host-side self test) and the kernel returns without exchanging.
+// A rank that never shows up does not hang the device for ever: after `timeout_ns` (default 30 s, generous against
+// checkpoint / evaluation hooks and data-loader stalls on some ranks) the block records the failure in the status word and
+// TRAPS -- the process dies with a sticky CUDA error instead of training on un-averaged gradients.  Only the
+// construction-time self test runs in the soft mode (status word, no exchange, host falls back to NCCL).
 __device__ __forceinline__ uint32_t* ar_flags(const AllReduceParams& p, int rank) {
   return reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(p.peer[rank]) + p.flag_off);
 }
@@ -109,26 +116,41 @@ __device__ __forceinline__ bool rank_barrier(const AllReduceParams& p, uint32_t 
     uint32_t* theirs = ar_flags(p, t) + blockIdx.x * p.world + p.rank;
     uint32_t* mine = ar_flags(p, p.rank) + blockIdx.x * p.world + t;
     uint32_t spins = 0;
+    long long t0 = 0;
     bool ok = true;
+    // the clock is only consulted every 1024 probes: the common case (peers arrive within microseconds) never reads it
+    auto expired = [&]() -> bool {
+      if ((++spins & 1023u) != 0u) return false;
+      const long long now = global_timer_ns();
+      if (t0 == 0) { t0 = now; return false; }
+      return now - t0 > p.timeout_ns;
+    };
     if (EPOCH) {
       st_release_sys_u32(theirs, epoch);
       while (static_cast<int32_t>(ld_acquire_sys_u32(mine) - epoch) < 0) {
         __nanosleep(20);
-        if (++spins > (1u << 22)) { ok = false; break; }
+        if (expired()) { ok = false; break; }
       }
     } else {
       while (cas_release_sys(theirs, 0u, 1u) != 0u) {
-        if (++spins > (1u << 22)) { ok = false; break; }
+        if (expired()) { ok = false; break; }
       }
-      spins = 0;
+      spins = 0; t0 = 0;
       while (ok && cas_acquire_sys(mine, 1u, 0u) != 1u) {
         __nanosleep(20);
-        if (++spins > (1u << 22)) { ok = false; break; }
+        if (expired()) { ok = false; break; }
       }
     }
     if (!ok) {
       *s_fail = 1;
       atomicExch(ar_flags(p, p.rank) + kArMaxBlocks * p.world + kArMaxBlocks, 1u);
+      if (p.trap_on_timeout) {
+        // Never hand un-averaged gradients back to a host that proceeds as if they were exchanged
+        // (the reference's NCCL call would simply wait here): fail the whole process, loudly.
+        printf("bags_grad_allreduce: rank %d block %d waited %lld ms for rank %d (epoch %u) -- aborting\n", p.rank,
+               (int)blockIdx.x, p.timeout_ns / 1000000, t, epoch);
+        __trap();
+      }
     }
   }
   __syncthreads();
@@ -138,14 +160,21 @@ __device__ __forceinline__ bool rank_barrier(const AllReduceParams& p, uint32_t 
 template <bool MULTIMEM, bool EPOCH>
 __global__ void __launch_bounds__(kArThreads, 6)
 bags_grad_allreduce_kernel(const AllReduceParams p) {
+  if (threadIdx.x == 0) stamp(p.timing, 0);
   pdl_trigger();   // the next kernel of the stream (next step's sampler / forward mainloop) may start launching
   pdl_wait();      // the local gradients come from the preceding backward kernel
+  if (threadIdx.x == 0) stamp(p.timing, 1);
   __shared__ int s_fail;
   if (threadIdx.x == 0) s_fail = 0;
-  // this block's barrier count so far (same on every rank); two more after this launch
+  // this block's barrier count so far (same on every rank); two more after this launch -- on EVERY exit path, so a
+  // soft-failed exchange (self test) leaves the epochs of all ranks consistent
   uint32_t* my_epoch = ar_flags(p, p.rank) + kArMaxBlocks * p.world + blockIdx.x;
   const uint32_t epoch = *my_epoch;
-  if (!rank_barrier<EPOCH>(p, epoch + 1u, &s_fail)) return;
+  if (!rank_barrier<EPOCH>(p, epoch + 1u, &s_fail)) {
+    if (threadIdx.x == 0) *my_epoch = epoch + 2u;
+    return;
+  }
+  if (threadIdx.x == 0) stamp(p.timing, 2);
 
   const long long vecs = p.count >> 2;
   const long long chunk = (vecs + p.world - 1) / p.world;
@@ -183,8 +212,9 @@ bags_grad_allreduce_kernel(const AllReduceParams p) {
       }
     }
   }
+  if (threadIdx.x == 0) stamp(p.timing, 3);
   rank_barrier<EPOCH>(p, epoch + 2u, &s_fail);
-  if (threadIdx.x == 0) *my_epoch = epoch + 2u;
+  if (threadIdx.x == 0) { *my_epoch = epoch + 2u; stamp(p.timing, 4); }
 }
 
 }  // namespace bags

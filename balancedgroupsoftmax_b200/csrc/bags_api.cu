@@ -69,8 +69,8 @@ static long long* g_timing = nullptr;
 static int g_dbg = 0;
 extern "C" int bags_debug_set_timing(void* dev_ptr) {
   g_timing = reinterpret_cast<long long*>(dev_ptr);
-  const char* v = getenv("BAGS_DBG");
-  g_dbg = (v && *v) ? atoi(v) : 0;
+  g_dbg = 0;
+  if (const char* v = getenv("BAGS_DBG")) g_dbg = atoi(v);   // test hook, not on the per-step path
   return BAGS_OK;
 }
 
@@ -179,9 +179,25 @@ static int make_group_table(GroupTable& gt, const int32_t* slices_host, int G, i
   return BAGS_OK;
 }
 
+// Tuning / experiment switches come from the environment.  They are read ONCE per name (no getenv on the per-call path);
+// bags_reload_env() drops the cache (tests flip switches inside one process).
+struct EnvEntry { const char* name; bool set; int value; };
+static EnvEntry g_env[96];
+static int g_env_n = 0;
+static std::mutex g_env_mutex;
 static int env_int(const char* name, int dflt) {
+  std::lock_guard<std::mutex> lk(g_env_mutex);
+  for (int i = 0; i < g_env_n; ++i)
+    if (g_env[i].name == name || strcmp(g_env[i].name, name) == 0) return g_env[i].set ? g_env[i].value : dflt;
   const char* v = getenv(name);
-  return (v && *v) ? atoi(v) : dflt;
+  EnvEntry e{name, v && *v, (v && *v) ? atoi(v) : 0};
+  if (g_env_n < 96) g_env[g_env_n++] = e;
+  return e.set ? e.value : dflt;
+}
+extern "C" int bags_reload_env(void) {
+  std::lock_guard<std::mutex> lk(g_env_mutex);
+  g_env_n = 0;
+  return BAGS_OK;
 }
 
 // Launch with the programmatic-stream-serialization attribute (PDL): the kernel may begin while its predecessor
@@ -469,9 +485,7 @@ static bool fused_eligible(const int32_t* slices_host, int G, int C) {
     }
     if (cnt > 2) return false;
   }
-  const char* v = getenv("BAGS_FUSED");
-  if (v && *v == '0') return false;
-  return true;
+  return env_int("BAGS_FUSED", 1) != 0;
 }
 
 extern "C" int bags_fused_eligible(const int32_t* slices_host, int G, int C) {
@@ -679,8 +693,8 @@ static int launch_bwd_merged(const void* dz, long long ldd, const void* x, long 
   if ((rc = make_tmap(&t_wT, wb, dtype, p0.Kf, p0.C, ldw, Cfg::SLAB, Cfg::BLOCK_K, TF32))) return rc;
   BwdFusedParams p = p0;
   p.timing = g_timing ? g_timing + 2048 * 8 : nullptr;   // rows [2048, ..): the forward of the same step uses [0, 2048)
-  // BAGS_BWD_TICKET=1 (experimental): preparation jobs handed out by an atomic ticket (no co-residency requirement)
-  auto kernel = (p.prep_jobs > 0 && env_int("BAGS_BWD_TICKET", 0)) ? bags_bwd_fused_kernel<TF32, MT, true>
+  // preparation jobs handed out by an atomic ticket (no co-residency requirement); BAGS_BWD_TICKET=0: static assignment
+  auto kernel = (p.prep_jobs > 0 && env_int("BAGS_BWD_TICKET", 1)) ? bags_bwd_fused_kernel<TF32, MT, true>
                                                                   : bags_bwd_fused_kernel<TF32, MT, false>;
   BAGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int units = p.dw_units + p.dx_units;
@@ -983,6 +997,11 @@ extern "C" int bags_grad_allreduce(void* const* peer_bufs_host, void* mc_buf, lo
   p.flag_off = flag_off_bytes;
   p.count = count;
   p.rank = rank; p.world = world; p.scale = scale;
+  // max_blocks < 0: soft-failure mode of the construction-time self test (grid = default)
+  p.trap_on_timeout = (max_blocks < 0) ? 0 : 1;
+  if (max_blocks < 0) max_blocks = 0;
+  p.timeout_ns = 1000000LL * env_int("BAGS_AR_TIMEOUT_MS", p.trap_on_timeout ? 30000 : 3000);
+  p.timing = g_timing ? g_timing + 4096 * 8 : nullptr;   // rows [4096, ..): after the forward's and the backward's
   if (count == 0) return BAGS_OK;
   // enough threads to keep one vector per thread and unroll slot in flight, at most kArMaxBlocks blocks;
   // every rank must launch the same grid: it depends only on (count, world, max_blocks) and the environment

@@ -39,12 +39,19 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// wait until every CTA of the grid has finished its preparation jobs (bounded: a broken launch must not hang the box)
+// wait until the preparation jobs of the grid are done.  With ticketed jobs (the default) the CTAs that are running finish
+// all of them, so this wait cannot depend on CTAs that are not resident yet; the time bound (10 s, checked every 4096
+// probes) only keeps a broken launch from hanging the device for ever.
 __device__ __forceinline__ void wait_grid_jobs(const unsigned int* ctr, unsigned int target) {
   unsigned int spins = 0;
+  long long t0 = 0;
   while (ld_acquire_gpu(ctr) < target) {
     __nanosleep(64);
-    if (++spins > (1u << 24)) { printf("bags: grid job counter timed out (block %d)\n", (int)blockIdx.x); __trap(); }
+    if ((++spins & 4095u) == 0u) {
+      const long long now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 10000000000LL) { printf("bags: grid job counter timed out (block %d)\n", (int)blockIdx.x); __trap(); }
+    }
   }
 }
 
@@ -68,9 +75,10 @@ struct BwdCfg {
   static_assert(SMEM_BYTES <= 232448, "exceeds shared memory");
 };
 
-// TICKET = false: preparation job j runs on CTA j % gridDim.x (all CTAs must be resident together before the grid
-// counter reaches its target).  TICKET = true (BAGS_BWD_TICKET=1, experimental): jobs are handed out through an atomic
-// ticket and counted one by one, so whichever CTAs are resident finish them all -- no co-residency requirement.
+// TICKET = true (default): preparation jobs are handed out through an atomic ticket, so whichever CTAs are resident
+// finish them all -- no co-residency requirement (MPS / green-context SM limits, concurrent kernels on other streams).
+// TICKET = false (BAGS_BWD_TICKET=0, opt-in): job j runs on CTA j % gridDim.x; only correct when all CTAs of the grid
+// are resident together.
 template <bool TF32, int MT, bool TICKET = false>
 __global__ void __launch_bounds__(64 + 32 * 8, 1)
 bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as MN-major A of dW  (box SLAB x BLOCK_K)
@@ -265,17 +273,25 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
       float (*s_part)[64] = reinterpret_cast<float (*)[64]>(smem_epi);
       pdl_wait();   // dW / W' may still be in use by whatever ran before the forward kernel; dz comes from it
       if constexpr (TICKET) {
+        // Jobs are claimed through an atomic ticket by whichever CTAs are running, so the grid counter reaches its
+        // target (= the number of jobs) without all CTAs having to be resident together: the CTAs that ARE resident
+        // claim and finish every job before any of them waits.  One fence + one counted publication per CTA.
         __shared__ int s_job;
+        unsigned int done = 0;
         for (;;) {
           if (tid == 0) s_job = static_cast<int>(atomicAdd(p.sync + 2, 1u));
           asm volatile("bar.sync 5, 256;" ::: "memory");
           const int j = s_job;
           if (j >= p.prep_jobs) break;
           bwd_prep_job<TF32, 5>(p.prep, j, tid, s_part);
+          asm volatile("bar.sync 5, 256;" ::: "memory");     // s_job / s_part may be reused
+          ++done;
+        }
+        if (done > 0) {
           asm volatile("fence.proxy.async;" ::: "memory");   // W' is read through TMA (async proxy) by other CTAs
           __threadfence();
-          asm volatile("bar.sync 5, 256;" ::: "memory");     // the job's writes are fenced; s_job / s_part may be reused
-          if (tid == 0) atomicAdd(p.sync, 1u);               // one count per finished job
+          asm volatile("bar.sync 5, 256;" ::: "memory");
+          if (tid == 0) atomicAdd(p.sync, done);
         }
       } else {
       for (int j = blockIdx.x; j < p.prep_jobs; j += gridDim.x) {

@@ -183,7 +183,8 @@ class PeerGradBucket(object):
             return False
 
     def status(self) -> int:
-        """0, or 1 after an exchange in which some rank never arrived (the kernel gave up; the bucket is unusable)."""
+        """0, or 1 after an exchange in which some rank never arrived (soft mode: the kernel gave up and the bucket is
+        unusable; normal mode: the kernel trapped and every later CUDA call of this process fails)."""
         from . import _native
         word = (self.flag_off + int(_native.lib().bags_grad_allreduce_status_offset(self.world))) // 4
         return int(self.storage[word:word + 1].view(torch.int32).item())
@@ -191,11 +192,19 @@ class PeerGradBucket(object):
     def self_test(self) -> bool:
         """One exchange of a known pattern, verified on every rank (collective: all ranks must call it)."""
         dev = self.storage.device
-        self.flat.fill_(float(self.rank + 1))
-        self.allreduce_()
+        # a rank-, position- and sign-dependent pattern (a constant fill cannot see a chunk-boundary or ordering bug);
+        # small integers, so the sum over ranks is exact in fp32 and the expected value is known in closed form
+        idx = torch.arange(self.numel, device=dev, dtype=torch.float32)
+        pat = torch.remainder(idx, 61.0) - 30.0
+        self.flat.copy_(pat * float(self.rank + 1) + float(self.rank))
+        self.allreduce_(soft=True)
         torch.cuda.synchronize(dev)
-        expect = (self.world + 1) / 2.0 if self.mean else self.world * (self.world + 1) / 2.0
-        ok = self.status() == 0 and bool(((self.flat - expect).abs() <= 1e-6 * expect).all().item())
+        s1 = self.world * (self.world + 1) / 2.0
+        s0 = self.world * (self.world - 1) / 2.0
+        expect = pat * s1 + s0
+        if self.mean:
+            expect = expect / self.world
+        ok = self.status() == 0 and bool(((self.flat - expect).abs() <= 1e-5 * expect.abs().clamp_min(1.0)).all().item())
         verdict = torch.tensor([1 if ok else 0], device=dev)
         dist.all_reduce(verdict, op=dist.ReduceOp.MIN, group=self.group)
         self.flat.zero_()
@@ -206,23 +215,26 @@ class PeerGradBucket(object):
     def transport(self) -> str:
         return 'nvls-multimem' if (self.mc_ptr and not os.environ.get('BAGS_AR_NO_MULTIMEM')) else 'peer-ldst'
 
-    def allreduce_(self, stream: Optional[int] = None) -> None:
-        """In place, on the current stream (or the given cudaStream_t): every rank ends with the mean (or sum)."""
+    def allreduce_(self, stream: Optional[int] = None, soft: bool = False) -> None:
+        """In place, on the current stream (or the given cudaStream_t): every rank ends with the mean (or sum).
+        A rank that never arrives makes the kernel trap after BAGS_AR_TIMEOUT_MS (default 30 s): the process fails
+        loudly instead of training on un-averaged gradients.  ``soft=True`` (the self test): only the status word is
+        set, so that the caller can fall back to NCCL."""
         from . import _native
         if stream is None:
             stream = torch.cuda.current_stream(self.storage.device).cuda_stream
         scale = (1.0 / self.world) if self.mean else 1.0
         rc = _native.lib().bags_grad_allreduce(self._peer_arr, self.mc_ptr or None, self.flag_off, self.count,
-                                               self.rank, self.world, scale, self.max_blocks, stream)
+                                               self.rank, self.world, scale, -1 if soft else self.max_blocks, stream)
         _native.check(rc, 'bags_grad_allreduce')
 
 
-def make_grad_bucket(shapes: List[Tuple[int, ...]], device, prefer_peer: bool = True):
+def make_grad_bucket(shapes: List[Tuple[int, ...]], device, prefer_peer: bool = True, max_blocks: int = 0):
     """(bucket_or_None, flat, views, allreduce_fn): the peer-memory bucket when it can be set up, else a plain bucket
     exchanged with NCCL (same results; the reference's path)."""
     if prefer_peer and PeerGradBucket.available() and os.environ.get('BAGS_ALLREDUCE', 'peer') != 'nccl':
         try:
-            b = PeerGradBucket(shapes, device)
+            b = PeerGradBucket(shapes, device, max_blocks=max_blocks)
             if b.self_test():
                 return b, b.flat, b.views, b.allreduce_
             import warnings

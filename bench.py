@@ -117,18 +117,50 @@ class ClockSampler(threading.Thread):
 
 
 # ======================================================================================= reference arm
+def _numa_nodes():
+    """[(node id, [cpu ids])] from sysfs, restricted to the CPUs this process may run on."""
+    allowed = os.sched_getaffinity(0)
+    nodes = []
+    base = '/sys/devices/system/node'
+    try:
+        for d in sorted(os.listdir(base)):
+            if not (d.startswith('node') and d[4:].isdigit()):
+                continue
+            cpus = []
+            for part in open(os.path.join(base, d, 'cpulist')).read().strip().split(','):
+                if not part:
+                    continue
+                a, _, b_ = part.partition('-')
+                cpus.extend(range(int(a), int(b_ or a) + 1))
+            cpus = [c for c in cpus if c in allowed]
+            if cpus:
+                nodes.append((int(d[4:]), cpus))
+    except Exception:
+        pass
+    return nodes or [(0, sorted(allowed))]
+
+
 def run_reference(args):
+    """The reference's CPU path on the host cores.  The 2-socket GPU hosts made an all-cores run 16-80x slower and
+    noisier than a one-socket run (OpenMP threads ping-ponging 25 MB of activations across NUMA nodes), so: pin the
+    process to ONE NUMA node before torch spins up its thread pool, sweep the thread count, and time the K steps with
+    the best setting.  The sweep is reported in the line."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    nodes = _numa_nodes()
+    node_id, node_cpus = max(nodes, key=lambda nc: len(nc[1]))
+    try:
+        os.sched_setaffinity(0, set(node_cpus))     # inherited by every thread torch / OpenMP creates later
+    except Exception:
+        pass
+    os.environ.setdefault('OMP_PROC_BIND', 'close')
     import numpy as np
     import torch
     from balancedgroupsoftmax_b200.tables import synthetic_tables
     from oracle import bags_oracle as O
     from oracle import ref_shim
 
-    rank = int(os.environ.get('RANK', '0'))
-    if rank != 0:
-        return 0
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     tables = synthetic_tables(NUM_CLASSES, seed=0)
     gen = torch.Generator().manual_seed(0)
     n = args.rois
@@ -156,21 +188,42 @@ def run_reference(args):
         def step():
             O.head_step(x, W, b, labels, l2b, ps, RATIO, need_dx=True)
 
+    ncpu = len(node_cpus)
+    cands = sorted({t for t in (8, 16, 32, 64, ncpu) if 1 <= t <= ncpu} or {ncpu})
+    sweep = {}
+    for t in cands:
+        torch.set_num_threads(t)
+        step()
+        times = []
+        t_begin = time.perf_counter()
+        while len(times) < 3 and time.perf_counter() - t_begin < 6.0:
+            t0 = time.perf_counter()
+            step()
+            times.append(time.perf_counter() - t0)
+        sweep[t] = min(times) * 1e3
+    best = min(sweep, key=lambda t: sweep[t])
+    torch.set_num_threads(best)
     for _ in range(max(args.warmup, 1)):
         step()
-    t0 = time.perf_counter()
+    times = []
     for _ in range(args.steps):
+        t0 = time.perf_counter()
         step()
-    dt = (time.perf_counter() - t0) / args.steps
+        times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
     value = n / dt
+    srt = sorted(times)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'RoIs/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'BAGS head fwd+loss+bwd(dW,db,dX), %d RoIs x %d feat x %d logits, 5 bins, '
                                'PyTorch CPU fp32' % (n, K_FEAT, tables.num_logits)},
-        'cpu_baseline': {'value': value, 'unit': 'RoIs/s', 'cores': torch.get_num_threads(), 'kind': kind,
-                         'sample': '%d steps of %d RoIs' % (args.steps, n)},
+        'cpu_baseline': {'value': value, 'unit': 'RoIs/s', 'cores': best, 'kind': kind,
+                         'sample': '%d steps of %d RoIs' % (args.steps, n),
+                         'pinned_to': 'NUMA node %d (%d of %d host CPUs)' % (node_id, ncpu, os.cpu_count() or ncpu),
+                         'thread_sweep_ms_per_step': {str(t): round(v, 2) for t, v in sweep.items()},
+                         'ms_per_step_median': srt[len(srt) // 2] * 1e3, 'ms_per_step_min': srt[0] * 1e3},
         'e2e': {'value': value, 'unit': 'RoIs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -178,32 +231,100 @@ def run_reference(args):
     return 0
 
 
-def cpu_baseline(torch, tables, n, budget_s=15.0):
-    """Oracle port of the reference CPU path, timed on the host cores (bounded sample)."""
-    import numpy as np
-    from oracle import bags_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    gen = torch.Generator().manual_seed(0)
-    x = torch.relu(torch.randn(n, K_FEAT, generator=gen))
-    W = torch.randn(tables.num_logits, K_FEAT, generator=gen) * 0.01
-    b = torch.zeros(tables.num_logits)
+def cpu_baseline(n, steps=10):
+    """The CPU arm (oracle port of the reference path, or the reference itself where a checkout is reachable) in a
+    fresh subprocess: pinned to one NUMA node before its thread pool exists, thread count swept (see run_reference)."""
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', str(steps), '--warmup', '2',
+           '--rois', str(n)]
+    env = dict(os.environ)
+    for k in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE', 'OMP_NUM_THREADS', 'MKL_NUM_THREADS'):
+        env.pop(k, None)
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
+        line = json.loads([l for l in res.stdout.splitlines() if l.startswith('{')][-1])
+        cb = line['cpu_baseline']
+        cb['ms_per_step'] = line['ms_per_step']
+        return cb
+    except Exception as ex:  # pragma: no cover
+        log('cpu baseline subprocess failed: %r' % (ex,))
+        return None
+
+
+def gpu_library_baseline(torch, tables, dev, n, iters=20):
+    """The on-device bar SURVEY.md 2.2 names: the reference's own formulation through the vendor libraries on the SAME
+    B200 -- F.linear (cuBLAS) + 5 x F.cross_entropy on column slices (ATen) + autograd backward (dW, db, dX).  The
+    reference's host-synchronising sampler (gs_bbox_head_with0.py:63-89) is left OUT (masks are precomputed device
+    tensors), which only flatters the library arm.  Timed eagerly (how the reference runs) and from a CUDA graph."""
+    import torch.nn.functional as F
+    gen = torch.Generator().manual_seed(5)
+    x32 = torch.relu(torch.randn(n, K_FEAT, generator=gen)).to(dev)
+    W32 = (torch.randn(tables.num_logits, K_FEAT, generator=gen) * 0.01).to(dev)
+    b32 = torch.zeros(tables.num_logits, device=dev)
     labels = make_labels(torch, n, NUM_CLASSES, gen)
-    l2b, ps = torch.from_numpy(tables.label2binlabel), torch.from_numpy(tables.pred_slice)
-    np.random.seed(0)
-    for _ in range(2):
-        O.head_step(x, W, b, labels, l2b, ps, RATIO)
-    times = []
-    t_start = time.perf_counter()
-    while len(times) < 20 and (time.perf_counter() - t_start) < budget_s:
-        t0 = time.perf_counter()
-        O.head_step(x, W, b, labels, l2b, ps, RATIO)
-        times.append(time.perf_counter() - t0)
-    times.sort()
-    med = times[len(times) // 2]
-    return {'value': n / med, 'unit': 'RoIs/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-            'sample': 'median of %d fwd+bwd iterations of %d RoIs (fp32, torch CPU)' % (len(times), n),
-            'ms_per_step': med * 1e3}
+    l2b = torch.from_numpy(tables.label2binlabel)
+    slices = [(int(s_), int(l_)) for s_, l_ in tables.pred_slice]
+    tg = [l2b[g][labels].to(dev) for g in range(tables.num_bins)]
+    wg = [torch.ones(n, device=dev) if g == 0 else (torch.rand(n, generator=gen) < 0.6).float().to(dev)
+          for g in range(tables.num_bins)]
+    inv_avg = [1.0 / max(float(w.sum().item()), 1.0) for w in wg]
+    out = {}
+    prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+    for name in ('fp32', 'tf32', 'bf16'):
+        torch.backends.cuda.matmul.allow_tf32 = (name == 'tf32')
+        dt_ = torch.bfloat16 if name == 'bf16' else torch.float32
+        x = x32.to(dt_).requires_grad_(True)
+        W = W32.to(dt_).requires_grad_(True)
+        b = b32.to(dt_).requires_grad_(True)
+
+        def step():
+            x.grad = W.grad = b.grad = None
+            z = F.linear(x, W, b)
+            total = None
+            for g, (s_, l_) in enumerate(slices):
+                ce = F.cross_entropy(z[:, s_:s_ + l_].float(), tg[g], reduction='none')
+                term = (ce * wg[g]).sum() * inv_avg[g]
+                total = term if total is None else total + term
+            total.backward()
+
+        st = torch.cuda.Stream(device=dev)
+        st.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(st):
+            for _ in range(3):
+                step()
+            st.synchronize()
+            a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st)
+            for _ in range(iters):
+                step()
+            c.record(st)
+            st.synchronize()
+            out[name + '_eager_us'] = a.elapsed_time(c) / iters * 1e3
+            try:
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_, stream=st):
+                    step()
+                g_.replay()
+                st.synchronize()
+                a.record(st)
+                for _ in range(iters):
+                    g_.replay()
+                c.record(st)
+                st.synchronize()
+                out[name + '_graph_us'] = a.elapsed_time(c) / iters * 1e3
+                del g_
+            except Exception as ex:  # pragma: no cover
+                out[name + '_graph_us'] = None
+                log('library baseline graph capture failed (%s): %r' % (name, ex))
+        torch.cuda.current_stream(dev).wait_stream(st)
+    torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+    best = min(v for k_, v in out.items() if v is not None)
+    out['best_us'] = best
+    out['value'] = n / (best * 1e-6)
+    out['unit'] = 'RoIs/s'
+    out['what'] = ('torch %s on the same GPU: F.linear (cuBLAS) + 5 x F.cross_entropy over column slices (ATen) + autograd '
+                   'backward (dW, db, dX), %d RoIs, precomputed masks (no host-sync sampler); fp32 = allow_tf32 off, '
+                   'the reference\'s setting' % (torch.__version__, n))
+    return out
 
 
 # ======================================================================================= our arm
@@ -241,7 +362,7 @@ def run_ours(args):
     pool = max(2, int(np.ceil(2.2 * 126e6 / per_set)))
     if args.pool:
         pool = max(2, args.pool)
-    elif world > 1 and args.exchange == 'overlap':
+    elif world > 1 and args.exchange == 'overlap-next-step':
         # one CUDA graph spans the pool; its last exchange cannot hide under a following step, so a longer graph
         # amortises that tail (each set is used once per graph: no exchange ever races a later step on its bucket)
         pool = 20
@@ -257,7 +378,7 @@ def run_ours(args):
         # flat fc_cls gradient bucket; at N > 1 it lives in NVLink peer-mapped memory (one-kernel exchange)
         if world > 1:
             s['bucket'], s['grad'], (s['dW'], s['db']), s['exchange'] = make_grad_bucket(
-                [(C, K_FEAT), (C,)], dev, prefer_peer=(args.allreduce == 'peer'))
+                [(C, K_FEAT), (C,)], dev, prefer_peer=(args.allreduce == 'peer'), max_blocks=args.ar_blocks)
         else:
             s['grad'] = torch.empty(C * K_FEAT + C, device=dev)
             s['dW'] = s['grad'][:C * K_FEAT].view(C, K_FEAT)
@@ -265,6 +386,31 @@ def run_ours(args):
         s['dX'] = torch.empty(n, K_FEAT, device=dev, dtype=dtype)
         s['wscratch'] = ops.bwd_scratch(s['w'])
         sets.append(s)
+    exchange_check = None
+    if world > 1:
+        # the exchange this run times, on RANDOM gradients, against dist.all_reduce(AVG) (dist_utils.py:9-41): same mean on
+        # every rank (bit-identical across ranks; vs NCCL exact at 2 ranks, fp32 summation-order rounding beyond)
+        gchk = torch.Generator(device=dev).manual_seed(99 + rank)
+        worst = 0.0
+        for s in sets[:2]:
+            src = torch.randn(s['grad'].numel(), device=dev, generator=gchk)
+            s['grad'].copy_(src)
+            ref = src.clone()
+            dist.all_reduce(ref, op=dist.ReduceOp.AVG)
+            s['exchange']()
+            torch.cuda.synchronize()
+            worst = max(worst, (s['grad'] - ref).abs().max().item())
+            other = s['grad'].clone()
+            dist.broadcast(other, src=0)
+            same = torch.tensor([1 if torch.equal(other, s['grad']) else 0], device=dev)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            tw = torch.tensor([worst], device=dev)
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+            worst = float(tw.item())
+            if not bool(same.item()) or worst > (0.0 if world == 2 else 2e-6):
+                raise SystemExit('gradient exchange check failed: max abs err %.3e vs NCCL AVG, ranks identical: %s'
+                                 % (worst, bool(same.item())))
+        exchange_check = {'max_abs_err_vs_nccl_avg': worst, 'ranks_bit_identical': True, 'data': 'randn, 2 buckets'}
     gout = torch.ones(dt.G, device=dev)
     seed_ctr = [0]
     last = {}
@@ -300,7 +446,7 @@ def run_ours(args):
     kernels_per_step = (4 if args.unfused else 3) + (1 if world > 1 and sets[0].get('bucket') is not None else 0)
 
     stream = torch.cuda.Stream(device=dev)
-    comm_stream = torch.cuda.Stream(device=dev) if (world > 1 and args.exchange == 'overlap') else None
+    comm_stream = torch.cuda.Stream(device=dev) if (world > 1 and args.exchange == 'overlap-next-step') else None
     fake = None
     if world == 1 and args.fake_exchange:
         from balancedgroupsoftmax_b200 import _native as nat
@@ -389,7 +535,9 @@ def run_ours(args):
         else:
             x_host = torch.relu(torch.randn(n, K_FEAT, generator=gen)).to(dtype).pin_memory()
             lab_host = make_labels(torch, n, NUM_CLASSES, gen).pin_memory()
-        w_param = torch.nn.Parameter(W_master.to(dev).to(dtype))
+        # fp32 MASTER weight (the reference's nn.Linear parameter): its bf16 operand copy is made inside every step,
+        # and dW / db come back in fp32
+        w_param = torch.nn.Parameter(W_master.to(dev))
         b_param = torch.nn.Parameter(torch.zeros(C, device=dev))
         loss_host = torch.empty(dt.G, dtype=torch.float32).pin_memory()
         e2e_steps = max(10, min(args.steps, 200))
@@ -518,6 +666,9 @@ def run_ours(args):
                'eager_ms_per_step': eager_ms,
                'h2d_ms_inside_pipeline': (sorted(h2d_in_pipe)[len(h2d_in_pipe) // 2] if h2d_in_pipe else None),
                'staging': 'pinned, GPU-local NUMA node' if args.numa_pinned else 'pinned',
+               'operands': ('features staged on the host in %s (the C ABI input format of this dtype mode); fp32 master '
+                            'fc_cls.weight cast to the operand dtype inside every step; dW / db returned in fp32'
+                            % args.dtype),
                'pipeline': 'H2D of step i+1 overlaps compute of step i (2 buffers); losses read back every step'}
     except Exception as ex:  # pragma: no cover
         log('e2e arm failed: %r' % (ex,))
@@ -602,28 +753,49 @@ def run_ours(args):
         flops = {'fc_cls_gemm': 2.0 * n * K_FEAT * C, 'fused_fwd': 2.0 * n * K_FEAT * C, 'dW_gemm': 2.0 * n * K_FEAT * C,
                  'dX_gemm': 2.0 * n * K_FEAT * C, 'bwd_merged(prep+dW+dX)': 4.0 * n * K_FEAT * C}
         bytes_ce = n * C * 4 + n * C * elt + n * 8 + dt.G * n   # read fp32 logits, write dz, labels, masks
+        # Isolated kernel timings (a few hundred microseconds of launches at full clocks) are judged against the BURST
+        # cuBLAS figure of MEASURED_PEAKS.json; the whole step, timed inside a seconds-long loop, against the SUSTAINED
+        # one.  Both fractions are printed for every entry.
+        tfac = 1.0 if dtype == torch.bfloat16 else 0.5
+        pk_burst, pk_sust = pk['bf16_tflops'] * tfac, pk['bf16_tflops_sustained'] * tfac
+        psrc = pk['source'] + (' cuBLAS bf16' if dtype == torch.bfloat16 else ' cuBLAS bf16 / 2 for tf32')
+        roof_worst = None
         if kernel_us:
-            dom = max(kernel_us, key=lambda k_: kernel_us[k_])
+            def tensor_roof(name):
+                ach = flops[name] / (kernel_us[name] * 1e-6) / 1e12
+                return {'kernel': name, 'bound': 'tensor', 'achieved': ach, 'peak': pk_burst, 'unit': 'TFLOP/s',
+                        'frac': ach / pk_burst, 'frac_of_sustained_peak': ach / pk_sust, 'peak_sustained': pk_sust,
+                        'kernel_us': kernel_us[name], 'algorithmic_flops': flops[name],
+                        'traffic': (ncu_traffic(name) if n == N_ROIS and not TF else None),
+                        'peak_source': psrc + ' (burst: the kernel is timed alone)'}
+            step_kernels = [k_ for k_ in ('fused_fwd', 'fc_cls_gemm', 'group_ce', 'bwd_merged(prep+dW+dX)') if k_ in kernel_us]
+            dom = max(step_kernels, key=lambda k_: kernel_us[k_])
             if dom in flops:
-                peak = pk['bf16_tflops_sustained'] if dtype == torch.bfloat16 else pk['bf16_tflops_sustained'] / 2.0
-                ach = flops[dom] / (kernel_us[dom] * 1e-6) / 1e12
-                roof = {'kernel': dom, 'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
-                        'frac': ach / peak, 'traffic': (ncu_traffic(dom) if n == N_ROIS and not TF else None),
-                        'peak_source': pk['source'] + (' (sustained bf16)' if dtype == torch.bfloat16 else
-                                                       ' (sustained bf16 / 2 for tf32)')}
+                roof = tensor_roof(dom)
             else:
                 ach = bytes_ce / (kernel_us[dom] * 1e-6) / 1e9
                 roof = {'kernel': dom, 'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                         'frac': ach / pk['hbm_gbs'], 'traffic': ncu_traffic(dom), 'peak_source': pk['source'],
                         'algorithmic_bytes': bytes_ce}
+            cands = [tensor_roof(k_) for k_ in step_kernels if k_ in flops]
+            if cands:
+                roof_worst = min(cands, key=lambda r_: r_['frac'])
         step_flops = 6.0 * n * K_FEAT * C
-        peak_t = pk['bf16_tflops_sustained'] if dtype == torch.bfloat16 else pk['bf16_tflops_sustained'] / 2.0
-        step_roof = {'bound': 'tensor', 'achieved': step_flops / (ms_step * 1e-3) / 1e12, 'peak': peak_t,
-                     'unit': 'TFLOP/s', 'algorithmic_flops_per_step': step_flops}
-        step_roof['frac'] = step_roof['achieved'] / peak_t
+        ach_step = step_flops / (ms_step * 1e-3) / 1e12
+        step_roof = {'bound': 'tensor', 'achieved': ach_step, 'peak': pk_sust, 'unit': 'TFLOP/s',
+                     'frac': ach_step / pk_sust, 'frac_of_burst_peak': ach_step / pk_burst, 'peak_burst': pk_burst,
+                     'algorithmic_flops_per_step': step_flops,
+                     'peak_source': psrc + ' (sustained: the step is timed inside a long loop)'}
+        lib_base = None
+        if world == 1 and not args.no_library_baseline:
+            try:
+                lib_base = gpu_library_baseline(torch, tables, dev, n)
+                lib_base['ours_over_library'] = lib_base['best_us'] / (ms_step * 1e3)
+            except Exception as ex:  # pragma: no cover
+                log('library baseline failed: %r' % (ex,))
 
     if rank == 0:
-        cb = cpu_baseline(torch, tables, n) if world == 1 else None
+        cb = cpu_baseline(n) if world == 1 else None
         line = {
             'metric': METRIC, 'value': value, 'unit': 'RoIs/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
@@ -640,14 +812,18 @@ def run_ours(args):
                     ('bags_grad_allreduce (%s over NVLink peer memory, one kernel) of %d fp32 fc_cls grads per step'
                      % (sets[0]['bucket'].transport, C * K_FEAT + C)) if sets[0].get('bucket') is not None else
                     ('nccl all_reduce(avg) of %d fp32 fc_cls grads per step' % (C * K_FEAT + C))) + (
-                    '; each exchange runs on a side stream under the next step and completes inside the timed region'
-                    if comm_stream is not None else '; in line after the backward'),
+                    '; RELAXED schedule: each exchange runs on a side stream under the NEXT step and completes inside the timed region'
+                    if comm_stream is not None else
+                    '; in-step: stream-ordered after the backward, complete before the next forward starts'),
+                'exchange_check': exchange_check,
             },
             'clocks': clk,
             'e2e': e2e,
             'gpu_launches': kernels_per_step * args.steps,
             'roofline': roof,
+            'roofline_worst': roof_worst,
             'roofline_step': step_roof,
+            'gpu_library_baseline': lib_base,
             'kernel_us': kernel_us,
             'loss_bins': [float(v) for v in last['loss'].detach().float().cpu().tolist()],
         }
@@ -677,14 +853,19 @@ def main():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--pool', type=int, default=0, help='number of rotating buffer sets (= steps per CUDA graph)')
     ap.add_argument('--fake-exchange', default='', help='probe (N = 1): blocks,threads,microseconds of a side-stream wait kernel per step')
-    ap.add_argument('--exchange', default='overlap', choices=['overlap', 'inline'],
-                    help='N > 1: gradient exchange on a side stream under the next step (default) or in line')
+    ap.add_argument('--exchange', default='instep', choices=['instep', 'overlap-next-step'],
+                    help='N > 1: gradient exchange inside the step, stream-ordered between the backward and the next '
+                         "step's forward (default: what an SGD step needs -- the optimizer reads the reduced gradients "
+                         'before the next forward reads W; mmdet/core/utils/dist_utils.py:51-58), or the relaxed schedule '
+                         'on a side stream under the NEXT step (not a valid training schedule; kept for comparison)')
+    ap.add_argument('--ar-blocks', type=int, default=0, help='N > 1: grid size limit of the peer-memory exchange kernel (0 = default)')
     ap.add_argument('--allreduce', default=os.environ.get('BAGS_ALLREDUCE', 'peer'), choices=['peer', 'nccl'],
                     help='N > 1: gradient exchange by the peer-memory kernel (default) or NCCL')
     ap.add_argument('--no-numa-pinned', dest='numa_pinned', action='store_false',
                     help='e2e leg: plain pin_memory() staging buffers instead of GPU-local NUMA placement')
     ap.add_argument('--e2e-eager-only', action='store_true', help='e2e leg: eager autograd calls only (no CUDA-graph step)')
     ap.add_argument('--unfused', action='store_true', help='GEMM -> fp32 logits -> grouped CE instead of the fused kernel')
+    ap.add_argument('--no-library-baseline', action='store_true', help='skip the torch/cuBLAS same-GPU baseline leg')
     ap.add_argument('--profile', action='store_true', help='timed loop only (for ncu): skip e2e / cpu / per-kernel legs')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -173,10 +173,15 @@ int bags_merge_scores(const float* logits, long long ldz, const int32_t* slices_
  *                    words that the caller zeroes ONCE (before the first exchange, on every rank); every call
  *                    leaves them zero
  *   scale          : applied to the sum (1/world = the reference's mean)
+ *   max_blocks     : grid size limit (0 = the library's default for the transport; every rank the same value);
+ *                    a NEGATIVE value selects the soft-failure mode of a construction-time self test (see below)
  * Every rank must issue the call with the same (count, world, max_blocks).  Stream-ordered after the local
- * gradients' producer; all waits are bounded: if a rank never arrives the kernel gives up, leaves the bucket
- * unreduced and sets the uint32 status word at flag_off_bytes + bags_grad_allreduce_status_offset(world) to 1
- * (0 otherwise). */
+ * gradients' producer.  A rank that never arrives at the exchange (BAGS_AR_TIMEOUT_MS, default 30 s -- generous
+ * against checkpoint / evaluation hooks and data-loader stalls) makes the waiting kernels set the uint32 status word at
+ * flag_off_bytes + bags_grad_allreduce_status_offset(world) to 1 and TRAP: the process fails with a sticky CUDA
+ * error instead of continuing on un-averaged gradients (the reference's NCCL all-reduce would wait for ever).  In the
+ * soft mode (max_blocks < 0, 3 s) the kernel only sets the status word and returns without exchanging, so that a
+ * self test at construction can fall back to NCCL. */
 size_t bags_grad_allreduce_flag_bytes(int world);
 long long bags_grad_allreduce_status_offset(int world);
 int bags_grad_allreduce(void* const* peer_bufs_host, void* mc_buf, long long flag_off_bytes, long long count,
@@ -208,6 +213,10 @@ int bags_gemm_probe(const void* a, long long lda, int a_mn, const void* b, long 
  * %globaltimer values (0 start, 1 setup done, 2 first operands landed, 3..6 phase ends, 7 SM id).
  * NULL (the default) disables it.  Not thread-safe; for profiling only. */
 int bags_debug_set_timing(void* dev_ptr);
+
+/* The library reads its tuning / experiment switches (BAGS_* environment variables) once per name and caches them;
+ * this drops the cache so that the next call re-reads the environment (tests flip switches inside one process). */
+int bags_reload_env(void);
 
 #ifdef __cplusplus
 }

@@ -8,9 +8,7 @@ import torch
 
 from oracle import bags_oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('BAGS_TEST_EXPERIMENTAL') != '1',
-                                 reason='experimental kernel: set BAGS_TEST_EXPERIMENTAL=1')]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize('n,classes,per_class_boxes', [(60, 9, False), (300, 40, True), (1000, 6, False), (5, 3, True)])

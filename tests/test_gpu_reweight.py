@@ -9,9 +9,7 @@ import torch
 from balancedgroupsoftmax_b200.tables import synthetic_tables
 from oracle import bags_oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('BAGS_TEST_EXPERIMENTAL') != '1',
-                                 reason='experimental kernels: set BAGS_TEST_EXPERIMENTAL=1')]
+pytestmark = [pytest.mark.gpu]
 
 
 def rel(a, b):
