@@ -51,7 +51,7 @@ SIGNATURES = {
     'bags_grad_allreduce_flag_bytes': (_sz, [_i]),
     'bags_grad_allreduce_status_offset': (_ll, [_i]),
     'bags_grad_allreduce': (_i, [_vp, _vp, _ll, _ll, _i, _i, C.c_float, _i, _vp]),
-    'bags_class_nms': (_i, [_vp, _vp, _i, _i, C.c_float, _vp, _vp]),
+    'bags_class_nms_dense': (_i, [_vp, _i, _vp, _vp, _i, _i, C.c_float, _vp, _vp, _vp]),
     'bags_debug_spin': (_i, [_i, _i, _i, _vp]),
     'bags_cast_bf16': (_i, [_vp, _ll, _vp, _ll, _i, _i, _vp]),
     'bags_debug_set_timing': (_i, [_vp]),

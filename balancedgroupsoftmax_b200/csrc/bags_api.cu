@@ -740,7 +740,7 @@ static int pick_pair_splits(int dw_tiles, int dw_kblocks, int dx_units, int dx_k
     const int units = dw_tiles * s + dx_units;
     const int rounds = (units + pairs - 1) / pairs;
     const int dwk = (dw_kblocks + s - 1) / s;
-    const long unit = (dwk > dx_kblocks ? dwk : dx_kblocks) + 4;   // + epilogue, in k-block equivalents
+    const long unit = ((dx_units > 0 && dx_kblocks > dwk) ? dx_kblocks : dwk) + 4;   // + epilogue, in k-block equivalents
     const long cost = rounds * unit;
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
   }
@@ -837,7 +837,18 @@ extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long 
 
   // ---- preparation: zero dW, W' = gout-scaled W, bias-gradient partial column sums.  On the merged single-CTA path
   // these jobs run inside the GEMM kernel (no extra launch in the dependent chain); otherwise one small kernel. ----
-  const bool merged_path = dW != nullptr && dX != nullptr && N > 0 && (K % 8) == 0 && env_int("BAGS_BWD_MERGED", 1);
+  // dW (+ db) alone also runs on the merged kernel (no dX units): in-kernel preparation, 256 x 256 units when the
+  // problem is large enough -- the launch the split in-step schedule (dW -> exchange || dX) puts on its critical path
+  const bool dw_only_merged = dW != nullptr && dX == nullptr && w != nullptr && N > 0 && (K % 8) == 0 &&
+                              (reinterpret_cast<uintptr_t>(w) & 15) == 0 && env_int("BAGS_BWD_DW_MERGED", 1) &&
+                              !env_int("BAGS_BWD_PAIR", 0);
+  // dX alone with per-bin upstream gradients: the merged kernel decides ON THE DEVICE whether they are uniform (then it
+  // reads W and scales in the epilogue: no scaled copy W', no preparation launch); with gout == NULL the plain GEMM is used
+  const bool dx_only_merged = dW == nullptr && db == nullptr && dX != nullptr && gout != nullptr && x != nullptr &&
+                              w != nullptr && N > 0 && (K % 8) == 0 && env_int("BAGS_BWD_DX_MERGED", 1) &&
+                              !env_int("BAGS_BWD_PAIR", 0);
+  const bool merged_path = ((dW != nullptr && dX != nullptr && N > 0 && (K % 8) == 0) || dw_only_merged || dx_only_merged) &&
+                           env_int("BAGS_BWD_MERGED", 1);
   unsigned int* sync = nullptr;
   if (merged_path && !env_int("BAGS_BWD_PAIR", 0) && env_int("BAGS_BWD_INKERNEL_PREP", 1)) {
     int dev = 0;
@@ -865,8 +876,9 @@ extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long 
   // ---- both contractions in one persistent launch when both are requested ----
   if (merged_path) {
     BAGS_REQUIRE(w != nullptr, "bags_bwd: w is NULL but dX requested");
-    BAGS_REQUIRE((reinterpret_cast<uintptr_t>(dX) & 15) == 0 && ((lddx * (bf ? 2 : 4)) % 16) == 0,
-                 "bags_bwd: dX rows must be 16-byte aligned");
+    if (dX != nullptr)
+      BAGS_REQUIRE((reinterpret_cast<uintptr_t>(dX) & 15) == 0 && ((lddx * (bf ? 2 : 4)) % 16) == 0,
+                   "bags_bwd: dX rows must be 16-byte aligned");
     const int bk = bf ? 64 : 32;
     BwdFusedParams bp{};
     bp.C = C; bp.Kf = K; bp.Nr = N;
@@ -874,8 +886,8 @@ extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long 
     bp.dw_splits = env_int("BAGS_DW_SPLITS", pick_splits(bp.dw_m_tiles * bp.dw_n_tiles, bp.dw_kblocks, di.num_sms));
     if (bp.dw_splits > bp.dw_kblocks) bp.dw_splits = bp.dw_kblocks;
     bp.dx_m_tiles = (N + 127) / 128; bp.dx_n_tiles = (K + 255) / 256; bp.dx_kblocks = (C + bk - 1) / bk;
-    bp.dw_units = bp.dw_m_tiles * bp.dw_n_tiles * bp.dw_splits;
-    bp.dx_units = bp.dx_m_tiles * bp.dx_n_tiles;
+    bp.dw_units = (dW != nullptr) ? bp.dw_m_tiles * bp.dw_n_tiles * bp.dw_splits : 0;
+    bp.dx_units = (dX != nullptr) ? bp.dx_m_tiles * bp.dx_n_tiles : 0;
     bp.dW = dW; bp.lddw = lddw; bp.dX = dX; bp.lddx = lddx;
     bp.gscale = gout; bp.G = (gout != nullptr) ? gt.G : 0;
     for (int g = 0; g < kMaxGroups; ++g) { bp.gstart[g] = gt.start[g]; bp.glen[g] = gt.len[g]; }
@@ -903,15 +915,21 @@ extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long 
     bp.dx_uniform_ok = (want_scale && env_int("BAGS_DX_UNIFORM", 1)) ? 1 : 0;
     bp.prep.skip_scale_if_uniform = (bp.dx_uniform_ok && prep_jobs > 0) ? 1 : 0;
     // 256 x 256 units (two accumulator sub-tiles sharing the B tile) once the problem fills the machine with them
-    const int mt_auto = (bp.dx_units + bp.dw_m_tiles * bp.dw_n_tiles >= di.num_sms) ? 2 : 1;
+    int mt_auto = (bp.dx_units + bp.dw_m_tiles * bp.dw_n_tiles >= di.num_sms) ? 2 : 1;
+    if (dW == nullptr) mt_auto = (bp.dx_units / 2 >= di.num_sms) ? 2 : 1;   // dX alone: 128-row units fill the machine sooner
+    if (dX == nullptr) {   // dW alone: 256 x 256 units once a full split still leaves every unit >= 4 k-blocks
+      const int tiles256 = ((C + 255) / 256) * bp.dw_n_tiles;
+      const int smax = di.num_sms / (tiles256 > 0 ? tiles256 : 1);
+      mt_auto = (smax >= 1 && bp.dw_kblocks / smax >= 4) ? 2 : 1;
+    }
     if (env_int("BAGS_BWD_MT", mt_auto) == 2) {
       bp.dw_m_tiles = (C + 255) / 256;
       bp.dx_m_tiles = (N + 255) / 256;
-      bp.dx_units = bp.dx_m_tiles * bp.dx_n_tiles;
+      bp.dx_units = (dX != nullptr) ? bp.dx_m_tiles * bp.dx_n_tiles : 0;
       bp.dw_splits = env_int("BAGS_DW_SPLITS", pick_pair_splits(bp.dw_m_tiles * bp.dw_n_tiles, bp.dw_kblocks, bp.dx_units,
                                                                 bp.dx_kblocks, di.num_sms));
       if (bp.dw_splits > bp.dw_kblocks) bp.dw_splits = bp.dw_kblocks;
-      bp.dw_units = bp.dw_m_tiles * bp.dw_n_tiles * bp.dw_splits;
+      bp.dw_units = (dW != nullptr) ? bp.dw_m_tiles * bp.dw_n_tiles * bp.dw_splits : 0;
       return bf ? launch_bwd_merged<false, 2>(dz, ldd, x, ldx, wb, w, ldw, bp, di, stream)
                 : launch_bwd_merged<true, 2>(dz, ldd, x, ldx, wb, w, ldw, bp, di, stream);
     }
@@ -1028,22 +1046,24 @@ extern "C" int bags_grad_allreduce(void* const* peer_bufs_host, void* mc_buf, lo
 }
 
 // ----------------------------------------------------------------------------
-// class-aware batched NMS (experimental; see bags_nms.cuh)
+// class-aware batched NMS (see bags_nms.cuh)
 // ----------------------------------------------------------------------------
-extern "C" int bags_class_nms(const float* boxes, const int32_t* seg_off, int num_segments, int max_segment,
-                              float iou_thr, uint8_t* keep, void* stream_) {
+extern "C" int bags_class_nms_dense(const float* boxes, int box_cols, const int32_t* order, const int32_t* counts,
+                                    int num_classes_fg, int n, float iou_thr, uint8_t* keep, int32_t* overflow,
+                                    void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  BAGS_REQUIRE(num_segments >= 0 && max_segment >= 0, "bags_class_nms: bad sizes");
-  if (num_segments == 0 || max_segment == 0) return BAGS_OK;
-  BAGS_REQUIRE(boxes && seg_off && keep, "bags_class_nms: NULL argument");
-  BAGS_REQUIRE((reinterpret_cast<uintptr_t>(boxes) & 15) == 0, "bags_class_nms: boxes must be 16-byte aligned");
-  BAGS_REQUIRE(max_segment <= kNmsMaxSeg, "bags_class_nms: a class holds %d candidates, more than the %d one CTA handles",
-               max_segment, kNmsMaxSeg);
-  const int words = (max_segment + 31) / 32;
-  const size_t smem = static_cast<size_t>((max_segment + 1) & ~1) * sizeof(float4) +
-                      static_cast<size_t>(max_segment) * words * sizeof(uint32_t);
-  BAGS_CUDA(cudaFuncSetAttribute(class_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  class_nms_kernel<<<num_segments, kNmsThreads, smem, stream>>>(reinterpret_cast<const float4*>(boxes), seg_off, iou_thr, keep);
+  BAGS_REQUIRE(num_classes_fg >= 0 && n >= 0, "bags_class_nms_dense: bad sizes");
+  if (num_classes_fg == 0 || n == 0) return BAGS_OK;
+  BAGS_REQUIRE(boxes && order && counts && keep && overflow, "bags_class_nms_dense: NULL argument");
+  BAGS_REQUIRE(box_cols == 4 || box_cols == 4 * (num_classes_fg + 1),
+               "bags_class_nms_dense: boxes must have 4 or 4 * (classes incl. background) = %d columns (got %d)",
+               4 * (num_classes_fg + 1), box_cols);
+  BAGS_REQUIRE((reinterpret_cast<uintptr_t>(boxes) & 15) == 0, "bags_class_nms_dense: boxes must be 16-byte aligned");
+  const int seg = n < kNmsMaxSeg ? n : kNmsMaxSeg;
+  const int words = (seg + 31) / 32;
+  const size_t smem = static_cast<size_t>((seg + 1) & ~1) * sizeof(float4) + static_cast<size_t>(seg) * words * sizeof(uint32_t);
+  BAGS_CUDA(cudaFuncSetAttribute(class_nms_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  class_nms_dense_kernel<<<num_classes_fg, kNmsThreads, smem, stream>>>(boxes, box_cols, order, counts, n, iou_thr, keep, overflow);
   BAGS_CUDA(cudaGetLastError());
   return BAGS_OK;
 }

@@ -597,17 +597,17 @@ class GSBBoxHeadWith0(SharedFCBBoxHead):
         bboxes = self._decode(rois, bbox_pred, img_shape, scale_factor, rescale)
         if cfg is None:
             return bboxes, scores
+        nms_cfg = _cfg_get(cfg, 'nms')
+        nms_type = _cfg_get(nms_cfg, 'type', 'nms')
+        if nms_type == 'nms' and os.environ.get('BAGS_NMS_NATIVE', '1') != '0':
+            # hard NMS (every configs/bags/* file): the device-side class-aware NMS -- one sort, one kernel, one sync
+            # instead of the reference's Python loop over 1230 classes (bbox_nms.py:34-54)
+            return ops.multiclass_nms(bboxes, scores, float(_cfg_get(cfg, 'score_thr')),
+                                      float(_cfg_get(nms_cfg, 'iou_thr')), int(_cfg_get(cfg, 'max_per_img')))
         multiclass_nms = _mmdet_core('multiclass_nms')
         if multiclass_nms is None:
-            if os.environ.get('BAGS_NMS_NATIVE') == '1':    # experimental one-launch class-aware NMS (ops.multiclass_nms)
-                nms_cfg = _cfg_get(cfg, 'nms')
-                if _cfg_get(nms_cfg, 'type', 'nms') != 'nms':
-                    raise NotImplementedError('only hard NMS is implemented natively (got %r)' % _cfg_get(nms_cfg, 'type'))
-                return ops.multiclass_nms(bboxes, scores, float(_cfg_get(cfg, 'score_thr')),
-                                          float(_cfg_get(nms_cfg, 'iou_thr')), int(_cfg_get(cfg, 'max_per_img')))
-            raise NotImplementedError('multiclass_nms is downstream of the BAGS path (SURVEY.md §8f-2); '
-                                      'install mmdetection v1.x, or set BAGS_NMS_NATIVE=1 for the experimental '
-                                      'one-launch class-aware NMS (ops.multiclass_nms)')
+            raise NotImplementedError('nms type %r is not implemented natively (hard NMS is); install mmdetection v1.x '
+                                      'for soft-NMS' % (nms_type,))
         return multiclass_nms(bboxes, scores, cfg.score_thr, cfg.nms, cfg.max_per_img)
 
 

@@ -316,43 +316,49 @@ def merge_scores(logits: torch.Tensor, dt: DeviceTables) -> torch.Tensor:
 
 def multiclass_nms(multi_bboxes: torch.Tensor, multi_scores: torch.Tensor, score_thr: float, iou_thr: float,
                    max_num: int = -1) -> Tuple[torch.Tensor, torch.Tensor]:
-    """EXPERIMENTAL (bags_class_nms has not run on a GPU yet).  mmdet/core/post_processing/bbox_nms.py:6-66 with the
-    per-class Python loop replaced by ONE launch: candidates (score > score_thr, background column ignored) are sorted
-    by (class, score descending) with torch, every class segment is suppressed by its own CTA, then the reference's
-    top-``max_num`` rule is applied.  Returns (dets [k,5], labels [k] 0-based)."""
+    """mmdet/core/post_processing/bbox_nms.py:6-66 (hard NMS) with the per-class Python loop -- 1230 NMS launches and as
+    many host syncs per image -- replaced by device-side work and ONE sync for the size of the result:
+
+        one batched descending sort of the class scores  ->  per-class candidate counts (score > score_thr) on the device
+        ->  bags_class_nms_dense: one CTA per class gathers its candidates' boxes and suppresses (IoU with "+1" widths,
+            mmdet/ops/nms/src/nms_kernel.cu:13-21,60)  ->  top-``max_num`` by score of the survivors (bbox_nms.py:55-61)
+
+    Returns (dets [k,5], labels [k] 0-based): class-major / score-descending order when nothing is cut, score order
+    when ``max_num`` cuts -- as the reference; ``max_num = -1`` drops the lowest-scored detection, as the reference does."""
     _require_cuda(multi_bboxes, multi_scores)
     n, num_classes = multi_scores.shape
     dev = multi_scores.device
-    fg = multi_scores[:, 1:]
-    cand = torch.nonzero(fg > score_thr, as_tuple=False)          # host sync: the output size is data dependent
-    if cand.shape[0] == 0:
+    S = num_classes - 1
+    if n == 0 or S <= 0:
         return multi_bboxes.new_zeros((0, 5)), multi_bboxes.new_zeros((0,), dtype=torch.long)
-    rows, cls = cand[:, 0], cand[:, 1]
-    sc = fg[rows, cls]
-    by_score = torch.argsort(sc, descending=True, stable=True)
-    by_class = torch.argsort(cls[by_score], stable=True)          # stable: score order survives inside a class
-    idx = by_score[by_class]
-    rows, cls, sc = rows[idx], cls[idx], sc[idx]
-    if multi_bboxes.shape[1] == 4:
-        boxes = multi_bboxes[rows]
+    boxes = multi_bboxes.float().contiguous()
+    if boxes.shape[1] not in (4, 4 * num_classes):
+        raise nat.BagsNativeError('multi_bboxes must be [n, 4] or [n, 4 * num_classes]')
+    vals, order = multi_scores[:, 1:].float().t().contiguous().sort(dim=1, descending=True, stable=True)   # [S, n]
+    counts = (vals > score_thr).sum(dim=1, dtype=torch.int32)
+    order32 = order.to(torch.int32)
+    keep = torch.empty((S, n), dtype=torch.uint8, device=dev)
+    overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+    nat.check(nat.lib().bags_class_nms_dense(boxes.data_ptr(), boxes.shape[1], order32.data_ptr(), counts.data_ptr(), S, n,
+                                             float(iou_thr), keep.data_ptr(), overflow.data_ptr(), _stream_ptr(dev)),
+              'bags_class_nms_dense')
+    kept = keep.bool()
+    flat = torch.where(kept, vals, torch.full_like(vals, float('-inf'))).reshape(-1)
+    cap = min(max_num, S * n) if max_num > 0 else S * n
+    topv, topi = flat.topk(cap)                                      # survivors by descending score, then -inf padding
+    total, ovf = (int(v) for v in torch.stack([kept.sum(), overflow[0].to(torch.int64)]).tolist())   # the one sync
+    if ovf:
+        raise nat.BagsNativeError('multiclass_nms: a class has more than 1024 candidates above score_thr (n = %d)' % n)
+    if total > max_num:                                              # bbox_nms.py:57-61 (true for max_num = -1 as well)
+        k = max_num if max_num > 0 else total - 1
+        sel = topi[:max(min(k, total), 0)]
     else:
-        boxes = multi_bboxes.view(n, -1, 4)[rows, cls + 1]
-    boxes = boxes.float().contiguous()
-    counts = torch.bincount(cls, minlength=num_classes - 1)
-    seg_off = torch.zeros(num_classes, dtype=torch.int32, device=dev)
-    seg_off[1:] = torch.cumsum(counts, 0).to(torch.int32)
-    max_seg = int(counts.max().item())
-    keep = torch.empty(boxes.shape[0], dtype=torch.uint8, device=dev)
-    nat.check(nat.lib().bags_class_nms(boxes.data_ptr(), seg_off.data_ptr(), num_classes - 1, max_seg, float(iou_thr),
-                                       keep.data_ptr(), _stream_ptr(dev)), 'bags_class_nms')
-    k = keep.bool()
-    dets = torch.cat([boxes[k], sc[k].float()[:, None]], 1)
-    labels = cls[k]
-    if dets.shape[0] > max_num:          # (as in the reference, max_num = -1 drops the lowest-scored detection)
-        _, inds = dets[:, -1].sort(descending=True)
-        inds = inds[:max_num]
-        dets, labels = dets[inds], labels[inds]
-    return dets, labels
+        sel = topi[:total].sort().values                             # class-major, score-descending inside a class
+    cls = torch.div(sel, n, rounding_mode='floor')
+    rows = order.reshape(-1)[sel]
+    b4 = boxes[rows] if boxes.shape[1] == 4 else boxes.view(n, num_classes, 4)[rows, cls + 1]
+    dets = torch.cat([b4, vals.reshape(-1)[sel][:, None]], 1)
+    return dets, cls
 
 
 def gemm_probe(a, a_mn: bool, b, b_mn: bool, M: int, N: int, K: int, block_n: int = 256, splits: int = 1,

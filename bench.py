@@ -385,6 +385,7 @@ def run_ours(args):
             s['db'] = s['grad'][C * K_FEAT:]
         s['dX'] = torch.empty(n, K_FEAT, device=dev, dtype=dtype)
         s['wscratch'] = ops.bwd_scratch(s['w'])
+        s['wscratch2'] = ops.bwd_scratch(s['w'])   # the split schedule's dX launch (its W' must not race the dW launch's partials)
         sets.append(s)
     exchange_check = None
     if world > 1:
@@ -420,6 +421,24 @@ def run_ours(args):
         wmask, avg = ops.sample_others(s['labels'], dt, RATIO, seed_ctr[0])
         loss, _, _, dz, colsum = ops.fused_fwd(s['x'], s['w'], s['bias'], s['labels'], dt, wmask, avg,
                                                logits=(s['logits'] if args.unfused else None))
+        if split_bwd:
+            # in-step schedule with overlap ("launch as soon as the dW epilogue finishes, overlap with the dX
+            # GEMM"): dW + db first, then the exchange on a side stream WHILE dX runs; joined before the step ends, so the
+            # reduced gradients are complete before the next forward starts
+            ops.fused_bwd(dz, s['x'], s['w'], gout, dt, colsum, need_dx=False, dW=s['dW'], wscratch=s['wscratch'], db=s['db'])
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            side_stream.wait_event(ev)
+            with torch.cuda.stream(side_stream):
+                if world > 1:
+                    s['exchange']()
+                elif fake is not None:
+                    nat.check(nat.lib().bags_debug_spin(fake[0], fake[1], fake[2], side_stream.cuda_stream), 'bags_debug_spin')
+            ops.fused_bwd(dz, s['x'], s['w'], gout, dt, None, need_dw=False, need_db=False, dX=s['dX'],
+                          wscratch=s['wscratch2'])
+            torch.cuda.current_stream(dev).wait_stream(side_stream)
+            last['loss'] = loss
+            return loss
         ops.fused_bwd(dz, s['x'], s['w'], gout, dt, colsum, dW=s['dW'], dX=s['dX'], wscratch=s['wscratch'],
                       db=s['db'])
         if world > 1:
@@ -443,15 +462,19 @@ def run_ours(args):
         return loss
 
     # sampler, fused fwd (or GEMM + grouped CE), merged backward (preparation jobs + dW + dX units in one launch)
-    kernels_per_step = (4 if args.unfused else 3) + (1 if world > 1 and sets[0].get('bucket') is not None else 0)
+    kernels_per_step = (4 if args.unfused else 3) + (1 if world > 1 and sets[0].get('bucket') is not None else 0) + (
+        3 if (world > 1 and args.exchange == 'instep-overlap-dx') else 0)   # split: + bwd_prep, dX GEMM, its prep
 
     stream = torch.cuda.Stream(device=dev)
     comm_stream = torch.cuda.Stream(device=dev) if (world > 1 and args.exchange == 'overlap-next-step') else None
+    split_bwd = args.exchange == 'instep-overlap-dx'   # (at N = 1: the split launches alone, or with --fake-exchange)
+    side_stream = torch.cuda.Stream(device=dev) if split_bwd else None
     fake = None
     if world == 1 and args.fake_exchange:
         from balancedgroupsoftmax_b200 import _native as nat
         fake = [int(v) for v in args.fake_exchange.split(',')]    # blocks,threads,microseconds
-        comm_stream = torch.cuda.Stream(device=dev)
+        if not split_bwd:
+            comm_stream = torch.cuda.Stream(device=dev)
     use_graph = not args.no_graph
     graph = None
     with torch.cuda.stream(stream):
@@ -813,8 +836,10 @@ def run_ours(args):
                      % (sets[0]['bucket'].transport, C * K_FEAT + C)) if sets[0].get('bucket') is not None else
                     ('nccl all_reduce(avg) of %d fp32 fc_cls grads per step' % (C * K_FEAT + C))) + (
                     '; RELAXED schedule: each exchange runs on a side stream under the NEXT step and completes inside the timed region'
-                    if comm_stream is not None else
-                    '; in-step: stream-ordered after the backward, complete before the next forward starts'),
+                    if comm_stream is not None else (
+                        '; in-step with overlap: dW+db first, the exchange runs on a side stream under the dX GEMM and is '
+                        'joined before the next forward starts' if split_bwd else
+                        '; in-step: stream-ordered after the backward, complete before the next forward starts')),
                 'exchange_check': exchange_check,
             },
             'clocks': clk,
@@ -853,7 +878,7 @@ def main():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--pool', type=int, default=0, help='number of rotating buffer sets (= steps per CUDA graph)')
     ap.add_argument('--fake-exchange', default='', help='probe (N = 1): blocks,threads,microseconds of a side-stream wait kernel per step')
-    ap.add_argument('--exchange', default='instep', choices=['instep', 'overlap-next-step'],
+    ap.add_argument('--exchange', default='instep', choices=['instep', 'instep-overlap-dx', 'overlap-next-step'],
                     help='N > 1: gradient exchange inside the step, stream-ordered between the backward and the next '
                          "step's forward (default: what an SGD step needs -- the optimizer reads the reduced gradients "
                          'before the next forward reads W; mmdet/core/utils/dist_utils.py:51-58), or the relaxed schedule '

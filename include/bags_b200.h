@@ -187,13 +187,17 @@ long long bags_grad_allreduce_status_offset(int world);
 int bags_grad_allreduce(void* const* peer_bufs_host, void* mc_buf, long long flag_off_bytes, long long count,
                         int rank, int world, float scale, int max_blocks, void* stream);
 
-/* EXPERIMENTAL (not yet run on a GPU): per-class greedy NMS of candidates sorted by (class, score descending), the
- * test-time consumer of bags_merge_scores -- one launch instead of the reference's Python loop over 1230 classes
- * (mmdet/core/post_processing/bbox_nms.py:34-54, IoU convention of mmdet/ops/nms/src/nms_kernel.cu:13-21).
- * boxes [M,4] fp32; seg_off [num_segments+1] int32 (device); max_segment = longest segment (<= 1024);
- * keep [M] uint8 out (1 = kept).  A box is suppressed when IoU("+1" widths) with a kept higher-score box > iou_thr. */
-int bags_class_nms(const float* boxes, const int32_t* seg_off, int num_segments, int max_segment, float iou_thr,
-                   uint8_t* keep, void* stream);
+/* Per-class greedy NMS, the test-time consumer of bags_merge_scores -- one launch instead of the reference's Python loop
+ * over 1230 classes (mmdet/core/post_processing/bbox_nms.py:34-54, IoU convention of
+ * mmdet/ops/nms/src/nms_kernel.cu:13-21: "+1" widths, a box is suppressed when IoU with a kept higher-score box >
+ * iou_thr), without any host-side candidate compaction (no device->host sync):
+ *   order  [S, n] int32 : RoI index of the i-th best score of foreground class s+1 (one batched descending sort)
+ *   counts [S]   int32 : how many of them exceed score_thr (bbox_nms.py:36), clamped to n by the kernel
+ *   boxes  [n, box_cols] fp32 decoded boxes, box_cols == 4 (class-agnostic) or 4 * (S + 1) (per class; bbox_nms.py:39-42)
+ *   keep   [S, n] uint8 out (0 beyond counts[s]); *overflow (device int32, zeroed by the caller) is set to 1 when a
+ *   class has more than 1024 candidates (its tail is dropped). */
+int bags_class_nms_dense(const float* boxes, int box_cols, const int32_t* order, const int32_t* counts,
+                         int num_classes_fg, int n, float iou_thr, uint8_t* keep, int32_t* overflow, void* stream);
 
 /* test hook: launch `blocks` x `threads` threads that wait `micros` microseconds and exit */
 int bags_debug_spin(int blocks, int threads, int micros, void* stream);

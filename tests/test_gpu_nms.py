@@ -1,6 +1,6 @@
-"""GPU, EXPERIMENTAL: the one-launch class-aware NMS (bags_class_nms) against the oracle's per-class loop.
-The kernel was written after round 1 ran out of GPU time, so this test only runs with BAGS_TEST_EXPERIMENTAL=1 until
-it has been seen green once (then drop the gate)."""
+"""GPU: the device-side class-aware NMS (ops.multiclass_nms -> bags_class_nms_dense) against the oracle's restatement of
+the reference's per-class loop (mmdet/core/post_processing/bbox_nms.py:6-66, pinned to the reference's own file in
+tests/test_oracle_vs_reference.py)."""
 import os
 
 import pytest
@@ -28,3 +28,32 @@ def test_class_nms_matches_oracle(n, classes, per_class_boxes):
         key_w = sorted(zip(want_l.tolist(), [tuple(r) for r in want_b.tolist()]))
         key_g = sorted(zip(got_l.cpu().tolist(), [tuple(r) for r in got_b.cpu().tolist()]))
         assert key_w == key_g
+
+
+def test_get_det_bboxes_runs_native_nms_at_lvis_shape():
+    """1000 proposals x 1231 classes, score_thr = 0.0, iou 0.5, max_per_img = 300 (configs/bags/*.py:115-117) through
+    GSBBoxHeadWith0.get_det_bboxes(cfg=...) -- the detections equal the oracle loop's on the same merged scores."""
+    from balancedgroupsoftmax_b200.head import GSBBoxHeadWith0
+    from balancedgroupsoftmax_b200.tables import synthetic_tables
+    t = synthetic_tables(1231, seed=0)
+    head = GSBBoxHeadWith0(num_fcs=2, in_channels=8, fc_out_channels=64, roi_feat_size=2, num_classes=1231,
+                           reg_class_agnostic=True,
+                           gs_config=dict(tables=t, others_sample_ratio=8.0, num_bins=5,
+                                          loss_bin=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0)))
+    head = head.cuda().eval()
+    g = torch.Generator().manual_seed(3)
+    n = 1000
+    z = (torch.randn(n, t.num_logits, generator=g) * 3).cuda()
+    xy = torch.rand(n, 2, generator=g) * 600
+    wh = torch.rand(n, 2, generator=g) * 200 + 4
+    rois = torch.cat([torch.zeros(n, 1), xy, xy + wh], 1).cuda()
+    cfg = dict(score_thr=0.0, nms=dict(type='nms', iou_thr=0.5), max_per_img=300)
+    with torch.no_grad():
+        dets, labels = head.get_det_bboxes(rois, z, None, (800, 1333, 3), 1.0, rescale=False, cfg=cfg)
+        boxes, scores = head.get_det_bboxes(rois, z, None, (800, 1333, 3), 1.0, rescale=False, cfg=None)
+    want_b, want_l = O.multiclass_nms(boxes.cpu(), scores.cpu(), 0.0, 0.5, 300)
+    assert dets.shape == want_b.shape == (300, 5)
+    # the cut at max_per_img falls between distinct scores, so the kept sets agree exactly
+    key_w = sorted(zip(want_l.tolist(), [tuple(r) for r in want_b.tolist()]))
+    key_g = sorted(zip(labels.cpu().tolist(), [tuple(r) for r in dets.cpu().tolist()]))
+    assert key_w == key_g

@@ -499,3 +499,25 @@ def test_graphed_step_config2_vs_oracle(env, need_dx):
             assert rel(dX.float(), dX_r) <= 4e-3
         else:
             assert step.grad_x is None
+
+
+@pytest.mark.parametrize('gname', ['uniform', 'nonuniform'])
+@pytest.mark.parametrize('mode', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
+@pytest.mark.parametrize('N', [512, 4096])
+def test_split_backward_matches_oracle(env, N, mode, gname):
+    """The two launches of the in-step exchange schedule (dW + db first, then dX while the gradients travel): each half
+    alone runs on the merged kernel (no dX units / no dW units) and must give the oracle's gradients."""
+    ops, t, dt, l2b, ps = env
+    x, W, b, labels, remapped = _problem(N, seed=55 + N)
+    gout = GOUTS[gname]
+    wmask = torch.stack([w.to(torch.uint8) for w in remapped[1]]).cuda()
+    avg = ops.mask_avg(wmask)
+    xc, wc = x.cuda().to(mode), W.cuda().to(mode)
+    loss, _, _, dz, _ = ops.fused_fwd(xc, wc, b.cuda(), labels.cuda(), dt, wmask, avg)
+    g = torch.tensor(gout, device='cuda')
+    for _ in range(2):   # twice: the library-owned grid counters must be left re-armed by either half
+        dW, db, none_dx = ops.fused_bwd(dz, xc, wc, g, dt, None, need_dx=False)
+        none_dw, none_db, dX = ops.fused_bwd(dz, xc, wc, g, dt, None, need_dw=False, need_db=False)
+    torch.cuda.synchronize()
+    assert none_dx is None and none_dw is None and none_db is None
+    _check_vs_oracle(ops, dt, l2b, ps, x, W, b, labels, remapped, mode, gout, loss, dW, db, dX)
