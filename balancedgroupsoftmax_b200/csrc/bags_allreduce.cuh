@@ -49,6 +49,11 @@ struct AllReduceParams {
                             //    loudly -- NCCL would hang); 0 (construction-time self test only): set the status word,
                             //    skip the exchange and let the host fall back to NCCL
   long long* timing;        // debug timeline [grid][8] (%globaltimer) or nullptr
+  int mode;                 // protocol switches (epoch flags only): bit 0 = the FIRST barrier's flag store is relaxed --
+                            //   the data it publishes was written by the preceding kernel and is in L2, the point of
+                            //   coherence peers read through, so no system-scope release fence is needed; bit 1 = poll
+                            //   with relaxed loads and acquire once at the end; bit 2 = let the next kernel launch
+                            //   (griddepcontrol.launch_dependents) only after the data phase instead of at the start
 };
 
 __device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
@@ -108,8 +113,11 @@ __device__ __forceinline__ uint32_t* ar_flags(const AllReduceParams& p, int rank
 }
 // EPOCH = true : slots carry monotonically growing epoch numbers (release store, local acquire-load polling).
 // EPOCH = false: slots toggle 0 -> 1 -> 0 (put = CAS 0->1 on the target, wait = CAS 1->0 on the own copy).
+__device__ __forceinline__ void st_relaxed_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 template <bool EPOCH>
-__device__ __forceinline__ bool rank_barrier(const AllReduceParams& p, uint32_t epoch, int* s_fail) {
+__device__ __forceinline__ bool rank_barrier(const AllReduceParams& p, uint32_t epoch, int* s_fail, bool first = false) {
   __syncthreads();
   if (threadIdx.x < static_cast<unsigned>(p.world)) {
     const int t = static_cast<int>(threadIdx.x);
@@ -126,10 +134,18 @@ __device__ __forceinline__ bool rank_barrier(const AllReduceParams& p, uint32_t 
       return now - t0 > p.timeout_ns;
     };
     if (EPOCH) {
-      st_release_sys_u32(theirs, epoch);
-      while (static_cast<int32_t>(ld_acquire_sys_u32(mine) - epoch) < 0) {
-        __nanosleep(20);
-        if (expired()) { ok = false; break; }
+      if (first && (p.mode & 1)) st_relaxed_sys_u32(theirs, epoch);
+      else                       st_release_sys_u32(theirs, epoch);
+      if (p.mode & 2) {
+        while (static_cast<int32_t>(ld_relaxed_sys_u32(mine) - epoch) < 0) {
+          if (expired()) { ok = false; break; }
+        }
+        if (ok) (void)ld_acquire_sys_u32(mine);
+      } else {
+        while (static_cast<int32_t>(ld_acquire_sys_u32(mine) - epoch) < 0) {
+          __nanosleep(20);
+          if (expired()) { ok = false; break; }
+        }
       }
     } else {
       while (cas_release_sys(theirs, 0u, 1u) != 0u) {
@@ -161,7 +177,7 @@ template <bool MULTIMEM, bool EPOCH>
 __global__ void __launch_bounds__(kArThreads, 6)
 bags_grad_allreduce_kernel(const AllReduceParams p) {
   if (threadIdx.x == 0) stamp(p.timing, 0);
-  pdl_trigger();   // the next kernel of the stream (next step's sampler / forward mainloop) may start launching
+  if (!(p.mode & 4)) pdl_trigger();   // the next kernel of the stream (next step's sampler / forward) may start launching
   pdl_wait();      // the local gradients come from the preceding backward kernel
   if (threadIdx.x == 0) stamp(p.timing, 1);
   __shared__ int s_fail;
@@ -170,7 +186,7 @@ bags_grad_allreduce_kernel(const AllReduceParams p) {
   // soft-failed exchange (self test) leaves the epochs of all ranks consistent
   uint32_t* my_epoch = ar_flags(p, p.rank) + kArMaxBlocks * p.world + blockIdx.x;
   const uint32_t epoch = *my_epoch;
-  if (!rank_barrier<EPOCH>(p, epoch + 1u, &s_fail)) {
+  if (!rank_barrier<EPOCH>(p, epoch + 1u, &s_fail, true)) {
     if (threadIdx.x == 0) *my_epoch = epoch + 2u;
     return;
   }
@@ -213,6 +229,7 @@ bags_grad_allreduce_kernel(const AllReduceParams p) {
     }
   }
   if (threadIdx.x == 0) stamp(p.timing, 3);
+  if (p.mode & 4) pdl_trigger();
   rank_barrier<EPOCH>(p, epoch + 2u, &s_fail);
   if (threadIdx.x == 0) { *my_epoch = epoch + 2u; stamp(p.timing, 4); }
 }

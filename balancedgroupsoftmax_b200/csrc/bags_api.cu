@@ -917,11 +917,9 @@ extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long 
     // 256 x 256 units (two accumulator sub-tiles sharing the B tile) once the problem fills the machine with them
     int mt_auto = (bp.dx_units + bp.dw_m_tiles * bp.dw_n_tiles >= di.num_sms) ? 2 : 1;
     if (dW == nullptr) mt_auto = (bp.dx_units / 2 >= di.num_sms) ? 2 : 1;   // dX alone: 128-row units fill the machine sooner
-    if (dX == nullptr) {   // dW alone: 256 x 256 units once a full split still leaves every unit >= 4 k-blocks
-      const int tiles256 = ((C + 255) / 256) * bp.dw_n_tiles;
-      const int smax = di.num_sms / (tiles256 > 0 ? tiles256 : 1);
-      mt_auto = (smax >= 1 && bp.dw_kblocks / smax >= 4) ? 2 : 1;
-    }
+    // dW alone: 128 x 256 units.  Filling the machine with 256 x 256 units takes a 7-way split at the benchmark shape, i.e.
+    // 35 MB of red.add for a 5 MB result -- the L2 atomic rate (~3 TB/s) then costs more than the larger tile saves
+    if (dX == nullptr) mt_auto = 1;
     if (env_int("BAGS_BWD_MT", mt_auto) == 2) {
       bp.dw_m_tiles = (C + 255) / 256;
       bp.dx_m_tiles = (N + 255) / 256;
@@ -1020,11 +1018,13 @@ extern "C" int bags_grad_allreduce(void* const* peer_bufs_host, void* mc_buf, lo
   if (max_blocks < 0) max_blocks = 0;
   p.timeout_ns = 1000000LL * env_int("BAGS_AR_TIMEOUT_MS", p.trap_on_timeout ? 30000 : 3000);
   p.timing = g_timing ? g_timing + 4096 * 8 : nullptr;   // rows [4096, ..): after the forward's and the backward's
+  p.mode = env_int("BAGS_AR_MODE", 0);
   if (count == 0) return BAGS_OK;
   // enough threads to keep one vector per thread and unroll slot in flight, at most kArMaxBlocks blocks;
   // every rank must launch the same grid: it depends only on (count, world, max_blocks) and the environment
   int threads = env_int("BAGS_AR_THREADS", 256);
   if (threads != 128 && threads != 256) threads = 256;
+  if (max_blocks > kArMaxBlocks) max_blocks = kArMaxBlocks;
   const long long per_rank = (count / 4 + world - 1) / world;
   long long blocks = (per_rank + static_cast<long long>(threads) * 4 - 1) / (static_cast<long long>(threads) * 4);
   if (blocks < 1) blocks = 1;

@@ -105,7 +105,14 @@ class TorchvisionTrunk(nn.Module):
 
     @torch.no_grad()
     def roi_features(self, feats: Dict[str, torch.Tensor], boxes: List[torch.Tensor], image_sizes) -> torch.Tensor:
-        return self.box_roi_pool(feats, boxes, image_sizes)
+        x = self.box_roi_pool(feats, boxes, image_sizes)
+        # The trunk is untrained (no checkpoints in the image): fifty randomly initialised layers with identity batch-norm
+        # statistics overflow, so its RoI features are not O(1) like a trained detector's.  Standardise every RoI's
+        # feature block (and drop non-finite values) -- shape and cost are what the harness needs from the trunk.
+        x = torch.nan_to_num(x.float(), nan=0.0, posinf=0.0, neginf=0.0)
+        mu = x.mean(dim=(1, 2, 3), keepdim=True)
+        sd = x.std(dim=(1, 2, 3), keepdim=True)
+        return torch.relu((x - mu) / (sd + 1e-6))
 
 
 class BagsDetectorHarness(nn.Module):

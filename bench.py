@@ -196,11 +196,11 @@ def run_reference(args):
         step()
         times = []
         t_begin = time.perf_counter()
-        while len(times) < 3 and time.perf_counter() - t_begin < 6.0:
+        while len(times) < 5 and time.perf_counter() - t_begin < 6.0:
             t0 = time.perf_counter()
             step()
             times.append(time.perf_counter() - t0)
-        sweep[t] = min(times) * 1e3
+        sweep[t] = sorted(times)[len(times) // 2] * 1e3   # median: a setting that is fast once but unstable loses
     best = min(sweep, key=lambda t: sweep[t])
     torch.set_num_threads(best)
     for _ in range(max(args.warmup, 1)):
@@ -762,10 +762,12 @@ def run_ours(args):
             else:
                 kernel_us['fused_fwd'] = graphed(lambda s: ops.fused_fwd(s['x'], s['w'], s['bias'], s['labels'], dt,
                                                                          wmask, avg))
-            kernel_us['dW_gemm'] = graphed(lambda s: ops.fused_bwd(dzs[idx[id(s)]], s['x'], s['w'], gout, dt, colsum0,
-                                                                   need_dx=False, dW=s['dW']))
-            kernel_us['dX_gemm'] = graphed(lambda s: ops.fused_bwd(dzs[idx[id(s)]], s['x'], s['w'], None, dt, colsum0,
-                                                                   need_dw=False, need_db=False, dX=s['dX']))
+            kernel_us['bwd_dW_db_only'] = graphed(lambda s: ops.fused_bwd(dzs[idx[id(s)]], s['x'], s['w'], gout, dt, None,
+                                                                          need_dx=False, dW=s['dW'], db=s['db'],
+                                                                          wscratch=s['wscratch']))
+            kernel_us['bwd_dX_only'] = graphed(lambda s: ops.fused_bwd(dzs[idx[id(s)]], s['x'], s['w'], gout, dt, None,
+                                                                       need_dw=False, need_db=False, dX=s['dX'],
+                                                                       wscratch=s['wscratch2']))
             kernel_us['bwd_merged(prep+dW+dX)'] = graphed(lambda s: ops.fused_bwd(dzs[idx[id(s)]], s['x'], s['w'], gout, dt,
                                                                                   None, dW=s['dW'], dX=s['dX'],
                                                                                   wscratch=s['wscratch'], db=s['db']))
@@ -773,8 +775,8 @@ def run_ours(args):
         except Exception as ex:  # pragma: no cover
             log('per-kernel timing failed: %r' % (ex,))
         TF = dtype != torch.bfloat16
-        flops = {'fc_cls_gemm': 2.0 * n * K_FEAT * C, 'fused_fwd': 2.0 * n * K_FEAT * C, 'dW_gemm': 2.0 * n * K_FEAT * C,
-                 'dX_gemm': 2.0 * n * K_FEAT * C, 'bwd_merged(prep+dW+dX)': 4.0 * n * K_FEAT * C}
+        flops = {'fc_cls_gemm': 2.0 * n * K_FEAT * C, 'fused_fwd': 2.0 * n * K_FEAT * C, 'bwd_dW_db_only': 2.0 * n * K_FEAT * C,
+                 'bwd_dX_only': 2.0 * n * K_FEAT * C, 'bwd_merged(prep+dW+dX)': 4.0 * n * K_FEAT * C}
         bytes_ce = n * C * 4 + n * C * elt + n * 8 + dt.G * n   # read fp32 logits, write dz, labels, masks
         # Isolated kernel timings (a few hundred microseconds of launches at full clocks) are judged against the BURST
         # cuBLAS figure of MEASURED_PEAKS.json; the whole step, timed inside a seconds-long loop, against the SUSTAINED

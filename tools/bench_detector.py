@@ -7,7 +7,9 @@
 Synthetic 1333x800 images -> frozen torchvision R50-FPN trunk + RPN + RoIAlign -> 512 sampled RoIs / image ->
 BAGS head(s) forward + loss + backward -> mean of the head gradients over ranks -> SGD step on the head.
 Reports images/s (whole job) and the share of a step spent in the head (CUDA events around the head's part), one JSON
-line on rank 0.  Written at the end of round 1; first run scheduled for round 2.
+line on rank 0.
+--config faster|cascade|htc selects BASELINE.json configs[2..4]' head-call shapes: 2 img x 512 RoIs x 1 head, 2 x 512 x 3
+heads, 1 x 512 x 3 heads (the HTC config's mask branch and X-101 trunk are not part of the harness: R50-FPN stands in).
 """
 from __future__ import annotations
 
@@ -22,6 +24,7 @@ sys.path.insert(0, ROOT)
 
 def main() -> int:
     ap = argparse.ArgumentParser()
+    ap.add_argument('--config', default=None, choices=['faster', 'cascade', 'htc'])
     ap.add_argument('--stages', type=int, default=1, choices=[1, 3])
     ap.add_argument('--imgs-per-gpu', type=int, default=2)
     ap.add_argument('--height', type=int, default=800)
@@ -31,6 +34,8 @@ def main() -> int:
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-amp', dest='amp', action='store_false', help='shared FCs / fc_reg in fp32 instead of bf16 autocast')
     args = ap.parse_args()
+    if args.config is not None:
+        args.stages, args.imgs_per_gpu = {'faster': (1, 2), 'cascade': (3, 2), 'htc': (3, 1)}[args.config]
 
     import torch
     import torch.distributed as dist
@@ -114,7 +119,7 @@ def main() -> int:
             'value': world * args.imgs_per_gpu / (ms * 1e-3), 'unit': 'img/s', 'n_gpus': world, 'ms_per_step': ms,
             'head_ms_per_step': head, 'head_share': head / ms, 'steps': args.steps, 'warmup': args.warmup,
             'dtype': args.dtype, 'amp_trunk_fcs': bool(args.amp), 'data': 'synthetic', 'loss': float(last.detach().float().item()),
-            'config': {'imgs_per_gpu': args.imgs_per_gpu, 'rois_per_image': 512, 'stages': args.stages,
+            'config': {'name': args.config, 'imgs_per_gpu': args.imgs_per_gpu, 'rois_per_image': 512, 'stages': args.stages,
                        'trunk': 'torchvision fasterrcnn_resnet50_fpn (frozen, random init)'}}), flush=True)
     if world > 1:
         dist.barrier()
