@@ -14,7 +14,6 @@
 #include "../../include/bags_b200.h"
 #include "bags_gemm.cuh"
 #include "bags_fused_fwd.cuh"
-#include "bags_fused_fwd_pair.cuh"
 #include "bags_bwd_fused.cuh"
 #include "bags_kernels.cuh"
 #include "bags_allreduce.cuh"
@@ -332,6 +331,64 @@ extern "C" int bags_linear_fwd(const void* x, long long ldx, const void* w, long
                    : launch_gemm<256, false, false, EPI_STORE_F32, true, 4>(ga, di, stream);
 }
 
+// y = act(x W^T + b): the head's shared FCs (ReLU) and fc_reg (identity) on the same tcgen05 pipeline
+// (convfc_bbox_head.py:138-143,167: nn.Linear + ReLU through cuBLAS / ATen in the reference)
+extern "C" int bags_linear_act_fwd(const void* x, long long ldx, const void* w, long long ldw, const float* bias,
+                                   void* out, long long ldo, int N, int K, int C, int dtype, int out_dtype, int relu,
+                                   void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BAGS_REQUIRE(N >= 0 && K >= 1 && C >= 1, "bags_linear_act_fwd: bad shape N=%d K=%d C=%d", N, K, C);
+  BAGS_REQUIRE(N == 0 || (x && w && out), "bags_linear_act_fwd: NULL operand");
+  BAGS_REQUIRE(dtype == BAGS_DTYPE_F32 || dtype == BAGS_DTYPE_BF16, "bags_linear_act_fwd: bad dtype %d", dtype);
+  BAGS_REQUIRE(out_dtype == BAGS_DTYPE_F32 || (out_dtype == BAGS_DTYPE_BF16 && dtype == BAGS_DTYPE_BF16),
+               "bags_linear_act_fwd: output dtype %d not available for operand dtype %d", out_dtype, dtype);
+  BAGS_REQUIRE(ldx >= K && ldw >= K && ldo >= C, "bags_linear_act_fwd: leading dimension smaller than row");
+  if (N == 0) return BAGS_OK;
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  if (bias != nullptr && out_dtype == BAGS_DTYPE_F32)
+    BAGS_REQUIRE((reinterpret_cast<uintptr_t>(bias) & 15) == 0, "bags_linear_act_fwd: bias must be 16-byte aligned");
+  GemmArgs ga{};
+  ga.a = x; ga.lda = ldx; ga.a_mn = false;
+  ga.b = w; ga.ldb = ldw; ga.b_mn = false;
+  ga.M = N; ga.N = C; ga.K = K; ga.dtype = dtype; ga.splits = 1;
+  ga.p.out = out; ga.p.ldo = ldo; ga.p.bias = bias; ga.p.relu = relu ? 1 : 0;
+  if (dtype == BAGS_DTYPE_BF16)
+    return out_dtype == BAGS_DTYPE_BF16 ? launch_gemm<256, false, false, EPI_STORE_BF16, false, 4>(ga, di, stream)
+                                        : launch_gemm<256, false, false, EPI_STORE_F32, false, 4>(ga, di, stream);
+  return launch_gemm<256, false, false, EPI_STORE_F32, true, 4>(ga, di, stream);
+}
+
+// g = (y > 0 ? dy : 0) in the operand dtype of the backward contractions (y == NULL: g = dy, i.e. a cast)
+extern "C" int bags_act_bwd(const void* dy, long long lddy, int dy_dtype, const void* y, long long ldy, int y_dtype,
+                            void* g, long long ldg, int g_dtype, int rows, int cols, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BAGS_REQUIRE(rows >= 0 && cols >= 0 && (cols % 4) == 0, "bags_act_bwd: cols must be a multiple of 4");
+  if (rows == 0 || cols == 0) return BAGS_OK;
+  BAGS_REQUIRE(dy && g, "bags_act_bwd: NULL argument");
+  BAGS_REQUIRE(lddy >= cols && ldg >= cols && (ldg % 4) == 0 && (y == nullptr || ldy >= cols), "bags_act_bwd: bad leading dimension");
+  BAGS_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, "bags_act_bwd: g must be 16-byte aligned");
+  const bool f_dy = dy_dtype == BAGS_DTYPE_F32, f_y = y_dtype == BAGS_DTYPE_F32, f_g = g_dtype == BAGS_DTYPE_F32;
+  const long long quads = static_cast<long long>(rows) * (cols / 4);
+  long long grid = (quads + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  const dim3 gr(static_cast<unsigned>(grid)), bl(256);
+  typedef __nv_bfloat16 bf;
+#define BAGS_ACT(TDY, TY, OB) act_bwd_kernel<TDY, TY, OB><<<gr, bl, 0, stream>>>(                                   \
+      static_cast<const TDY*>(dy), lddy, static_cast<const TY*>(y), ldy, g, ldg, rows, cols)
+  if (f_dy && f_y && f_g) BAGS_ACT(float, float, false);
+  else if (f_dy && f_y) BAGS_ACT(float, float, true);
+  else if (f_dy && f_g) BAGS_ACT(float, bf, false);
+  else if (f_dy) BAGS_ACT(float, bf, true);
+  else if (f_y && f_g) BAGS_ACT(bf, float, false);
+  else if (f_y) BAGS_ACT(bf, float, true);
+  else if (f_g) BAGS_ACT(bf, bf, false);
+  else BAGS_ACT(bf, bf, true);
+#undef BAGS_ACT
+  BAGS_CUDA(cudaGetLastError());
+  return BAGS_OK;
+}
+
 extern "C" int bags_sample_others_step(const int64_t* labels, const int32_t* label2bin, int N, int G,
                                        int classes, double ratio, uint64_t seed, const uint64_t* seed_step,
                                        uint8_t* wmask, float* avg, void* stream_) {
@@ -529,59 +586,21 @@ static int launch_fused_fwd(const void* x, long long ldx, const void* w, long lo
   return BAGS_OK;
 }
 
-// EXPERIMENTAL (BAGS_FWD_PAIR=1): the CTA-pair forward, bags_fused_fwd_pair.cuh.  Same parameters and outputs.
-template <bool TF32>
-static int launch_fused_fwd_pair(const void* x, long long ldx, const void* w, long long ldw, const FusedFwdParams& p0,
-                                 void* dz, long long ldd, cudaStream_t stream) {
-  using Cfg = FusedPairCfg<TF32>;
-  const int dtype = TF32 ? BAGS_DTYPE_F32 : BAGS_DTYPE_BF16;
-  CUtensorMap tx, tw;
-  int rc = make_tmap(&tx, x, dtype, p0.K, p0.N, ldx, Cfg::BLOCK_K, Cfg::BLOCK_M);
-  if (rc) return rc;
-  rc = make_tmap(&tw, w, dtype, p0.K, p0.C, ldw, Cfg::BLOCK_K, Cfg::HALF_N);   // each CTA stages 80 of 160 W rows
-  if (rc) return rc;
-  if (dz != nullptr && (reinterpret_cast<uintptr_t>(dz) & 15) != 0)
-    return fail(BAGS_ERR_INVALID, "bags_fwd: dz must be 16-byte aligned");
-  FusedFwdParams p = p0;
-  p.dz = dz;
-  p.ldd = ldd;
-  p.kblocks = (p.K + Cfg::BLOCK_K - 1) / Cfg::BLOCK_K;
-  p.want_dz = dz != nullptr ? 1 : 0;
-  p.timing = g_timing;
-  p.dbg = g_timing ? g_dbg : 0;
-  auto kernel = bags_fwd_pair_kernel<TF32>;
-  BAGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  const int row_tiles = (p.N + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
-  const int grid = Cfg::CLUSTER * ((row_tiles + 1) / 2);   // an 8-CTA cluster owns two row tiles (the last may be empty)
-  if (grid > 4096) return fail(BAGS_ERR_INVALID, "bags_fwd: N=%d too large for the fused path's loss workspace", p.N);
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(Cfg::NUM_THREADS);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = env_int("BAGS_PDL", 1) ? 1 : 0;
-  if (env_int("BAGS_DBG_OCC", 0)) {   // how many 8-CTA clusters fit at once (16 are needed for one wave at N = 4096)
-    int nclusters = -1;
-    cudaLaunchConfig_t q = cfg;
-    q.numAttrs = 0;
-    const cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, kernel, &q);
-    fprintf(stderr, "bags: pair forward: %d clusters of %d CTAs requested, max active clusters = %d (%s)\n",
-            grid / Cfg::CLUSTER, Cfg::CLUSTER, nclusters, cudaGetErrorString(e));
-  }
-  BAGS_CUDA(cudaLaunchKernelEx(&cfg, kernel, tx, tw, p));
-  return BAGS_OK;
-}
-
 static int fwd_impl(const void* x, long long ldx, const void* w, long long ldw,
                     const float* bias, const int64_t* labels, const int32_t* label2bin,
                     const int32_t* slices_host, const uint8_t* wmask, bool wf, const float* avg, int N,
                         int K, int C, int G, int classes, int dtype, float* logits, long long ldz,
                         float* loss, float* lse, void* dz, long long ldd, float* colsum,
-                        int colsum_tiles, void* workspace, size_t workspace_bytes, void* stream_) {
+                        int colsum_tiles, void* workspace, size_t workspace_bytes, void* stream_,
+                        void* clear = nullptr, size_t clear_bytes = 0) {
+  if (clear != nullptr) {
+    BAGS_REQUIRE((reinterpret_cast<uintptr_t>(clear) & 15) == 0 && (clear_bytes % 16) == 0,
+                 "bags_fwd_ex: the buffer to clear must be 16-byte aligned and a multiple of 16 bytes");
+    if (logits != nullptr || N == 0) {   // not the fused kernel: a plain memset
+      BAGS_CUDA(cudaMemsetAsync(clear, 0, clear_bytes, static_cast<cudaStream_t>(stream_)));
+      clear = nullptr;
+    }
+  }
   if (colsum != nullptr)
     BAGS_REQUIRE(colsum_tiles >= 1 && (logits != nullptr || colsum_tiles == (N + 127) / 128 || N == 0),
                  "bags_fwd: colsum must hold ceil(N/128) = %d row tiles of C floats (got %d)", (N + 127) / 128, colsum_tiles);
@@ -624,9 +643,8 @@ static int fwd_impl(const void* x, long long ldx, const void* w, long long ldw,
   p.counter = reinterpret_cast<unsigned int*>(workspace);
   p.part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
   if (N == 0) dz = nullptr;
-  if (!wf && env_int("BAGS_FWD_PAIR", 0))
-    return dtype == BAGS_DTYPE_BF16 ? launch_fused_fwd_pair<false>(x, ldx, w, ldw, p, dz, ldd, stream)
-                                    : launch_fused_fwd_pair<true>(x, ldx, w, ldw, p, dz, ldd, stream);
+  p.clear = reinterpret_cast<float4*>(clear);
+  p.clear_vecs = static_cast<long long>(clear_bytes / 16);
   return dtype == BAGS_DTYPE_BF16 ? launch_fused_fwd<false>(x, ldx, w, ldw, p, dz, ldd, di, stream, wf)
                                   : launch_fused_fwd<true>(x, ldx, w, ldw, p, dz, ldd, di, stream, wf);
 }
@@ -639,6 +657,18 @@ extern "C" int bags_fwd(const void* x, long long ldx, const void* w, long long l
                         int colsum_tiles, void* workspace, size_t workspace_bytes, void* stream_) {
   return fwd_impl(x, ldx, w, ldw, bias, labels, label2bin, slices_host, wmask, false, avg, N, K, C, G, classes, dtype,
                   logits, ldz, loss, lse, dz, ldd, colsum, colsum_tiles, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int bags_fwd_ex(const void* x, long long ldx, const void* w, long long ldw,
+                           const float* bias, const int64_t* labels, const int32_t* label2bin,
+                           const int32_t* slices_host, const uint8_t* wmask, const float* avg, int N,
+                           int K, int C, int G, int classes, int dtype, float* logits, long long ldz,
+                           float* loss, float* lse, void* dz, long long ldd, float* colsum,
+                           int colsum_tiles, void* workspace, size_t workspace_bytes, void* clear, size_t clear_bytes,
+                           void* stream_) {
+  return fwd_impl(x, ldx, w, ldw, bias, labels, label2bin, slices_host, wmask, false, avg, N, K, C, G, classes, dtype,
+                  logits, ldz, loss, lse, dz, ldd, colsum, colsum_tiles, workspace, workspace_bytes, stream_, clear,
+                  clear_bytes);
 }
 
 extern "C" int bags_fwd_w(const void* x, long long ldx, const void* w, long long ldw,
@@ -790,12 +820,28 @@ extern "C" size_t bags_bwd_scratch_bytes(int C, long long ldw, int dtype) {
   return wbytes + static_cast<size_t>(kColsumTiles) * C * sizeof(float);
 }
 
+extern "C" int bags_bwd_ex(const void* dz, long long ldd, const void* x, long long ldx, const void* w,
+                           long long ldw, const float* gout, const int32_t* slices_host,
+                           const float* colsum, int colsum_tiles, float* dW, long long lddw, float* db, void* dX,
+                           long long lddx, void* wscratch, size_t wscratch_bytes, int N, int K, int C, int G,
+                           int dtype, int flags, void* stream_);
+
 extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long ldx, const void* w,
                         long long ldw, const float* gout, const int32_t* slices_host,
                         const float* colsum, int colsum_tiles, float* dW, long long lddw, float* db, void* dX,
                         long long lddx, void* wscratch, size_t wscratch_bytes, int N, int K, int C, int G,
                         int dtype, void* stream_) {
+  return bags_bwd_ex(dz, ldd, x, ldx, w, ldw, gout, slices_host, colsum, colsum_tiles, dW, lddw, db, dX, lddx, wscratch,
+                     wscratch_bytes, N, K, C, G, dtype, 0, stream_);
+}
+
+extern "C" int bags_bwd_ex(const void* dz, long long ldd, const void* x, long long ldx, const void* w,
+                           long long ldw, const float* gout, const int32_t* slices_host,
+                           const float* colsum, int colsum_tiles, float* dW, long long lddw, float* db, void* dX,
+                           long long lddx, void* wscratch, size_t wscratch_bytes, int N, int K, int C, int G,
+                           int dtype, int flags, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool prezeroed = (flags & BAGS_BWD_DW_PREZEROED) != 0;   // the caller (bags_fwd_ex's clear hook) zeroed dW
   BAGS_REQUIRE(dz != nullptr || N == 0, "bags_bwd: dz is NULL");
   BAGS_REQUIRE(dtype == BAGS_DTYPE_F32 || dtype == BAGS_DTYPE_BF16, "bags_bwd: bad dtype %d", dtype);
   BAGS_REQUIRE(N >= 0 && K >= 1 && C >= 1, "bags_bwd: bad shape");
@@ -857,17 +903,19 @@ extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long 
   }
   BwdPrepParams pp{};
   int prep_jobs = 0;
+  bool prep_launched = false;
   if (dW != nullptr || want_scale || want_colpart) {
     pp.dW = dW; pp.lddw = lddw; pp.C = C; pp.K = K;
     pp.w = w; pp.wscr = wscratch; pp.ldw = ldw; pp.gout = gout; pp.gt = gt;
     pp.dz = dz; pp.ldd = ldd; pp.N = N; pp.colpart = colpart; pp.ctiles = kColsumTiles;
-    pp.z_ctas = (dW != nullptr) ? di.num_sms : 0;
+    pp.z_ctas = (dW != nullptr && !prezeroed) ? di.num_sms : 0;
     pp.s_ctas = want_scale ? di.num_sms : 0;
     pp.c_ctas = want_colpart ? ((C + 63) / 64) * kColsumTiles : 0;
     const int grid = pp.z_ctas + pp.s_ctas + pp.c_ctas;
-    if (sync != nullptr) prep_jobs = grid;
-    else if (bf) BAGS_CUDA(launch_pdl(bwd_prep_kernel<false>, dim3(grid), dim3(256), 0, stream, pp));
-    else         BAGS_CUDA(launch_pdl(bwd_prep_kernel<true>, dim3(grid), dim3(256), 0, stream, pp));
+    if (grid == 0) { /* nothing to prepare */ }
+    else if (sync != nullptr) prep_jobs = grid;
+    else if (bf) { BAGS_CUDA(launch_pdl(bwd_prep_kernel<false>, dim3(grid), dim3(256), 0, stream, pp)); prep_launched = true; }
+    else         { BAGS_CUDA(launch_pdl(bwd_prep_kernel<true>, dim3(grid), dim3(256), 0, stream, pp)); prep_launched = true; }
   }
   const float* cs_in = (colsum != nullptr) ? colsum : colpart;
   const int cs_tiles = (colsum != nullptr) ? colsum_tiles : kColsumTiles;
@@ -895,6 +943,10 @@ extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long 
     bp.colsum_tiles = cs_tiles;
     bp.db = db;
     bp.prep = pp; bp.prep_jobs = prep_jobs; bp.sync = sync;
+    // the first operand load must wait for the producer of dz unless a preparation kernel sits in between (its own wait
+    // covers it); the dW epilogues only depend on the zeroing / column-sum jobs
+    bp.wait_dz = (prep_jobs > 0 || !prep_launched) ? 1 : 0;
+    bp.dw_needs_prep = (pp.z_ctas > 0 || pp.c_ctas > 0 || prep_launched) ? 1 : 0;
     const void* wb = want_scale ? wscratch : w;
     if (env_int("BAGS_BWD_PAIR", 0)) {
       // units are 256-row CTA pairs
@@ -950,6 +1002,7 @@ extern "C" int bags_bwd(const void* dz, long long ldd, const void* x, long long 
     ga.p.colsum_tiles = cs_tiles;
     ga.p.colsum_out = (db != nullptr) ? db : nullptr;
     ga.p.pdl_wait_epilogue = 1;   // dW zeroing + column-sum partials come from bwd_prep; the mainloop overlaps it
+    ga.p.pdl_wait_producer = prep_launched ? 0 : 1;   // no preparation kernel in between: dz comes from the preceding kernel
     int rc = bf ? launch_gemm_pdl<256, true, true, EPI_RED_F32, false, 4>(ga, di, stream)
                 : launch_gemm_pdl<256, true, true, EPI_RED_F32, true, 4>(ga, di, stream);
     if (rc) return rc;
@@ -1018,7 +1071,7 @@ extern "C" int bags_grad_allreduce(void* const* peer_bufs_host, void* mc_buf, lo
   if (max_blocks < 0) max_blocks = 0;
   p.timeout_ns = 1000000LL * env_int("BAGS_AR_TIMEOUT_MS", p.trap_on_timeout ? 30000 : 3000);
   p.timing = g_timing ? g_timing + 4096 * 8 : nullptr;   // rows [4096, ..): after the forward's and the backward's
-  p.mode = env_int("BAGS_AR_MODE", 0);
+  p.mode = env_int("BAGS_AR_MODE", 3);   // relaxed first-barrier store + relaxed polling: -3..4 us per exchange
   if (count == 0) return BAGS_OK;
   // enough threads to keep one vector per thread and unroll slot in flight, at most kArMaxBlocks blocks;
   // every rank must launch the same grid: it depends only on (count, world, max_blocks) and the environment
@@ -1029,11 +1082,10 @@ extern "C" int bags_grad_allreduce(void* const* peer_bufs_host, void* mc_buf, lo
   long long blocks = (per_rank + static_cast<long long>(threads) * 4 - 1) / (static_cast<long long>(threads) * 4);
   if (blocks < 1) blocks = 1;
   const bool mm = p.mc != nullptr && !env_int("BAGS_AR_NO_MULTIMEM", 0);
-  // Default grid: the multimem path runs on few blocks -- its system-scope fences and switch round trips disturb
-  // co-resident GEMM CTAs, and an exchange that overlaps the next step is not latency-critical (N = 2, overlapped:
-  // 16 blocks 60.5 us/step, 155 blocks 64.2; profiles/r01_bench_2gpu_v18_variants.log); plain peer ld/st keeps one
-  // vector per thread in flight (16 blocks: 73.1 us/step, 155 blocks: 64.8).
-  if (max_blocks <= 0) max_blocks = env_int("BAGS_AR_MAX_BLOCKS", mm ? 16 : kArMaxBlocks);
+  // Default grid (measured inside the step at 2 ranks, profiles/r02_exchange_2gpu.md): one block per SM on the multimem
+  // path (a 16-block grid, right for an exchange hidden under the NEXT step in round 1, costs 2x inside the step); the
+  // plain peer path keeps one vector per thread in flight.
+  if (max_blocks <= 0) max_blocks = env_int("BAGS_AR_MAX_BLOCKS", mm ? 148 : kArMaxBlocks);
   if (max_blocks <= 0 || max_blocks > kArMaxBlocks) max_blocks = kArMaxBlocks;
   if (blocks > max_blocks) blocks = max_blocks;
   const bool epoch = env_int("BAGS_AR_EPOCH", 1) != 0;

@@ -31,6 +31,9 @@ struct BwdFusedParams {
   // bwd_prep_kernel ran before this one (programmatic dependent launch).
   BwdPrepParams prep; int prep_jobs; unsigned int* sync;
   int dx_uniform_ok;   // gout given and tmap_w valid: dX units may read W and scale by gout[0] when gout is uniform
+  int wait_dz;         // the producer waits (griddepcontrol.wait) before its first load: dz comes from the preceding kernel
+  int dw_needs_prep;   // dW epilogues wait for preparation (zeroed dW / column-sum partials); 0: dW was zeroed by the
+                       // forward's clear hook and the column sums come from the forward as well
   long long* timing;
 };
 
@@ -157,7 +160,7 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
       uint32_t phase = 0;
       bool waited = false;
       const bool inkernel = p.prep_jobs > 0;
-      if (inkernel) pdl_wait();   // dz comes from the forward kernel (no preparation kernel in between)
+      if (p.wait_dz) pdl_wait();   // dz comes from the forward kernel (no preparation kernel in between)
       // equal per-bin upstream gradients (the usual case: every bin's loss has weight 1): dX = g0 * dz W, so the
       // scaled copy W' is neither made nor waited for
       float g0 = 1.f;
@@ -318,8 +321,8 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
       float scale = dx_scale;
       if (un.is_dw) {
         if (!waited) {   // dW was zeroed / column-sum partials were made by bwd_prep or by every CTA's jobs
-          if (inkernel) { if (lane == 0) wait_grid_jobs(p.sync, TICKET ? static_cast<unsigned int>(p.prep_jobs) : gridDim.x); __syncwarp(); __threadfence(); }
-          else pdl_wait();
+          if (inkernel && p.dw_needs_prep) { if (lane == 0) wait_grid_jobs(p.sync, TICKET ? static_cast<unsigned int>(p.prep_jobs) : gridDim.x); __syncwarp(); __threadfence(); }
+          else pdl_wait();   // (the zeroed dW / the forward's column sums come from the preceding kernel)
           waited = true;
         }
         scale = 0.f;

@@ -55,6 +55,10 @@ struct FusedFwdParams {
   int want_dz;
   long long* timing;        // debug timeline [grid][8] or nullptr
   int dbg;                  // test hook: bit0 skip dz stores, bit2 skip column sums
+  // optional: a buffer the idle epilogue warps set to zero while the MMAs run (the caller's dW: the backward's split-K
+  // red.add then needs no zeroing job and, with `colsum` taken from here too, no preparation at all)
+  float4* clear;
+  long long clear_vecs;
 };
 
 template <bool TF32>
@@ -371,6 +375,12 @@ bags_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 
     // ===================== epilogue, part 1: row info (overlaps the mainloop) + pass A ==========
     pdl_wait();   // masks / avg come from the preceding sampler kernel (programmatic dependent launch)
+    if (p.clear != nullptr) {   // (a write: only after the wait -- the buffer may still be in use by an earlier kernel)
+      const long long stride = static_cast<long long>(gridDim.x) * (32 * Cfg::EPI_WARPS);
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (long long i = static_cast<long long>(blockIdx.x) * (32 * Cfg::EPI_WARPS) + (threadIdx.x - 64); i < p.clear_vecs; i += stride)
+        p.clear[i] = zero4;
+    }
     if (cg == 0) {
       long long lab = 0;
       if (row < p.N) lab = __ldg(p.labels + row);

@@ -24,8 +24,8 @@
 namespace bags {
 
 enum EpiMode : int {
-  EPI_STORE_F32 = 0,   // out fp32 = acc (+ bias[n])
-  EPI_STORE_BF16 = 1,  // out bf16 = acc
+  EPI_STORE_F32 = 0,   // out fp32 = act(acc + bias[n])          act = ReLU when GemmParams::relu, else identity
+  EPI_STORE_BF16 = 1,  // out bf16 = act(acc + bias[n])
   EPI_RED_F32 = 2,     // out fp32 += rowscale(m) * acc   (split-K via red.global)
 };
 
@@ -37,7 +37,9 @@ struct GemmParams {
   int kblocks_total;   // ceil(K / BLOCK_K)
   void* out;           // [M, ldo]
   long long ldo;       // elements
-  const float* bias;   // [N] or nullptr                    (EPI_STORE_F32)
+  const float* bias;   // [N] or nullptr                    (EPI_STORE_F32 / EPI_STORE_BF16)
+  int relu;            // 1: max(., 0) after the bias         (EPI_STORE_F32 / EPI_STORE_BF16; the shared-FC trunk,
+                       //    convfc_bbox_head.py:138-143)
   // EPI_RED_F32: per-row scale = gscale[group(m)], groups = [gstart, gstart+glen)
   const float* gscale; // device [G] or nullptr (=> 1.0)
   int G;
@@ -302,11 +304,23 @@ bags_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 8; ++j) {  // 16-byte chunk j = 8 bf16 = columns 8j..8j+7
             const uint32_t* src = (j < 4) ? (v + 8 * j) : (v2 + 8 * (j - 4));
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(src[e]);
+            if (p.bias != nullptr) {   // (all rows of the warp read the same addresses: one broadcast transaction each)
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (n + 8 * j + e < p.N) f[e] += __ldg(p.bias + n + 8 * j + e);
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+            }
             uint4 r;
-            r.x = pack_bf16x2(__uint_as_float(src[0]), __uint_as_float(src[1]));
-            r.y = pack_bf16x2(__uint_as_float(src[2]), __uint_as_float(src[3]));
-            r.z = pack_bf16x2(__uint_as_float(src[4]), __uint_as_float(src[5]));
-            r.w = pack_bf16x2(__uint_as_float(src[6]), __uint_as_float(src[7]));
+            r.x = pack_bf16x2(f[0], f[1]);
+            r.y = pack_bf16x2(f[2], f[3]);
+            r.z = pack_bf16x2(f[4], f[5]);
+            r.w = pack_bf16x2(f[6], f[7]);
             rowp[j ^ (lane & 7)] = r;
           }
         } else {
@@ -324,6 +338,7 @@ bags_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 if (n + 4 * j + 1 < p.N) r.y += __ldg(p.bias + n + 4 * j + 1);
                 if (n + 4 * j + 2 < p.N) r.z += __ldg(p.bias + n + 4 * j + 2);
               }
+              if (p.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
             } else {
               r.x *= scale; r.y *= scale; r.z *= scale; r.w *= scale;
             }

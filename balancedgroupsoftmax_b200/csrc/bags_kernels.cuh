@@ -742,4 +742,35 @@ cast_bf16_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __
   }
 }
 
+// Backward of y = act(x W^T + b) up to the two contractions (shared FCs / fc_reg of the head's trunk,
+// convfc_bbox_head.py:138-143,167): g = (y > 0 ? dy : 0) for a ReLU layer (y == nullptr: g = dy), cast to the GEMM
+// operand dtype with a padded leading dimension.  HBM-bound elementwise pass: reads dy (+ y), writes g.
+template <typename TDY, typename TY, bool OUT_BF16>
+__global__ void __launch_bounds__(256)
+act_bwd_kernel(const TDY* __restrict__ dy, long long lddy, const TY* __restrict__ y, long long ldy,
+               void* __restrict__ g, long long ldg, int rows, int cols) {
+  const long long quads = static_cast<long long>(rows) * (cols / 4);
+  for (long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < quads;
+       q += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(q / (cols / 4)), c = static_cast<int>(q % (cols / 4)) * 4;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = static_cast<float>(dy[static_cast<long long>(r) * lddy + c + e]);
+    if (y != nullptr) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (!(static_cast<float>(y[static_cast<long long>(r) * ldy + c + e]) > 0.f)) v[e] = 0.f;
+    }
+    if (OUT_BF16) {
+      uint2 o;
+      o.x = pack_bf16x2(v[0], v[1]);
+      o.y = pack_bf16x2(v[2], v[3]);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g) + static_cast<long long>(r) * ldg + c) = o;
+    } else {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(g) + static_cast<long long>(r) * ldg + c) =
+          make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
 }  // namespace bags

@@ -445,6 +445,13 @@ class GSBBoxHeadWith0(SharedFCBBoxHead):
         cd = _cfg_get(gs_config, 'compute_dtype', os.environ.get('BAGS_COMPUTE_DTYPE', 'bf16'))
         self.compute_dtype = {'bf16': torch.bfloat16, 'bfloat16': torch.bfloat16, 'fp32': torch.float32,
                               'float32': torch.float32, 'tf32': torch.float32}[str(cd).lower()]
+        # test-time logits: fp32 operands (TF32 products) by default -- a reference fp32 checkpoint scored through bf16
+        # operands moves logits by ~1e-2, which reaches the score_thr / NMS ranking of rare classes
+        ed = _cfg_get(gs_config, 'eval_compute_dtype', os.environ.get('BAGS_EVAL_COMPUTE_DTYPE', 'fp32'))
+        self.eval_compute_dtype = {'bf16': torch.bfloat16, 'bfloat16': torch.bfloat16, 'fp32': torch.float32,
+                                   'float32': torch.float32, 'tf32': torch.float32}[str(ed).lower()]
+        # shared FCs + fc_reg on this library's tcgen05 GEMMs (bias + ReLU in the epilogue) instead of nn.Linear / cuBLAS
+        self.native_trunk = bool(_cfg_get(gs_config, 'native_trunk', os.environ.get('BAGS_NATIVE_TRUNK', '1') != '0'))
         self.sampler = str(_cfg_get(gs_config, 'sampler', 'device'))
         assert self.sampler in ('device', 'numpy')
         self.fuse_loss = bool(_cfg_get(gs_config, 'fuse_loss', True))
@@ -488,13 +495,39 @@ class GSBBoxHeadWith0(SharedFCBBoxHead):
         return dt
 
     # ---- forward ------------------------------------------------------------------------
+    def _active_dtype(self):
+        return self.compute_dtype if self.training else self.eval_compute_dtype
+
     def _fc_cls_logits(self, x_cls):
-        return FcClsFunction.apply(x_cls, self.fc_cls.weight, self.fc_cls.bias, self.compute_dtype)
+        return FcClsFunction.apply(x_cls, self.fc_cls.weight, self.fc_cls.bias, self._active_dtype())
+
+    def _use_native_trunk(self, x) -> bool:
+        return (self.native_trunk and x.is_cuda and not self.with_avg_pool and self.num_shared_fcs > 0
+                and self.num_cls_fcs == 0 and self.num_reg_fcs == 0)
+
+    def _trunk(self, x):
+        """convfc_bbox_head.py:132-160 for the FC-only configuration the BAGS configs use: flatten -> (Linear + ReLU) x
+        num_shared_fcs, each one LinearActFunction (tcgen05 GEMM, bias + ReLU in its epilogue; the activations travel
+        in the operand dtype)."""
+        if not self._use_native_trunk(x):
+            return super()._trunk(x)
+        cd = self._active_dtype()
+        act_dtype = torch.bfloat16 if cd == torch.bfloat16 else torch.float32
+        x = x.reshape(x.size(0), -1)
+        for fc in self.shared_fcs:
+            x = ops.LinearActFunction.apply(x, fc.weight, fc.bias, True, cd, act_dtype)
+        return x, x
+
+    def _fc_reg(self, x_reg):
+        if self.native_trunk and x_reg.is_cuda:
+            return ops.LinearActFunction.apply(x_reg, self.fc_reg.weight, self.fc_reg.bias, False, self._active_dtype(),
+                                               torch.float32)
+        return self.fc_reg(x_reg)
 
     @auto_fp16()
     def forward(self, x):
         x_cls, x_reg = self._trunk(x)
-        bbox_pred = self.fc_reg(x_reg) if self.with_reg else None
+        bbox_pred = self._fc_reg(x_reg) if self.with_reg else None
         if not self.with_cls:
             return None, bbox_pred
         if self.training and self.fuse_loss and torch.is_grad_enabled():

@@ -15,6 +15,7 @@ raises if the inputs are not CUDA tensors or the extension is missing.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional, Tuple
 
@@ -218,7 +219,7 @@ def fused_eligible(dt: DeviceTables) -> bool:
 
 def fused_fwd(x, w, bias, labels, dt: DeviceTables, wmask, avg, logits: Optional[torch.Tensor] = None,
               want_dz: bool = True, want_lse: bool = False, materialize: Optional[bool] = None,
-              want_colsum: bool = False):
+              want_colsum: bool = False, clear: Optional[torch.Tensor] = None):
     """bags_fwd: fc_cls + grouped CE in one ABI call.  Returns (loss, logits | None, lse, dz, colsum).
 
     By default (``logits is None`` and the bin table is eligible) the fused kernel runs and no logits
@@ -251,7 +252,20 @@ def fused_fwd(x, w, bias, labels, dt: DeviceTables, wmask, avg, logits: Optional
             colsum = torch.empty((max((N + 127) // 128, 1), Cc), dtype=torch.float32, device=dev)
     ws = _workspace(dev)
     wmask = _weights_arg(wmask)
-    entry = nat.lib().bags_fwd_w if (wmask is not None and wmask.dtype == torch.float32) else nat.lib().bags_fwd
+    wfloat = wmask is not None and wmask.dtype == torch.float32
+    if clear is not None and not wfloat:
+        # ``clear``: a contiguous buffer (the caller's dW) that the kernel zeroes while its MMAs run
+        assert clear.is_contiguous() and (clear.numel() * clear.element_size()) % 16 == 0
+        nat.check(nat.lib().bags_fwd_ex(
+            x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), nat.ptr(bias), labels.data_ptr(),
+            dt.label2bin.data_ptr(), dt.slices_host, nat.ptr(wmask), nat.ptr(avg), N, K, Cc, dt.G, dt.num_classes,
+            _dtype_code(x.dtype), nat.ptr(logits), logits.stride(0) if logits is not None else 0, loss.data_ptr(),
+            nat.ptr(lse), nat.ptr(dz), ldd, nat.ptr(colsum), colsum.shape[0] if colsum is not None else 0, ws.data_ptr(),
+            ws.numel(), clear.data_ptr(), clear.numel() * clear.element_size(), _stream_ptr(dev)), 'bags_fwd_ex')
+        return loss, logits, lse, dz, colsum
+    if clear is not None:
+        clear.zero_()
+    entry = nat.lib().bags_fwd_w if wfloat else nat.lib().bags_fwd
     nat.check(entry(
         x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), nat.ptr(bias), labels.data_ptr(),
         dt.label2bin.data_ptr(), dt.slices_host, nat.ptr(wmask), nat.ptr(avg), N, K, Cc, dt.G, dt.num_classes,
@@ -269,9 +283,10 @@ def bwd_scratch(w: torch.Tensor) -> torch.Tensor:
 
 def fused_bwd(dz, x, w, gout, dt: DeviceTables, colsum=None, need_dw=True, need_db=True, need_dx=True,
               dW: Optional[torch.Tensor] = None, dX: Optional[torch.Tensor] = None,
-              wscratch: Optional[torch.Tensor] = None, db: Optional[torch.Tensor] = None):
+              wscratch: Optional[torch.Tensor] = None, db: Optional[torch.Tensor] = None, dw_prezeroed: bool = False):
     """bags_bwd: (dW fp32 [C,K] | None, db fp32 [C] | None, dX [N,K] operand dtype | None)   (a8).
-    ``colsum`` (forward's column-sum partials) is optional; without it db is recomputed from dz."""
+    ``colsum`` (forward's column-sum partials) is optional; without it db is recomputed from dz.
+    ``dw_prezeroed``: the given ``dW`` is already zero (``fused_fwd(clear=dW)``): no zeroing job in the backward."""
     _require_cuda(dz, x, w, gout, colsum)
     x, w = _row_major(x), _row_major(w)
     N, K = x.shape
@@ -290,13 +305,13 @@ def fused_bwd(dz, x, w, gout, dt: DeviceTables, colsum=None, need_dw=True, need_
     if gout is not None:
         gout = gout.contiguous()
         assert gout.dtype == torch.float32 and gout.numel() == dt.G
-    nat.check(nat.lib().bags_bwd(
+    nat.check(nat.lib().bags_bwd_ex(
         dz.data_ptr(), dz.stride(0), x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), nat.ptr(gout),
         dt.slices_host, nat.ptr(colsum), (colsum.shape[0] if colsum.dim() == 2 else 1) if colsum is not None else 0,
         nat.ptr(dW) if need_dw else None, dW.stride(0) if need_dw else 0,
         nat.ptr(db), nat.ptr(dX) if need_dx else None, dX.stride(0) if need_dx else 0,
         nat.ptr(wscratch), wscratch.numel() * wscratch.element_size() if wscratch is not None else 0,
-        N, K, Cc, dt.G, _dtype_code(x.dtype), _stream_ptr(dev)), 'bags_bwd')
+        N, K, Cc, dt.G, _dtype_code(x.dtype), 1 if (dw_prezeroed and need_dw) else 0, _stream_ptr(dev)), 'bags_bwd')
     return (dW if need_dw else None), db, (dX if need_dx else None)
 
 
@@ -375,7 +390,120 @@ def gemm_probe(a, a_mn: bool, b, b_mn: bool, M: int, N: int, K: int, block_n: in
     return out
 
 
+# --------------------------------------------------------------------------- the trunk's linear layers
+def linear_act(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], relu: bool,
+               out_dtype: Optional[torch.dtype] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[N,C] = act(x @ w^T + bias), act = ReLU or identity, on the tcgen05 GEMM (convfc_bbox_head.py:138-143,167).
+    x and w share the operand dtype (bf16, or fp32 = TF32 products); out is fp32 or (bf16 operands) bf16."""
+    _require_cuda(x, w, bias)
+    x, w = _row_major(x), _row_major(w)
+    if x.dtype != w.dtype:
+        raise nat.BagsNativeError('x (%s) and w (%s) must share a dtype' % (x.dtype, w.dtype))
+    N, K = x.shape
+    Cc = w.shape[0]
+    if out_dtype is None:
+        out_dtype = x.dtype
+    if out is None:
+        out = torch.empty((N, Cc), dtype=out_dtype, device=x.device)
+    if bias is not None:
+        bias = bias.contiguous()
+        assert bias.dtype == torch.float32
+    nat.check(nat.lib().bags_linear_act_fwd(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), nat.ptr(bias),
+                                            out.data_ptr(), out.stride(0), N, K, Cc, _dtype_code(x.dtype),
+                                            _dtype_code(out.dtype), 1 if relu else 0, _stream_ptr(x.device)),
+              'bags_linear_act_fwd')
+    return out
+
+
+def act_bwd(dy: torch.Tensor, y: Optional[torch.Tensor], g_dtype: torch.dtype) -> torch.Tensor:
+    """g [rows, pad64(cols)] = (y > 0 ? dy : 0) in ``g_dtype`` (y None: a cast of dy): the A operand of the layer's
+    backward contractions, with the padded leading dimension bags_bwd wants."""
+    _require_cuda(dy, y)
+    dy = _row_major(dy)
+    rows, cols = dy.shape
+    g = torch.empty((rows, pad_cols(cols)), dtype=g_dtype, device=dy.device)
+    if y is not None:
+        y = _row_major(y)
+    nat.check(nat.lib().bags_act_bwd(dy.data_ptr(), dy.stride(0), _dtype_code(dy.dtype), nat.ptr(y),
+                                     y.stride(0) if y is not None else 0,
+                                     _dtype_code(y.dtype) if y is not None else nat.DTYPE_F32, g.data_ptr(), g.stride(0),
+                                     _dtype_code(g_dtype), rows, cols, _stream_ptr(dy.device)), 'bags_act_bwd')
+    return g
+
+
+_operand_cache: Dict[int, tuple] = {}   # id(parameter) -> (weakref to it, version, bf16 copy)
+
+
+def _bf16_operand(t: torch.Tensor) -> torch.Tensor:
+    """bf16 copy of an fp32 master parameter, re-made only when the parameter changed (its version counter moves with
+    every in-place optimizer update) -- shared_fcs.0.weight alone is 51 MB."""
+    import weakref
+    if t.dtype == torch.bfloat16:
+        return _row_major(t)
+    key = id(t)
+    hit = _operand_cache.get(key)
+    if hit is not None and hit[0]() is t and hit[1] == t._version and hit[2].device == t.device:
+        return hit[2]
+    c = cast_bf16(_row_major(t.detach().float()))
+    if len(_operand_cache) > 64:      # parameters that went away
+        for k in [k for k, v in _operand_cache.items() if v[0]() is None]:
+            del _operand_cache[k]
+    _operand_cache[key] = (weakref.ref(t), t._version, c)
+    return c
+
+
+def _single_slice_tables(cols: int, device) -> DeviceTables:
+    return DeviceTables(1, 1, cols, torch.zeros(1, 1, dtype=torch.int32, device=device),
+                        torch.zeros(1, dtype=torch.int32, device=device), nat.int32_array([0, cols]),
+                        np.array([[0, cols]], dtype=np.int64))
+
+
+class LinearActFunction(torch.autograd.Function):
+    """y = act(x W^T + b) for the head's shared FCs (ReLU) and fc_reg (identity) -- nn.Linear (+ nn.ReLU) of the
+    reference (convfc_bbox_head.py:138-143,167) on this library's tcgen05 GEMMs, forward and backward:
+
+    forward : bags_linear_act_fwd (bias + activation in the GEMM epilogue; bf16 output feeds the next layer)
+    backward: bags_act_bwd (ReLU mask + cast) -> bags_bwd (dW = g^T x, db, dX = g W in one merged launch)"""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu, compute_dtype, out_dtype):
+        _require_cuda(x, weight, bias)
+        xin = x.detach()
+        if compute_dtype == torch.bfloat16:
+            xc = _row_major(xin) if xin.dtype == torch.bfloat16 else cast_bf16(_row_major(xin.float()))
+            wc = _bf16_operand(weight)
+        elif compute_dtype == torch.float32:
+            xc, wc = _row_major(xin.float()), _row_major(weight.detach().float())
+        else:
+            raise nat.BagsNativeError('compute_dtype must be torch.bfloat16 or torch.float32')
+        b32 = None if bias is None else bias.detach().float().contiguous()
+        y = linear_act(xc, wc, b32, bool(relu), out_dtype=out_dtype)
+        ctx.relu = bool(relu)
+        ctx.meta = (x.dtype, weight.dtype, None if bias is None else bias.dtype)
+        if any(ctx.needs_input_grad[:3]):
+            ctx.save_for_backward(xc, wc, y if relu else None)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        xc, wc, y = ctx.saved_tensors
+        xd, wd, bd = ctx.meta
+        g = act_bwd(grad_out.detach(), y, xc.dtype)
+        dt1 = _single_slice_tables(wc.shape[0], xc.device)
+        dW, db, dX = fused_bwd(g, xc, wc, None, dt1, None, need_dw=ctx.needs_input_grad[1],
+                               need_db=ctx.needs_input_grad[2] and bd is not None, need_dx=ctx.needs_input_grad[0])
+        return (None if dX is None else dX.to(xd), None if dW is None else dW.to(wd),
+                None if db is None else db.to(bd), None, None, None)
+
+
 # --------------------------------------------------------------------------- autograd
+# where the backward's preparation work runs: 1 = dW is zeroed by the fused forward kernel (idle epilogue warps)
+PREP_IN_FORWARD = os.environ.get('BAGS_PREP_IN_FORWARD', '1') != '0'
+# 1 = the bias-gradient column sums come from the forward's epilogue as well (otherwise a job of the backward kernel)
+FWD_COLSUM = os.environ.get('BAGS_FWD_COLSUM', '0') == '1'
+
+
 class GroupSoftmaxFunction(torch.autograd.Function):
     """losses[G] = BAGS(fc_cls(x)) with a fused backward.
 
@@ -405,8 +533,16 @@ class GroupSoftmaxFunction(torch.autograd.Function):
             raise nat.BagsNativeError('compute_dtype must be torch.bfloat16 or torch.float32')
         b32 = None if bias is None else bias.detach().float().contiguous()
         need_grad = any(ctx.needs_input_grad[:3])
+        # dW is allocated here and zeroed by the forward kernel's idle epilogue warps (its split-K red.add in the
+        # backward then needs no zeroing job); BAGS_FWD_COLSUM=1 also takes the bias-gradient partials from the forward
+        dW = None
+        if need_grad and ctx.needs_input_grad[1] and logits_out is None and PREP_IN_FORWARD:
+            dW = torch.empty((wc.shape[0], wc.shape[1]), dtype=torch.float32, device=xc.device)
         loss, _, _, dz, colsum = fused_fwd(xc, wc, b32, labels, dt, wmask, avg, logits=logits_out,
-                                           want_dz=need_grad)
+                                           want_dz=need_grad, clear=dW,
+                                           want_colsum=(dW is not None and FWD_COLSUM and bias is not None))
+        ctx.dW = dW
+        ctx.colsum = colsum if dW is not None else None
         ctx.dt = dt
         ctx.x_dtype = x.dtype
         ctx.w_dtype = weight.dtype
@@ -422,8 +558,10 @@ class GroupSoftmaxFunction(torch.autograd.Function):
         xc, wc, dz = ctx.saved_tensors
         need_dx, need_dw, need_db = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         gout = grad_loss.detach().to(torch.float32).contiguous()
-        dW, db, dX = fused_bwd(dz, xc, wc, gout, ctx.dt, None, need_dw=need_dw,
-                               need_db=(need_db and ctx.has_bias), need_dx=need_dx)
+        dW0, ctx.dW = ctx.dW, None                      # (a second backward through a retained graph zeroes again)
+        dW, db, dX = fused_bwd(dz, xc, wc, gout, ctx.dt, ctx.colsum, need_dw=need_dw,
+                               need_db=(need_db and ctx.has_bias), need_dx=need_dx,
+                               dW=dW0 if need_dw else None, dw_prezeroed=dW0 is not None)
         if dX is not None and dX.dtype != ctx.x_dtype:
             dX = dX.to(ctx.x_dtype)
         if dW is not None and dW.dtype != ctx.w_dtype:

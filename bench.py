@@ -419,28 +419,43 @@ def run_ours(args):
     def one_step(s):
         seed_ctr[0] += 1
         wmask, avg = ops.sample_others(s['labels'], dt, RATIO, seed_ctr[0])
+        prez = args.prep != 'bwd' and not args.unfused
         loss, _, _, dz, colsum = ops.fused_fwd(s['x'], s['w'], s['bias'], s['labels'], dt, wmask, avg,
-                                               logits=(s['logits'] if args.unfused else None))
+                                               logits=(s['logits'] if args.unfused else None),
+                                               clear=(s['dW'] if prez else None),
+                                               want_colsum=(args.prep == 'fwd-zero-colsum' and not args.unfused))
         if split_bwd:
             # in-step schedule with overlap ("launch as soon as the dW epilogue finishes, overlap with the dX
             # GEMM"): dW + db first, then the exchange on a side stream WHILE dX runs; joined before the step ends, so the
             # reduced gradients are complete before the next forward starts
-            ops.fused_bwd(dz, s['x'], s['w'], gout, dt, colsum, need_dx=False, dW=s['dW'], wscratch=s['wscratch'], db=s['db'])
+            ops.fused_bwd(dz, s['x'], s['w'], gout, dt, colsum, need_dx=False, dW=s['dW'], wscratch=s['wscratch'], db=s['db'],
+                          dw_prezeroed=prez)
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(dev))
             side_stream.wait_event(ev)
-            with torch.cuda.stream(side_stream):
+
+            def do_exchange(st):
                 if world > 1:
                     s['exchange']()
                 elif fake is not None:
-                    nat.check(nat.lib().bags_debug_spin(fake[0], fake[1], fake[2], side_stream.cuda_stream), 'bags_debug_spin')
-            ops.fused_bwd(dz, s['x'], s['w'], gout, dt, None, need_dw=False, need_db=False, dX=s['dX'],
-                          wscratch=s['wscratch2'])
+                    nat.check(nat.lib().bags_debug_spin(fake[0], fake[1], fake[2], st.cuda_stream), 'bags_debug_spin')
+
+            def do_dx():
+                ops.fused_bwd(dz, s['x'], s['w'], gout, dt, None, need_dw=False, need_db=False, dX=s['dX'],
+                              wscratch=s['wscratch2'])
+            if args.dx_side:    # the exchange stays on the launching stream (programmatic dependent launch after dW); dX forks
+                with torch.cuda.stream(side_stream):
+                    do_dx()
+                do_exchange(torch.cuda.current_stream(dev))
+            else:
+                with torch.cuda.stream(side_stream):
+                    do_exchange(side_stream)
+                do_dx()
             torch.cuda.current_stream(dev).wait_stream(side_stream)
             last['loss'] = loss
             return loss
         ops.fused_bwd(dz, s['x'], s['w'], gout, dt, colsum, dW=s['dW'], dX=s['dX'], wscratch=s['wscratch'],
-                      db=s['db'])
+                      db=s['db'], dw_prezeroed=prez)
         if world > 1:
             # mean over ranks of dW, db (dist_utils.py:9-41).  'overlap': on a side stream, concurrently with the next
             # step's kernels (which use another member of the buffer pool); every exchange still completes inside the
@@ -885,6 +900,12 @@ def main():
                          "step's forward (default: what an SGD step needs -- the optimizer reads the reduced gradients "
                          'before the next forward reads W; mmdet/core/utils/dist_utils.py:51-58), or the relaxed schedule '
                          'on a side stream under the NEXT step (not a valid training schedule; kept for comparison)')
+    ap.add_argument('--prep', default='fwd-zero', choices=['bwd', 'fwd-zero', 'fwd-zero-colsum'],
+                    help="where the backward's preparation runs: 'bwd' = jobs inside the backward kernel (zero dW, column sums); "
+                         "'fwd-zero' = dW is zeroed by the forward kernel's idle epilogue warps; 'fwd-zero-colsum' = the "
+                         'bias-gradient column sums come from the forward epilogue as well (no preparation left)')
+    ap.add_argument('--dx-side', action='store_true',
+                    help='instep-overlap-dx: fork the dX launch to the side stream and keep the exchange on the launching stream')
     ap.add_argument('--ar-blocks', type=int, default=0, help='N > 1: grid size limit of the peer-memory exchange kernel (0 = default)')
     ap.add_argument('--allreduce', default=os.environ.get('BAGS_ALLREDUCE', 'peer'), choices=['peer', 'nccl'],
                     help='N > 1: gradient exchange by the peer-memory kernel (default) or NCCL')

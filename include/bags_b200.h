@@ -155,6 +155,23 @@ int bags_bwd(const void* dz, long long ldd, const void* x, long long ldx, const 
              int colsum_tiles, float* dW, long long lddw, float* db, void* dX, long long lddx,
              void* wscratch, size_t wscratch_bytes, int N, int K, int C, int G, int dtype, void* stream);
 
+/* bags_fwd with a "clear" hook: the fused kernel's idle epilogue warps set `clear_bytes` bytes at `clear` (16-byte
+ * aligned, a multiple of 16; typically the caller's dW) to zero while the MMAs run.  Together with `colsum` this lets
+ * bags_bwd_ex run without any preparation work (no zeroing job, no column-sum job). */
+int bags_fwd_ex(const void* x, long long ldx, const void* w, long long ldw, const float* bias,
+                const int64_t* labels, const int32_t* label2bin, const int32_t* slices_host,
+                const uint8_t* wmask, const float* avg, int N, int K, int C, int G, int classes, int dtype,
+                float* logits, long long ldz, float* loss, float* lse, void* dz, long long ldd, float* colsum,
+                int colsum_tiles, void* workspace, size_t workspace_bytes, void* clear, size_t clear_bytes,
+                void* stream);
+
+/* bags_bwd with flags: BAGS_BWD_DW_PREZEROED = dW is already zero on entry (stream-ordered), e.g. by bags_fwd_ex. */
+#define BAGS_BWD_DW_PREZEROED 1
+int bags_bwd_ex(const void* dz, long long ldd, const void* x, long long ldx, const void* w,
+                long long ldw, const float* gout, const int32_t* slices_host, const float* colsum,
+                int colsum_tiles, float* dW, long long lddw, float* db, void* dX, long long lddx,
+                void* wscratch, size_t wscratch_bytes, int N, int K, int C, int G, int dtype, int flags, void* stream);
+
 /* scores[N,classes]: scores[:,0] = softmax(z[:,slice_0])[:,0];
  * scores[:,c] = softmax(z[:,slice_0])[:,1] * softmax(z[:,slice_g])[:,j] where cls2col[c] = start_g + j.
  * cls2col: int32 [classes] (device), -1 => score 0. */
@@ -201,6 +218,18 @@ int bags_class_nms_dense(const float* boxes, int box_cols, const int32_t* order,
 
 /* test hook: launch `blocks` x `threads` threads that wait `micros` microseconds and exit */
 int bags_debug_spin(int blocks, int threads, int micros, void* stream);
+
+/* The head's trunk, the step before the path (convfc_bbox_head.py:138-143 shared FCs + ReLU, :167 fc_reg):
+ * out[N,C] = act(x[N,K] W[C,K]^T + bias), act = ReLU when relu != 0, on the tcgen05 GEMM of bags_linear_fwd.
+ * dtype = operand dtype of x and W; out_dtype: BAGS_DTYPE_F32, or BAGS_DTYPE_BF16 (bf16 operands only: feeds the next layer). */
+int bags_linear_act_fwd(const void* x, long long ldx, const void* w, long long ldw, const float* bias,
+                        void* out, long long ldo, int N, int K, int C, int dtype, int out_dtype, int relu,
+                        void* stream);
+
+/* Its backward up to the contractions: g[rows, cols] = (y > 0 ? dy : 0) in dtype g_dtype (y == NULL: a plain cast of dy);
+ * dW / db / dX then come from bags_bwd(g, ...) with a single slice (0, cols) and gout == NULL.  cols % 4 == 0. */
+int bags_act_bwd(const void* dy, long long lddy, int dy_dtype, const void* y, long long ldy, int y_dtype,
+                 void* g, long long ldg, int g_dtype, int rows, int cols, void* stream);
 
 /* dst[rows, cols] (bf16, leading dim ldd) = bf16(src[rows, cols] fp32, leading dim lds); cols % 4 == 0 */
 int bags_cast_bf16(const float* src, long long lds, void* dst, long long ldd, int rows, int cols,

@@ -521,3 +521,34 @@ def test_split_backward_matches_oracle(env, N, mode, gname):
     torch.cuda.synchronize()
     assert none_dx is None and none_dw is None and none_db is None
     _check_vs_oracle(ops, dt, l2b, ps, x, W, b, labels, remapped, mode, gout, loss, dW, db, dX)
+
+
+@pytest.mark.parametrize('fwd_colsum', [False, True], ids=['bwdcolsum', 'fwdcolsum'])
+@pytest.mark.parametrize('mode', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
+@pytest.mark.parametrize('N', [200, 512, 4096])
+def test_preparation_in_forward_matches_oracle(env, N, mode, fwd_colsum):
+    """dW zeroed by the forward kernel's clear hook (bags_fwd_ex) -- and optionally the bias-gradient partials from the
+    forward too -- then bags_bwd_ex(DW_PREZEROED): same gradients as the oracle; the hook really zeroes a dirty buffer."""
+    ops, t, dt, l2b, ps = env
+    x, W, b, labels, remapped = _problem(N, seed=77 + N)
+    gout = GOUTS['nonuniform']
+    wmask = torch.stack([w.to(torch.uint8) for w in remapped[1]]).cuda()
+    avg = ops.mask_avg(wmask)
+    xc, wc = x.cuda().to(mode), W.cuda().to(mode)
+    dW = torch.full((t.num_logits, 1024), 123.0, device='cuda')
+    loss, _, _, dz, colsum = ops.fused_fwd(xc, wc, b.cuda(), labels.cuda(), dt, wmask, avg, clear=dW,
+                                           want_colsum=fwd_colsum)
+    torch.cuda.synchronize()
+    assert dW.abs().max().item() == 0.0
+    g = torch.tensor(gout, device='cuda')
+    _, db, dX = ops.fused_bwd(dz, xc, wc, g, dt, colsum, dW=dW, dw_prezeroed=True)
+    torch.cuda.synchronize()
+    _check_vs_oracle(ops, dt, l2b, ps, x, W, b, labels, remapped, mode, gout, loss, dW, db, dX)
+    # the split launches with a pre-zeroed dW
+    dW2 = torch.full_like(dW, -7.0)
+    loss, _, _, dz, colsum = ops.fused_fwd(xc, wc, b.cuda(), labels.cuda(), dt, wmask, avg, clear=dW2,
+                                           want_colsum=fwd_colsum)
+    _, db2, _ = ops.fused_bwd(dz, xc, wc, g, dt, colsum, dW=dW2, dw_prezeroed=True, need_dx=False)
+    _, _, dX2 = ops.fused_bwd(dz, xc, wc, g, dt, None, need_dw=False, need_db=False)
+    torch.cuda.synchronize()
+    _check_vs_oracle(ops, dt, l2b, ps, x, W, b, labels, remapped, mode, gout, loss, dW2, db2, dX2)
