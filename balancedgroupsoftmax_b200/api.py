@@ -22,12 +22,15 @@ def bags_head_loss(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.T
                    tables: Union[GroupTables, ops.DeviceTables], others_sample_ratio: float = 8.0,
                    compute_dtype: torch.dtype = torch.bfloat16, wmask: Optional[torch.Tensor] = None,
                    avg: Optional[torch.Tensor] = None, seed: Optional[int] = None,
-                   return_logits: bool = False):
+                   return_logits: bool = False, grad_bucket=None):
     """losses[G] (fp32, one per bin, already divided by the per-bin avg_factor).
 
     x [N,K] and weight [C,K] may be fp32 or bf16; ``compute_dtype`` selects bf16 or TF32 tensor-core
     products.  Without ``wmask`` the "others" rows are sampled on the device (``seed`` fixes the draw);
     with ``wmask`` [G,N] uint8 (e.g. recorded from the reference's numpy sampler) it is used as is.
+    ``grad_bucket`` (data-parallel training; ``dist.PeerGradBucket`` / ``dist.NcclGradBucket`` over [(C,K), (C,)]): the
+    backward writes dW / db into the bucket, exchanges them over NVLink as soon as they are complete and computes dX
+    meanwhile; ``weight.grad`` / ``bias.grad`` receive the mean over ranks.
     """
     dt = tables if isinstance(tables, ops.DeviceTables) else ops.DeviceTables.from_tables(tables, x.device)
     if wmask is None:
@@ -39,7 +42,7 @@ def bags_head_loss(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.T
     logits = None
     if return_logits:
         logits = torch.empty((x.shape[0], weight.shape[0]), dtype=torch.float32, device=x.device)
-    loss = ops.GroupSoftmaxFunction.apply(x, weight, bias, labels, dt, wmask, avg, compute_dtype, logits)
+    loss = ops.GroupSoftmaxFunction.apply(x, weight, bias, labels, dt, wmask, avg, compute_dtype, logits, grad_bucket)
     return (loss, logits) if return_logits else loss
 
 
@@ -66,7 +69,7 @@ class GraphedHeadStep(object):
                  tables: Union[GroupTables, ops.DeviceTables], n_rois: int, others_sample_ratio: float = 8.0,
                  compute_dtype: torch.dtype = torch.bfloat16, x_dtype: Optional[torch.dtype] = None,
                  loss_weights: Optional[torch.Tensor] = None, need_dx: bool = True, seed: Optional[int] = None,
-                 exchange=None, stream: Optional[torch.cuda.Stream] = None, warmup: int = 2):
+                 exchange=None, stream: Optional[torch.cuda.Stream] = None, warmup: int = 2, grad_bucket=None):
         dev = weight.device
         if dev.type != 'cuda':
             raise ops.nat.BagsNativeError('GraphedHeadStep runs on a B200 GPU only (weight is on %s)' % dev)
@@ -76,6 +79,9 @@ class GraphedHeadStep(object):
         self.compute_dtype = compute_dtype
         self.loss_weights = None if loss_weights is None else loss_weights.to(dev, torch.float32)
         self.exchange = exchange
+        # data-parallel: dW / db are written into this bucket (dist.PeerGradBucket / NcclGradBucket), exchanged as soon as
+        # they are complete and while dX is computed; weight.grad / bias.grad become the bucket's views (mean over ranks)
+        self.grad_bucket = grad_bucket
         self.seed = int(seed if seed is not None else
                         (torch.initial_seed() * 0x9E3779B97F4A7C15 + next(_seed_counter))) & 0xFFFFFFFFFFFFFFFF
         K = weight.shape[1]
@@ -108,7 +114,7 @@ class GraphedHeadStep(object):
     def _body(self):
         wmask, avg = ops.sample_others(self.labels, self.dt, self.ratio, self.seed, seed_step=self.seed_step)
         losses = ops.GroupSoftmaxFunction.apply(self.x, self.weight, self.bias, self.labels, self.dt, wmask, avg,
-                                                self.compute_dtype, None)
+                                                self.compute_dtype, None, self.grad_bucket)
         total = losses.sum() if self.loss_weights is None else (losses * self.loss_weights).sum()
         total.backward()
         if self.exchange is not None:

@@ -971,7 +971,7 @@ extern "C" int bags_bwd_ex(const void* dz, long long ldd, const void* x, long lo
     if (dW == nullptr) mt_auto = (bp.dx_units / 2 >= di.num_sms) ? 2 : 1;   // dX alone: 128-row units fill the machine sooner
     // dW alone: 128 x 256 units.  Filling the machine with 256 x 256 units takes a 7-way split at the benchmark shape, i.e.
     // 35 MB of red.add for a 5 MB result -- the L2 atomic rate (~3 TB/s) then costs more than the larger tile saves
-    if (dX == nullptr) mt_auto = 1;
+    if (dX == nullptr) mt_auto = env_int("BAGS_DW_ONLY_MT", 1);
     if (env_int("BAGS_BWD_MT", mt_auto) == 2) {
       bp.dw_m_tiles = (C + 255) / 256;
       bp.dx_m_tiles = (N + 255) / 256;
@@ -1131,6 +1131,31 @@ extern "C" int bags_debug_spin(int blocks, int threads, int micros, void* stream
   bags_debug_spin_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream_)>>>(1000LL * micros);
   BAGS_CUDA(cudaGetLastError());
   return BAGS_OK;
+}
+
+// test hook: how many clusters of `cluster` CTAs (each `threads` threads + `smem_bytes` dynamic shared memory, i.e. one CTA
+// per SM for the GEMM-sized value) can be resident at once -- the GPC layout decides (148 SMs do not split evenly)
+extern "C" int bags_debug_max_clusters(int cluster, int threads, int smem_bytes) {
+  if (cluster < 1 || cluster > 16 || threads < 32 || threads > 1024 || smem_bytes < 0) return -1;
+  DeviceInfo di;
+  if (device_info(di)) return -1;
+  if (cudaFuncSetAttribute(bags_debug_spin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return -1;
+  }
+  if (cluster > 8) (void)cudaFuncSetAttribute(bags_debug_spin_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(cluster * ((2 * di.num_sms) / cluster)));
+  cfg.blockDim = dim3(static_cast<unsigned>(threads));
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem_bytes);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(cluster); attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = -1;
+  if (cudaOccupancyMaxActiveClusters(&n, bags_debug_spin_kernel, &cfg) != cudaSuccess) { (void)cudaGetLastError(); return -1; }
+  return n;
 }
 
 extern "C" int bags_merge_scores(const float* logits, long long ldz, const int32_t* slices_host,

@@ -229,6 +229,46 @@ class PeerGradBucket(object):
         _native.check(rc, 'bags_grad_allreduce')
 
 
+def _exchange_overlapped(self, side_stream=None):
+    """Start this bucket's exchange on a side stream, ordered after everything launched so far on the current stream
+    (i.e. after the kernel that completed the gradients), and return a ``join()`` that makes the current stream wait
+    for it.  What is launched on the current stream between the two -- the dX contraction -- overlaps the exchange."""
+    dev = self.flat.device
+    cur = torch.cuda.current_stream(dev)
+    if side_stream is None:
+        side_stream = getattr(self, '_side_stream', None)
+        if side_stream is None:
+            side_stream = self._side_stream = torch.cuda.Stream(device=dev)
+    ev = torch.cuda.Event()
+    ev.record(cur)
+    side_stream.wait_event(ev)
+    with torch.cuda.stream(side_stream):
+        self.allreduce_()
+
+    def join():
+        cur.wait_stream(side_stream)
+    return join
+
+
+PeerGradBucket.exchange_overlapped = _exchange_overlapped
+
+
+class NcclGradBucket(object):
+    """The same interface over a plain flat bucket exchanged with NCCL / gloo (the reference's route), for process
+    groups where the peer-memory path is unavailable."""
+
+    def __init__(self, shapes: List[Tuple[int, ...]], device):
+        self.flat, self.views = flat_grad_bucket(shapes, device)
+
+    def allreduce_(self):
+        allreduce_flat_(self.flat)
+
+    def status(self) -> int:
+        return 0
+
+    exchange_overlapped = _exchange_overlapped
+
+
 def make_grad_bucket(shapes: List[Tuple[int, ...]], device, prefer_peer: bool = True, max_blocks: int = 0):
     """(bucket_or_None, flat, views, allreduce_fn): the peer-memory bucket when it can be set up, else a plain bucket
     exchanged with NCCL (same results; the reference's path)."""

@@ -436,6 +436,17 @@ class GSBBoxHeadWith0(SharedFCBBoxHead):
         assert tables.num_bins == num_bins, 'gs_config.num_bins does not match the tables'
         assert tables.num_logits == self.num_classes + num_bins, 'pred_slice does not cover fc_cls outputs'
         self.tables = tables
+        # limits of the native kernels, reported here rather than at the first loss / merge call
+        if num_bins > ops.nat.MAX_BINS:
+            raise ValueError('GSBBoxHeadWith0: %d bins, the native kernels support at most %d' % (num_bins, ops.nat.MAX_BINS))
+        if tables.num_logits % 4 != 0:
+            raise ValueError('GSBBoxHeadWith0: %d logits (classes + bins) -- the native kernels need a multiple of 4 '
+                             '(the 5-bin LVIS tables give 1236); pad the bin table or use 1, 5 or 9 ... bins'
+                             % tables.num_logits)
+        for lb in self.loss_bins:
+            if getattr(lb, 'reduction', 'mean') != 'mean':
+                raise ValueError("GSBBoxHeadWith0: loss_bin.reduction=%r -- the fused path implements the reference's "
+                                 "'mean' (sum / avg_factor, losses/utils.py:26-53)" % (lb.reduction,))
         # plain attributes like the reference (not buffers -> not in the state dict)
         self.label2binlabel = torch.from_numpy(tables.label2binlabel)
         self.pred_slice = torch.from_numpy(tables.pred_slice)

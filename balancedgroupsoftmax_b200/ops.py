@@ -518,7 +518,12 @@ class GroupSoftmaxFunction(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, weight, bias, labels, dt: DeviceTables, wmask, avg, compute_dtype, logits_out):
+    def forward(ctx, x, weight, bias, labels, dt: DeviceTables, wmask, avg, compute_dtype, logits_out, grad_bucket=None):
+        """``grad_bucket`` (optional, data-parallel training): an object with ``views = (dW [C,K] fp32, db [C] fp32)`` living
+        in the ranks' exchange bucket and ``exchange_overlapped()`` -- e.g. ``dist.PeerGradBucket``.  The backward then
+        writes dW / db straight into the bucket, starts the exchange as soon as they are complete and computes dX while
+        the gradients travel (SURVEY.md 8e; the reference exchanges after the whole backward, dist_utils.py:51-58);
+        the returned weight / bias gradients ARE the bucket views, holding the mean over ranks."""
         _require_cuda(x, weight, bias, labels)
         xin = x.detach()
         win = weight.detach()
@@ -536,7 +541,13 @@ class GroupSoftmaxFunction(torch.autograd.Function):
         # dW is allocated here and zeroed by the forward kernel's idle epilogue warps (its split-K red.add in the
         # backward then needs no zeroing job); BAGS_FWD_COLSUM=1 also takes the bias-gradient partials from the forward
         dW = None
-        if need_grad and ctx.needs_input_grad[1] and logits_out is None and PREP_IN_FORWARD:
+        ctx.grad_bucket = grad_bucket if (grad_bucket is not None and need_grad and ctx.needs_input_grad[1]) else None
+        if ctx.grad_bucket is not None:
+            dW = grad_bucket.views[0]
+            assert dW.dtype == torch.float32 and tuple(dW.shape) == (wc.shape[0], wc.shape[1]) and dW.is_contiguous()
+            if logits_out is not None or not PREP_IN_FORWARD:
+                dW.zero_()
+        elif need_grad and ctx.needs_input_grad[1] and logits_out is None and PREP_IN_FORWARD:
             dW = torch.empty((wc.shape[0], wc.shape[1]), dtype=torch.float32, device=xc.device)
         loss, _, _, dz, colsum = fused_fwd(xc, wc, b32, labels, dt, wmask, avg, logits=logits_out,
                                            want_dz=need_grad, clear=dW,
@@ -559,16 +570,32 @@ class GroupSoftmaxFunction(torch.autograd.Function):
         need_dx, need_dw, need_db = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         gout = grad_loss.detach().to(torch.float32).contiguous()
         dW0, ctx.dW = ctx.dW, None                      # (a second backward through a retained graph zeroes again)
-        dW, db, dX = fused_bwd(dz, xc, wc, gout, ctx.dt, ctx.colsum, need_dw=need_dw,
-                               need_db=(need_db and ctx.has_bias), need_dx=need_dx,
-                               dW=dW0 if need_dw else None, dw_prezeroed=dW0 is not None)
+        bucket = ctx.grad_bucket
+        if bucket is not None and need_dw:
+            # dW + db first, straight into the exchange bucket; the exchange starts when they are complete and runs
+            # while the dX contraction does
+            if dW0 is None:
+                bucket.views[0].zero_()
+            db_view = bucket.views[1] if (need_db and ctx.has_bias and len(bucket.views) > 1) else None
+            dW, db, _ = fused_bwd(dz, xc, wc, gout, ctx.dt, ctx.colsum, need_dw=True,
+                                  need_db=(need_db and ctx.has_bias), need_dx=False, dW=bucket.views[0], db=db_view,
+                                  dw_prezeroed=True)
+            join = bucket.exchange_overlapped()
+            dX = None
+            if need_dx:
+                _, _, dX = fused_bwd(dz, xc, wc, gout, ctx.dt, None, need_dw=False, need_db=False, need_dx=True)
+            join()
+        else:
+            dW, db, dX = fused_bwd(dz, xc, wc, gout, ctx.dt, ctx.colsum, need_dw=need_dw,
+                                   need_db=(need_db and ctx.has_bias), need_dx=need_dx,
+                                   dW=dW0 if need_dw else None, dw_prezeroed=dW0 is not None)
         if dX is not None and dX.dtype != ctx.x_dtype:
             dX = dX.to(ctx.x_dtype)
         if dW is not None and dW.dtype != ctx.w_dtype:
             dW = dW.to(ctx.w_dtype)
         if db is not None and db.dtype != ctx.bias_dtype:
             db = db.to(ctx.bias_dtype)
-        return dX, dW, db, None, None, None, None, None, None
+        return dX, dW, db, None, None, None, None, None, None, None
 
 
 class GroupCEFunction(torch.autograd.Function):

@@ -590,21 +590,21 @@ def run_ours(args):
         ev_copied = [torch.cuda.Event() for _ in range(2)]
         ev_free = [torch.cuda.Event() for _ in range(2)]
         ev_loss = [torch.cuda.Event() for _ in range(2)]
+        e2e_bucket = None
         if world > 1:
-            _, e2e_flat, (e2e_dW, e2e_db), e2e_exchange = make_grad_bucket([(C, K_FEAT), (C,)], dev,
-                                                                           prefer_peer=(args.allreduce == 'peer'))
-
-            def exchange():
-                e2e_dW.copy_(w_param.grad)
-                e2e_db.copy_(b_param.grad)
-                e2e_exchange()
-        else:
-            exchange = None
+            # the public data-parallel API: dW / db land in the exchange bucket, the exchange starts when they are complete
+            # and overlaps the dX contraction; weight.grad / bias.grad receive the mean over ranks (dist_utils.py:9-41)
+            from balancedgroupsoftmax_b200.dist import NcclGradBucket
+            e2e_bucket = make_grad_bucket([(C, K_FEAT), (C,)], dev, prefer_peer=(args.allreduce == 'peer'),
+                                          max_blocks=(args.ar_blocks or 48))[0]
+            if e2e_bucket is None:
+                e2e_bucket = NcclGradBucket([(C, K_FEAT), (C,)], dev)
+        exchange = None
         graphed = []
         if not args.e2e_eager_only:
             from balancedgroupsoftmax_b200.api import GraphedHeadStep
             graphed = [GraphedHeadStep(w_param, b_param, dt, n, RATIO, compute_dtype=dtype, x_dtype=dtype,
-                                       exchange=exchange) for _ in range(2)]
+                                       grad_bucket=e2e_bucket) for _ in range(2)]
             if world > 1:
                 dist.barrier()
         xd_eager = [torch.empty(n, K_FEAT, device=dev, dtype=dtype) for _ in range(2)]
@@ -639,10 +639,9 @@ def run_ours(args):
                 xin = xd_eager[b_].detach().requires_grad_(True)
                 w_param.grad = None
                 b_param.grad = None
-                losses = bags_head_loss(xin, w_param, b_param, ld_eager[b_], dt, RATIO, compute_dtype=dtype)
+                losses = bags_head_loss(xin, w_param, b_param, ld_eager[b_], dt, RATIO, compute_dtype=dtype,
+                                        grad_bucket=e2e_bucket)
                 losses.sum().backward()
-                if exchange is not None:
-                    exchange()
             ev_free[b_].record(comp_stream)
             loss_hosts[b_].copy_(losses.detach(), non_blocking=True)
             ev_loss[b_].record(comp_stream)

@@ -218,6 +218,8 @@ int bags_class_nms_dense(const float* boxes, int box_cols, const int32_t* order,
 
 /* test hook: launch `blocks` x `threads` threads that wait `micros` microseconds and exit */
 int bags_debug_spin(int blocks, int threads, int micros, void* stream);
+/* Test hook: the number of `cluster`-CTA clusters (threads, dynamic shared memory per CTA) that can be resident at once. */
+int bags_debug_max_clusters(int cluster, int threads, int smem_bytes);
 
 /* The head's trunk, the step before the path (convfc_bbox_head.py:138-143 shared FCs + ReLU, :167 fc_reg):
  * out[N,C] = act(x[N,K] W[C,K]^T + bias), act = ReLU when relu != 0, on the tcgen05 GEMM of bags_linear_fwd.

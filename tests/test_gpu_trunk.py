@@ -22,12 +22,6 @@ def test_linear_act_forward_backward_vs_torch(N, K, C, relu, mode):
     W = torch.randn(C, K, generator=g) * (1.0 / K ** 0.5)
     b = torch.randn(C, generator=g) * 0.1
     dy = torch.randn(N, C, generator=g)
-    # reference: fp32 torch on the CPU
-    xr, Wr, br = x.clone().requires_grad_(True), W.clone().requires_grad_(True), b.clone().requires_grad_(True)
-    yr = torch.nn.functional.linear(xr, Wr, br)
-    if relu:
-        yr = torch.relu(yr)
-    yr.backward(dy)
     xd = x.cuda().requires_grad_(True)
     Wd = torch.nn.Parameter(W.cuda())
     bd = torch.nn.Parameter(b.cuda())
@@ -35,14 +29,23 @@ def test_linear_act_forward_backward_vs_torch(N, K, C, relu, mode):
     y = ops.LinearActFunction.apply(xd, Wd, bd, relu, mode, out_dtype)
     y.backward(dy.cuda().to(y.dtype))
     torch.cuda.synchronize()
+    # reference: fp32 torch on the CPU.  ReLU is discontinuous: an output within rounding distance of zero may land on the
+    # other side in TF32 / bf16, and each flipped mask entry changes the gradients by O(1) -- so the reference backward
+    # uses THIS run's mask (checked separately below to agree with the fp32 one wherever the fp32 output is clearly
+    # away from zero), which makes the gradient comparison a test of the three contractions, not of the mask's luck.
+    xr, Wr, br = x.clone().requires_grad_(True), W.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    lin = torch.nn.functional.linear(xr, Wr, br)
+    mask = (y.detach().float().cpu() > 0).float() if relu else torch.ones_like(lin)
+    yr = lin * mask
+    yr.backward(dy.to(y.dtype).float())
     tol = 2e-3 if mode == torch.float32 else 1.2e-2      # TF32 / bf16 operand rounding, fp32 accumulation
-    assert y.dtype == out_dtype and rel(y.float(), yr) <= tol
-    assert rel(Wd.grad, Wr.grad) <= tol and rel(bd.grad, br.grad) <= tol and rel(xd.grad, xr.grad) <= tol
+    assert y.dtype == out_dtype and rel(y.float(), torch.relu(lin) if relu else lin) <= tol
+    errs = dict(dW=rel(Wd.grad, Wr.grad), db=rel(bd.grad, br.grad), dX=rel(xd.grad, xr.grad))
+    assert max(errs.values()) <= tol, errs
     if relu:
         assert bool((y >= 0).all())
-        # the ReLU mask is exact wherever the reference is clearly away from zero
-        far = yr.abs() > 0.05
-        assert torch.equal((y.float().cpu() > 0)[far], (yr > 0)[far])
+        far = lin.detach().abs() > (0.02 if mode == torch.float32 else 0.1)
+        assert torch.equal((y.float().cpu() > 0)[far], (lin.detach() > 0)[far])
 
 
 def test_bf16_weight_copy_follows_parameter_updates():
@@ -84,5 +87,6 @@ def test_head_trunk_runs_native_and_matches_torch_trunk():
         losses = h.loss(cls, reg, labels, None, torch.randn(200, 4, device='cuda'), torch.ones(200, 4, device='cuda'))
         sum(losses.values()).backward()
         outs.append((cls.x_cls.float(), reg.float(), h.shared_fcs[0].weight.grad, h.fc_reg.weight.grad))
-    for u, v in zip(*outs):
-        assert rel(u, v) <= 3e-3
+    # forward values agree to TF32 rounding; the gradients additionally see the few ReLU mask entries that rounding flips
+    for i, (u, v) in enumerate(zip(*outs)):
+        assert rel(u, v) <= (3e-3 if i < 2 else 3e-2), (i, rel(u, v))
