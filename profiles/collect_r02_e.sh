@@ -7,15 +7,15 @@ out=gpurun_out
 mkdir -p $out
 port=29600
 TRN() { n=$1; shift; port=$((port+1)); python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port "$@"; }
-DIAG_GRIDS=16,40 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29600 tests/multi_gpu_exchange_diag.py --json $out/${tag}_exchange_diag_8gpu.json > $out/${tag}_exchange_diag_8gpu.log 2>&1; echo "diag rc=$?"
+DIAG_GRIDS=16,40 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29600 tests/multi_gpu_exchange_diag.py --json $out/${tag}_exchange_diag_8gpu.json > $out/${tag}_exchange_diag_8gpu.log 2>&1; echo "diag rc=$?"
 grep -E "^\{" $out/${tag}_exchange_diag_8gpu.log | cut -c1-1100
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29601 tests/multi_gpu_head_step.py > $out/${tag}_head_step_8gpu.log 2>&1; echo "head step rc=$?"; grep -E " ok | FAIL |rror" $out/${tag}_head_step_8gpu.log | grep -v "^\[rank[1-9]" | head -16
+timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29601 tests/multi_gpu_head_step.py > $out/${tag}_head_step_8gpu.log 2>&1; echo "head step rc=$?"; grep -E " ok | FAIL |rror" $out/${tag}_head_step_8gpu.log | grep -v "^\[rank[1-9]" | head -16
 port=29610
 run_bench() {  # N, name, env assignments, extra args
   port=$((port+1))
   n=$1; f=$out/${tag}_bench_${n}gpu_$2; envs=$3
   shift; shift; shift
-  env $envs timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port bench.py --gpus $n --steps 160 --warmup 10 --profile "$@" > $f.json 2> $f.err; rc=$?
+  env $envs timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port bench.py --gpus $n --steps 160 --warmup 10 --profile "$@" > $f.json 2> $f.err; rc=$?
   echo -n "$(basename $f) rc=$rc "; grep -E "^\{" $f.json | tail -1 | cut -c1-120
 }
 run_bench 8 mm_instep "A=0" --exchange instep
