@@ -7,7 +7,7 @@ Every rank runs the head on its own RoIs (bags_head_loss / GraphedHeadStep with 
 the NVLink exchange bucket, exchanged as soon as they are complete and while dX is computed.  Checked against the
 reference's order of operations -- local backward, then all_reduce + divide of the flattened gradients
 (mmdet/core/utils/dist_utils.py:9-41, :51-58) -- on the same inputs and masks: weight.grad / bias.grad equal the NCCL
-mean (exactly at 2 ranks; to fp32 summation-order rounding beyond), dX equals the local one bit for bit.
+mean to fp32 summation-order rounding (the split-K red.add order of dW is not fixed), dX equals the local one bit for bit.
 """
 import datetime
 import json
@@ -55,7 +55,9 @@ def main():
     labels[:N // 4] = torch.randint(1, t.num_classes, (N // 4,), generator=gr)
     labels = labels.to(dev)
     wmask, avg = ops.sample_others(labels, dt, 8.0, 555 + rank)
-    tol = 0.0 if world == 2 else 1e-6
+    # the exchange itself is exact at 2 ranks (bench.py / multi_gpu_exchange_diag.py check that on random data); here the
+    # two sides also differ in the ORDER of the split-K red.add of dW (fp32 atomics: last-bit differences)
+    tol = 1e-6
 
     def reference():
         W = torch.nn.Parameter(W0.clone())
