@@ -578,6 +578,12 @@ static int launch_fused_fwd(const void* x, long long ldx, const void* w, long lo
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
+  // PDL INVARIANT (also the sampler's): this kernel reads x, W, bias and labels BEFORE its griddepcontrol.wait (only the
+  // sampler's masks / avg and every global write come after it).  That is correct as long as those tensors are not
+  // produced by the immediately preceding kernel of the stream with an early launch_dependents trigger -- true for torch
+  // kernels (they never trigger early) and for this library's own chain (the predecessor is the sampler / the previous
+  // step's backward or exchange, none of which writes them).  A future producer that triggers early must be followed by
+  // a non-PDL launch (BAGS_PDL=0) or move these reads behind the wait.
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // overlap with the sampler (pdl_wait in-kernel)
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;

@@ -235,6 +235,13 @@ def _exchange_overlapped(self, side_stream=None):
     for it.  What is launched on the current stream between the two -- the dX contraction -- overlaps the exchange."""
     dev = self.flat.device
     cur = torch.cuda.current_stream(dev)
+    if isinstance(self, PeerGradBucket) and self.max_blocks == 0:
+        # An exchange that shares the GPU with the dX GEMM wants a SMALL grid: its blocks then live on the SMs the GEMM
+        # leaves free instead of competing with GEMM CTAs for issue slots (measured at 2 / 4 / 8 ranks,
+        # profiles/r02_bench_*gpu_matrix.log: 8 ranks 67.0 us/step on 16 blocks vs 74.7 on 39), but large enough to keep
+        # this rank's slice in flight: one block per 2048 16-byte vectors of the slice, between 16 and 48.
+        per_rank = (self.count // 4 + self.world - 1) // self.world
+        self.max_blocks = max(16, min(48, (per_rank + 2047) // 2048))
     if side_stream is None:
         side_stream = getattr(self, '_side_stream', None)
         if side_stream is None:
@@ -275,10 +282,17 @@ def make_grad_bucket(shapes: List[Tuple[int, ...]], device, prefer_peer: bool = 
     if prefer_peer and PeerGradBucket.available() and os.environ.get('BAGS_ALLREDUCE', 'peer') != 'nccl':
         try:
             b = PeerGradBucket(shapes, device, max_blocks=max_blocks)
-            if b.self_test():
+            if not b.mc_ptr and b.world > 4 and os.environ.get('BAGS_ALLREDUCE') != 'peer':
+                # without an NVSwitch multicast object the kernel falls back to plain peer loads / stores, which read every
+                # element from all ranks: fine at 2 ranks (18.5 us vs 25), slower than NCCL at 8 (163 vs 102 us per step
+                # with the exchange inside the step; profiles/r02_bench_8gpu_matrix.log)
+                import warnings
+                warnings.warn('no multicast (NVLS) mapping at %d ranks: using NCCL all-reduce for the gradient bucket' % b.world)
+            elif b.self_test():
                 return b, b.flat, b.views, b.allreduce_
-            import warnings
-            warnings.warn('peer-memory gradient exchange failed its self test; using NCCL all-reduce')
+            else:
+                import warnings
+                warnings.warn('peer-memory gradient exchange failed its self test; using NCCL all-reduce')
         except Exception as ex:  # symmetric memory not usable on this system
             import warnings
             warnings.warn('peer-memory gradient bucket unavailable (%r); using NCCL all-reduce' % (ex,))

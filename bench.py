@@ -379,6 +379,10 @@ def run_ours(args):
         if world > 1:
             s['bucket'], s['grad'], (s['dW'], s['db']), s['exchange'] = make_grad_bucket(
                 [(C, K_FEAT), (C,)], dev, prefer_peer=(args.allreduce == 'peer'), max_blocks=args.ar_blocks)
+            if s['bucket'] is not None and args.ar_blocks == 0 and args.exchange == 'instep-overlap-dx':
+                # the product's rule for an exchange that shares the GPU with the dX GEMM (dist.exchange_overlapped)
+                per_rank = (s['bucket'].count // 4 + world - 1) // world
+                s['bucket'].max_blocks = max(16, min(48, (per_rank + 2047) // 2048))
         else:
             s['grad'] = torch.empty(C * K_FEAT + C, device=dev)
             s['dW'] = s['grad'][:C * K_FEAT].view(C, K_FEAT)
@@ -478,7 +482,7 @@ def run_ours(args):
 
     # sampler, fused fwd (or GEMM + grouped CE), merged backward (preparation jobs + dW + dX units in one launch)
     kernels_per_step = (4 if args.unfused else 3) + (1 if world > 1 and sets[0].get('bucket') is not None else 0) + (
-        3 if (world > 1 and args.exchange == 'instep-overlap-dx') else 0)   # split: + bwd_prep, dX GEMM, its prep
+        1 if args.exchange == 'instep-overlap-dx' else 0)   # split schedule: the backward is two launches (dW+db, dX)
 
     stream = torch.cuda.Stream(device=dev)
     comm_stream = torch.cuda.Stream(device=dev) if (world > 1 and args.exchange == 'overlap-next-step') else None
@@ -596,7 +600,7 @@ def run_ours(args):
             # and overlaps the dX contraction; weight.grad / bias.grad receive the mean over ranks (dist_utils.py:9-41)
             from balancedgroupsoftmax_b200.dist import NcclGradBucket
             e2e_bucket = make_grad_bucket([(C, K_FEAT), (C,)], dev, prefer_peer=(args.allreduce == 'peer'),
-                                          max_blocks=(args.ar_blocks or 48))[0]
+                                          max_blocks=args.ar_blocks)[0]
             if e2e_bucket is None:
                 e2e_bucket = NcclGradBucket([(C, K_FEAT), (C,)], dev)
         exchange = None
@@ -894,7 +898,7 @@ def main():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--pool', type=int, default=0, help='number of rotating buffer sets (= steps per CUDA graph)')
     ap.add_argument('--fake-exchange', default='', help='probe (N = 1): blocks,threads,microseconds of a side-stream wait kernel per step')
-    ap.add_argument('--exchange', default='instep', choices=['instep', 'instep-overlap-dx', 'overlap-next-step'],
+    ap.add_argument('--exchange', default=None, choices=['instep', 'instep-overlap-dx', 'overlap-next-step'],
                     help='N > 1: gradient exchange inside the step, stream-ordered between the backward and the next '
                          "step's forward (default: what an SGD step needs -- the optimizer reads the reduced gradients "
                          'before the next forward reads W; mmdet/core/utils/dist_utils.py:51-58), or the relaxed schedule '
@@ -921,6 +925,10 @@ def main():
         return run_reference(args)
     args.steps = args.steps or 600
     args.warmup = 20 if args.warmup is None else args.warmup
+    if args.exchange is None:
+        # N > 1: the exchange inside the step, overlapped by the dX contraction (the product's data-parallel schedule);
+        # one GPU: the merged backward (nothing to exchange)
+        args.exchange = 'instep-overlap-dx' if int(os.environ.get('WORLD_SIZE', '1')) > 1 else 'instep'
     return run_ours(args)
 
 
