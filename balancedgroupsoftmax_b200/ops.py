@@ -275,10 +275,25 @@ def fused_fwd(x, w, bias, labels, dt: DeviceTables, wmask, avg, logits: Optional
     return loss, logits, lse, dz, colsum
 
 
-def bwd_scratch(w: torch.Tensor) -> torch.Tensor:
-    """Scratch buffer for fused_bwd (row-scaled copy of W + bias-gradient partials), reusable across calls."""
+_scratch_cache: Dict[Tuple, torch.Tensor] = {}
+
+
+def bwd_scratch(w: torch.Tensor, cached: bool = False) -> torch.Tensor:
+    """Scratch buffer for fused_bwd (row-scaled copy of W + bias-gradient partials), reusable across calls.
+    ``cached``: one buffer per (device, stream, shape) -- safe because consecutive launches on a stream are ordered."""
+    key = None
+    if cached:
+        key = (w.device.index, _stream_ptr(w.device), w.shape[0], w.stride(0), w.dtype)
+        hit = _scratch_cache.get(key)
+        if hit is not None:
+            return hit
     nbytes = nat.lib().bags_bwd_scratch_bytes(w.shape[0], w.stride(0), _dtype_code(w.dtype))
-    return torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    if cached:
+        if len(_scratch_cache) > 32:
+            _scratch_cache.clear()
+        _scratch_cache[key] = buf
+    return buf
 
 
 def fused_bwd(dz, x, w, gout, dt: DeviceTables, colsum=None, need_dw=True, need_db=True, need_dx=True,
@@ -301,7 +316,8 @@ def fused_bwd(dz, x, w, gout, dt: DeviceTables, colsum=None, need_dw=True, need_
     if need_dx and dX is None:
         dX = torch.empty((N, K), dtype=x.dtype, device=dev)
     if wscratch is None and ((need_dx and gout is not None) or (need_db and colsum is None)):
-        wscratch = bwd_scratch(w)
+        # (not under stream capture: a captured graph must own its buffers)
+        wscratch = bwd_scratch(w, cached=not torch.cuda.is_current_stream_capturing())
     if gout is not None:
         gout = gout.contiguous()
         assert gout.dtype == torch.float32 and gout.numel() == dt.G
@@ -525,18 +541,20 @@ class GroupSoftmaxFunction(torch.autograd.Function):
         the gradients travel (SURVEY.md 8e; the reference exchanges after the whole backward, dist_utils.py:51-58);
         the returned weight / bias gradients ARE the bucket views, holding the mean over ranks."""
         _require_cuda(x, weight, bias, labels)
-        xin = x.detach()
-        win = weight.detach()
+        # (autograd does not record inside Function.forward: the inputs are used as they are, no detach() round trips)
         if compute_dtype == torch.bfloat16:
-            xc = xin if xin.dtype == torch.bfloat16 else cast_bf16(_row_major(xin.float()))
-            wc = win if win.dtype == torch.bfloat16 else cast_bf16(_row_major(win.float()))
+            xc = _row_major(x) if x.dtype == torch.bfloat16 else cast_bf16(_row_major(x.float()))
+            wc = _bf16_operand(weight)      # fp32 master: re-cast only when the parameter changed (version counter)
         elif compute_dtype == torch.float32:
-            if xin.dtype != torch.float32 or win.dtype != torch.float32:
+            if x.dtype != torch.float32 or weight.dtype != torch.float32:
                 raise nat.BagsNativeError('float32 compute needs float32 x and weight')
-            xc, wc = _row_major(xin), _row_major(win)
+            xc, wc = _row_major(x), _row_major(weight)
         else:
             raise nat.BagsNativeError('compute_dtype must be torch.bfloat16 or torch.float32')
-        b32 = None if bias is None else bias.detach().float().contiguous()
+        if bias is None or (bias.dtype == torch.float32 and bias.is_contiguous()):
+            b32 = bias
+        else:
+            b32 = bias.float().contiguous()
         need_grad = any(ctx.needs_input_grad[:3])
         # dW is allocated here and zeroed by the forward kernel's idle epilogue warps (its split-K red.add in the
         # backward then needs no zeroing job); BAGS_FWD_COLSUM=1 also takes the bias-gradient partials from the forward
@@ -568,7 +586,8 @@ class GroupSoftmaxFunction(torch.autograd.Function):
     def backward(ctx, grad_loss):
         xc, wc, dz = ctx.saved_tensors
         need_dx, need_dw, need_db = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
-        gout = grad_loss.detach().to(torch.float32).contiguous()
+        gout = grad_loss if (grad_loss.dtype == torch.float32 and grad_loss.is_contiguous()) \
+            else grad_loss.to(torch.float32).contiguous()
         dW0, ctx.dW = ctx.dW, None                      # (a second backward through a retained graph zeroes again)
         bucket = ctx.grad_bucket
         if bucket is not None and need_dw:

@@ -291,3 +291,42 @@ def test_reweight_head_variant_construction(tmp_path):
     bad['gs_config'] = dict(cfg['gs_config'], cls_weights=[w[:-1] for w in ws])
     with pytest.raises(AssertionError):
         build_from_cfg(bad, HEADS)
+
+
+def test_head_reports_kernel_limits_at_construction():
+    """Bin tables the native kernels cannot take (3 bins -> 1234 logits, 9 bins) are rejected when the head is
+    built, not at the first loss / merge call; a non-'mean' loss_bin reduction likewise."""
+    from balancedgroupsoftmax_b200.tables import GroupTables
+
+    def fake_tables(num_bins, num_classes=1231):
+        # bin 0 = {bg, fg}; foreground classes dealt round-robin to bins 1..num_bins-1
+        l2b = np.zeros((num_bins, num_classes), dtype=np.int64)
+        l2b[0, 1:] = 1
+        counts = [2]
+        splits = []
+        for g in range(1, num_bins):
+            ids = np.arange(g, num_classes, num_bins - 1)
+            ids = ids[ids >= 1]
+            l2b[g, ids] = np.arange(1, len(ids) + 1)
+            counts.append(len(ids) + 1)
+            splits.append(ids.astype(np.int64))
+        starts = np.concatenate([[0], np.cumsum(counts)[:-1]])
+        ps = np.stack([starts, np.array(counts)], 1).astype(np.int64)
+        return GroupTables(l2b, ps, splits)
+
+    def build(tables, **over):
+        cfg = dict(tables=tables, others_sample_ratio=8.0, num_bins=tables.num_bins,
+                   loss_bin=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0))
+        cfg.update(over)
+        return GSBBoxHeadWith0(num_fcs=1, in_channels=4, fc_out_channels=16, roi_feat_size=1, num_classes=1231, gs_config=cfg)
+
+    t3 = fake_tables(3)
+    assert t3.num_logits == 1231 + 3
+    with pytest.raises(ValueError, match='multiple of 4'):
+        build(t3)
+    with pytest.raises(ValueError, match='at most 8'):
+        build(fake_tables(9))
+    with pytest.raises(ValueError, match='reduction'):
+        build(synthetic_tables(1231, seed=0), loss_bin=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0,
+                                                             reduction='sum'))
+    build(synthetic_tables(1231, seed=0))     # the 5-bin LVIS-shaped tables are fine
