@@ -729,6 +729,14 @@ static int launch_bwd_merged(const void* dz, long long ldd, const void* x, long 
   if ((rc = make_tmap(&t_wT, wb, dtype, p0.Kf, p0.C, ldw, Cfg::SLAB, Cfg::BLOCK_K, TF32))) return rc;
   BwdFusedParams p = p0;
   p.timing = g_timing ? g_timing + 2048 * 8 : nullptr;   // rows [2048, ..): the forward of the same step uses [0, 2048)
+  if (p.dw_units > 0 && p.dw_splits == 1 && p.prep_jobs > 0) {
+    // no split-K: every dW unit owns its output tile -> plain stores, and the zeroing job (the first z_ctas tickets)
+    // disappears.  (Only with in-kernel preparation: a separate preparation kernel has already been launched.)
+    p.dw_store = 1;
+    p.prep_jobs -= p.prep.z_ctas;
+    p.prep.z_ctas = 0;
+    if (p.prep.c_ctas == 0) p.dw_needs_prep = 0;
+  }
   // preparation jobs handed out by an atomic ticket (no co-residency requirement); BAGS_BWD_TICKET=0: static assignment
   auto kernel = (p.prep_jobs > 0 && env_int("BAGS_BWD_TICKET", 1)) ? bags_bwd_fused_kernel<TF32, MT, true>
                                                                   : bags_bwd_fused_kernel<TF32, MT, false>;

@@ -31,6 +31,7 @@ struct BwdFusedParams {
   // bwd_prep_kernel ran before this one (programmatic dependent launch).
   BwdPrepParams prep; int prep_jobs; unsigned int* sync;
   int dx_uniform_ok;   // gout given and tmap_w valid: dX units may read W and scale by gout[0] when gout is uniform
+  int dw_store;        // split-K factor 1: a dW unit owns its tile -- plain stores, no zeroing, no red.add (the trunk's wide layers)
   int wait_dz;         // the producer waits (griddepcontrol.wait) before its first load: dz comes from the preceding kernel
   int dw_needs_prep;   // dW epilogues wait for preparation (zeroed dW / column-sum partials); 0: dW was zeroed by the
                        // forward's clear hook and the column sums come from the forward as well
@@ -390,8 +391,11 @@ bags_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_dzT,   // dz as M
           const int gn = n + ch * vec;
           if (gm < Mrows && gn + vec <= p.Kf) {
             if (un.is_dw) {
-              red_add_v4_f32(p.dW + static_cast<long long>(gm) * p.lddw + gn, __uint_as_float(val.x), __uint_as_float(val.y),
-                             __uint_as_float(val.z), __uint_as_float(val.w));
+              if (p.dw_store)
+                *reinterpret_cast<uint4*>(p.dW + static_cast<long long>(gm) * p.lddw + gn) = val;
+              else
+                red_add_v4_f32(p.dW + static_cast<long long>(gm) * p.lddw + gn, __uint_as_float(val.x), __uint_as_float(val.y),
+                               __uint_as_float(val.z), __uint_as_float(val.w));
             } else if (out_bf16) {
               *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.dX) + static_cast<long long>(gm) * p.lddx + gn) = val;
             } else {

@@ -1,5 +1,10 @@
-# stage timing of ops.multiclass_nms at the LVIS test shape
+"""Stage timing of ops.multiclass_nms at the LVIS test shape (1000 proposals x 1231 classes): python tests/gpu_probe_nms.py"""
+import os
+import sys
+
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from balancedgroupsoftmax_b200 import ops, _native as nat
 from balancedgroupsoftmax_b200.tables import synthetic_tables
 t = synthetic_tables(1231, seed=0)
