@@ -13,7 +13,7 @@
 namespace bags {
 
 constexpr int kNmsMaxSeg = 1024;
-constexpr int kNmsThreads = 256;
+constexpr int kNmsThreads = 1024;   // 32 warps: the mask rows are dealt to the warps; with 8 the loop was issue-latency bound
 
 __device__ __forceinline__ float iou_plus1(const float4 a, const float4 b) {
   const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
