@@ -589,6 +589,7 @@ def run_ours(args):
         # Compute = the public API: GraphedHeadStep (CUDA-graph replay of bags_head_loss + backward, one instance per
         # input buffer); the eager autograd calls of the same API are timed as well (`eager_ms_per_step`).
         copy_stream = torch.cuda.Stream(device=dev)
+        extra_copy_streams = [torch.cuda.Stream(device=dev) for _ in range(max(args.e2e_copy_streams, 1) - 1)]
         comp_stream = torch.cuda.current_stream(dev)
         loss_hosts = [torch.empty(dt.G, dtype=torch.float32).pin_memory() for _ in range(2)]
         ev_copied = [torch.cuda.Event() for _ in range(2)]
@@ -629,7 +630,25 @@ def run_ours(args):
                     ev_h2d1[b_].synchronize()
                     h2d_in_pipe.append(ev_h2d0[b_].elapsed_time(ev_h2d1[b_]))   # step i-2's copy (long finished)
                 ev_h2d0[b_].record(copy_stream)
-                xdst.copy_(x_host, non_blocking=True)
+                if len(extra_copy_streams) == 0:
+                    xdst.copy_(x_host, non_blocking=True)
+                else:
+                    # the feature block in row slabs over several copy streams (several copy engines share the PCIe link)
+                    parts = len(extra_copy_streams) + 1
+                    bounds = [n * k // parts for k in range(parts + 1)]
+                    fork = torch.cuda.Event()
+                    fork.record(copy_stream)
+                    joins = []
+                    for k, st_ in enumerate(extra_copy_streams, start=1):
+                        with torch.cuda.stream(st_):
+                            st_.wait_event(fork)
+                            xdst[bounds[k]:bounds[k + 1]].copy_(x_host[bounds[k]:bounds[k + 1]], non_blocking=True)
+                            e_ = torch.cuda.Event()
+                            e_.record(st_)
+                            joins.append(e_)
+                    xdst[bounds[0]:bounds[1]].copy_(x_host[bounds[0]:bounds[1]], non_blocking=True)
+                    for e_ in joins:
+                        copy_stream.wait_event(e_)
                 ldst.copy_(lab_host, non_blocking=True)
                 ev_h2d1[b_].record(copy_stream)
                 ev_copied[b_].record(copy_stream)
@@ -706,7 +725,8 @@ def run_ours(args):
                        if graphed else 'balancedgroupsoftmax_b200.api.bags_head_loss + autograd backward (eager)'),
                'eager_ms_per_step': eager_ms,
                'h2d_ms_inside_pipeline': (sorted(h2d_in_pipe)[len(h2d_in_pipe) // 2] if h2d_in_pipe else None),
-               'staging': 'pinned, GPU-local NUMA node' if args.numa_pinned else 'pinned',
+               'staging': ('pinned, GPU-local NUMA node' if args.numa_pinned else 'pinned') + (
+                   '; H2D split over %d copy streams' % args.e2e_copy_streams if args.e2e_copy_streams > 1 else ''),
                'operands': ('features staged on the host in %s (the C ABI input format of this dtype mode); fp32 master '
                             'fc_cls.weight cast to the operand dtype inside every step; dW / db returned in fp32'
                             % args.dtype),
@@ -914,6 +934,7 @@ def main():
                     help='N > 1: gradient exchange by the peer-memory kernel (default) or NCCL')
     ap.add_argument('--no-numa-pinned', dest='numa_pinned', action='store_false',
                     help='e2e leg: plain pin_memory() staging buffers instead of GPU-local NUMA placement')
+    ap.add_argument('--e2e-copy-streams', type=int, default=1, help='e2e leg: copy streams the H2D of the features is split over')
     ap.add_argument('--e2e-eager-only', action='store_true', help='e2e leg: eager autograd calls only (no CUDA-graph step)')
     ap.add_argument('--unfused', action='store_true', help='GEMM -> fp32 logits -> grouped CE instead of the fused kernel')
     ap.add_argument('--no-library-baseline', action='store_true', help='skip the torch/cuBLAS same-GPU baseline leg')
