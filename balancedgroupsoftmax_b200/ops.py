@@ -375,13 +375,13 @@ def multiclass_nms(multi_bboxes: torch.Tensor, multi_scores: torch.Tensor, score
               'bags_class_nms_dense')
     kept = keep.bool()
     flat = torch.where(kept, vals, torch.full_like(vals, float('-inf'))).reshape(-1)
-    cap = min(max_num, S * n) if max_num > 0 else S * n
+    cap = min(max_num, S * n) if max_num >= 0 else S * n
     topv, topi = flat.topk(cap)                                      # survivors by descending score, then -inf padding
     total, ovf = (int(v) for v in torch.stack([kept.sum(), overflow[0].to(torch.int64)]).tolist())   # the one sync
     if ovf:
         raise nat.BagsNativeError('multiclass_nms: a class has more than 1024 candidates above score_thr (n = %d)' % n)
     if total > max_num:                                              # bbox_nms.py:57-61 (true for max_num = -1 as well)
-        k = max_num if max_num > 0 else total - 1
+        k = max_num if max_num >= 0 else total + max_num             # inds[:max_num]: a negative bound drops the tail
         sel = topi[:max(min(k, total), 0)]
     else:
         sel = topi[:total].sort().values                             # class-major, score-descending inside a class

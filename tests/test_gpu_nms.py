@@ -20,7 +20,7 @@ def test_class_nms_matches_oracle(n, classes, per_class_boxes):
     b4 = torch.cat([xy, xy + wh], 1)
     boxes = (b4[:, None, :] + torch.rand(n, classes, 4, generator=g)).reshape(n, classes * 4) if per_class_boxes else b4
     scores = torch.rand(n, classes, generator=g) ** 2
-    for thr, iou, k in ((0.05, 0.5, 100), (0.0, 0.3, 300), (0.999999, 0.5, 10), (0.3, 0.7, -1)):
+    for thr, iou, k in ((0.05, 0.5, 100), (0.0, 0.3, 300), (0.999999, 0.5, 10), (0.3, 0.7, -1), (0.3, 0.5, 0), (0.2, 0.5, -2)):
         want_b, want_l = O.multiclass_nms(boxes, scores, thr, iou, k)
         got_b, got_l = ops.multiclass_nms(boxes.cuda(), scores.cuda(), thr, iou, k)
         assert got_b.shape == want_b.shape
