@@ -718,7 +718,32 @@ def run_ours(args):
             cb.record(copy_stream)
         copy_stream.synchronize()
         h2d_ms = ca.elapsed_time(cb) / 20
+        # the eager module-level API with device-resident inputs and a DIFFERENT RoI count every call (N is data-dependent in
+        # a real detector: no graph) -- what a step costs on the host when nothing hides it
+        eager_var_us = None
+        if world == 1:
+            try:
+                sizes = [1024, 960, 1000, 896, 1024, 777, 1010, 512]
+                xs = {m: torch.relu(torch.randn(m, K_FEAT, generator=gen)).to(dev).to(dtype) for m in set(sizes)}
+                ls = {m: make_labels(torch, m, NUM_CLASSES, gen).to(dev) for m in set(sizes)}
+
+                def eager_var(k):
+                    for i in range(k):
+                        m = sizes[i % len(sizes)]
+                        xin = xs[m].detach().requires_grad_(True)
+                        w_param.grad = None
+                        b_param.grad = None
+                        bags_head_loss(xin, w_param, b_param, ls[m], dt, RATIO, compute_dtype=dtype).sum().backward()
+                eager_var(16)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                eager_var(200)
+                torch.cuda.synchronize()
+                eager_var_us = (time.perf_counter() - t0) / 200 * 1e6
+            except Exception as ex:  # pragma: no cover
+                log('eager variable-N timing failed: %r' % (ex,))
         e2e = {'value': world * n / (e2e_ms * 1e-3), 'unit': 'RoIs/s', 'h2d_only_ms_per_step': h2d_ms,
+               'eager_api_us_per_step_variable_n_le_1024': eager_var_us,
                'h2d_bytes_per_step': int(x_host.numel() * x_host.element_size() + lab_host.numel() * 8),
                'd2h_bytes_per_step': int(loss_host.numel() * 4), 'ms_per_step': e2e_ms, 'steps': e2e_steps,
                'api': ('balancedgroupsoftmax_b200.api.GraphedHeadStep (CUDA-graph replay of bags_head_loss + backward)'
