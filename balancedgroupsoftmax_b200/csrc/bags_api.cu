@@ -899,9 +899,13 @@ extern "C" int bags_bwd_ex(const void* dz, long long ldd, const void* x, long lo
   // these jobs run inside the GEMM kernel (no extra launch in the dependent chain); otherwise one small kernel. ----
   // dW (+ db) alone also runs on the merged kernel (no dX units): in-kernel preparation, 256 x 256 units when the
   // problem is large enough -- the launch the split in-step schedule (dW -> exchange || dX) puts on its critical path
+  // ... unless there is nothing to prepare (dW zeroed and the bias-gradient partials supplied by the forward): then the
+  // plain split-K GEMM (4-stage ring, no job machinery) is the faster dW-only launch -- 52.9 vs 53.7 us per
+  // forward + dW-only + dX-only sequence, and 54.6 with the jobs in the backward (profiles/r02_dwonly_path.log)
+  const bool nothing_to_prepare = prezeroed && (db == nullptr || colsum != nullptr);
   const bool dw_only_merged = dW != nullptr && dX == nullptr && w != nullptr && N > 0 && (K % 8) == 0 &&
-                              (reinterpret_cast<uintptr_t>(w) & 15) == 0 && env_int("BAGS_BWD_DW_MERGED", 1) &&
-                              !env_int("BAGS_BWD_PAIR", 0);
+                              (reinterpret_cast<uintptr_t>(w) & 15) == 0 && !env_int("BAGS_BWD_PAIR", 0) &&
+                              env_int("BAGS_BWD_DW_MERGED", nothing_to_prepare ? 0 : 1);
   // dX alone with per-bin upstream gradients: the merged kernel decides ON THE DEVICE whether they are uniform (then it
   // reads W and scales in the epilogue: no scaled copy W', no preparation launch); with gout == NULL the plain GEMM is used
   const bool dx_only_merged = dW == nullptr && db == nullptr && dX != nullptr && gout != nullptr && x != nullptr &&

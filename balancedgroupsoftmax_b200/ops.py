@@ -516,7 +516,9 @@ class LinearActFunction(torch.autograd.Function):
 # --------------------------------------------------------------------------- autograd
 # where the backward's preparation work runs: 1 = dW is zeroed by the fused forward kernel (idle epilogue warps)
 PREP_IN_FORWARD = os.environ.get('BAGS_PREP_IN_FORWARD', '1') != '0'
-# 1 = the bias-gradient column sums come from the forward's epilogue as well (otherwise a job of the backward kernel)
+# 1 = the bias-gradient column sums come from the forward's epilogue as well (otherwise a job of the backward kernel).
+# Costs the forward ~1.2 us and is a loss for the merged backward (one GPU); with a grad_bucket (data-parallel schedule)
+# it is always on: the dW + db launch -- on the critical path before the exchange -- then has nothing to prepare.
 FWD_COLSUM = os.environ.get('BAGS_FWD_COLSUM', '0') == '1'
 
 
@@ -569,7 +571,8 @@ class GroupSoftmaxFunction(torch.autograd.Function):
             dW = torch.empty((wc.shape[0], wc.shape[1]), dtype=torch.float32, device=xc.device)
         loss, _, _, dz, colsum = fused_fwd(xc, wc, b32, labels, dt, wmask, avg, logits=logits_out,
                                            want_dz=need_grad, clear=dW,
-                                           want_colsum=(dW is not None and FWD_COLSUM and bias is not None))
+                                           want_colsum=(dW is not None and bias is not None and
+                                                        (FWD_COLSUM or ctx.grad_bucket is not None)))
         ctx.dW = dW
         ctx.colsum = colsum if dW is not None else None
         ctx.dt = dt

@@ -948,7 +948,7 @@ def main():
                          "step's forward (default: what an SGD step needs -- the optimizer reads the reduced gradients "
                          'before the next forward reads W; mmdet/core/utils/dist_utils.py:51-58), or the relaxed schedule '
                          'on a side stream under the NEXT step (not a valid training schedule; kept for comparison)')
-    ap.add_argument('--prep', default='fwd-zero', choices=['bwd', 'fwd-zero', 'fwd-zero-colsum'],
+    ap.add_argument('--prep', default=None, choices=['bwd', 'fwd-zero', 'fwd-zero-colsum'],
                     help="where the backward's preparation runs: 'bwd' = jobs inside the backward kernel (zero dW, column sums); "
                          "'fwd-zero' = dW is zeroed by the forward kernel's idle epilogue warps; 'fwd-zero-colsum' = the "
                          'bias-gradient column sums come from the forward epilogue as well (no preparation left)')
@@ -975,6 +975,9 @@ def main():
         # N > 1: the exchange inside the step, overlapped by the dX contraction (the product's data-parallel schedule);
         # one GPU: the merged backward (nothing to exchange)
         args.exchange = 'instep-overlap-dx' if int(os.environ.get('WORLD_SIZE', '1')) > 1 else 'instep'
+    if args.prep is None:
+        # split schedule: the dW + db launch sits on the critical path before the exchange -> nothing left to prepare there
+        args.prep = 'fwd-zero-colsum' if args.exchange == 'instep-overlap-dx' else 'fwd-zero'
     return run_ours(args)
 
 
