@@ -168,6 +168,20 @@ class ClsScoreHandle(object):
     def __getitem__(self, idx):
         return self.tensor()[idx]
 
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        """torch.cat([cls_score, ...]), torch.softmax(cls_score, 1), F.cross_entropy(cls_score, ...) ...: any torch
+        function handed a handle sees the materialised logits (callers written for the reference's plain tensor)."""
+        def unwrap(a):
+            if isinstance(a, ClsScoreHandle):
+                return a.tensor()
+            if isinstance(a, (list, tuple)):
+                return type(a)(unwrap(v) for v in a)
+            if isinstance(a, dict):
+                return {k: unwrap(v) for k, v in a.items()}
+            return a
+        return func(*unwrap(tuple(args)), **unwrap(kwargs or {}))
+
 
 class FcClsFunction(torch.autograd.Function):
     """Materialised logits = x W^T + b on tcgen05 (bags_linear_fwd); backward reuses bags_bwd."""

@@ -71,6 +71,8 @@ def _workspace(device: torch.device) -> torch.Tensor:
     key = (device.index if device.index is not None else torch.cuda.current_device(), _stream_ptr(device))
     ws = _workspaces.get(key)
     if ws is None:
+        if len(_workspaces) >= 64:      # streams come and go (side streams, graph captures): keep the table bounded
+            _workspaces.pop(next(iter(_workspaces)))
         ws = torch.zeros(nat.lib().bags_workspace_bytes(), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws

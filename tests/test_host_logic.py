@@ -330,3 +330,22 @@ def test_head_reports_kernel_limits_at_construction():
         build(synthetic_tables(1231, seed=0), loss_bin=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0,
                                                              reduction='sum'))
     build(synthetic_tables(1231, seed=0))     # the 5-bin LVIS-shaped tables are fine
+
+
+def test_cls_score_handle_works_with_torch_functions():
+    """The lazy cls_score of the training forward behaves like the reference's plain tensor for callers that hand it
+    to torch functions (torch.cat, softmax, ...): __torch_function__ materialises the logits."""
+    class FakeHead(object):
+        class fc_cls(object):
+            out_features = 6
+
+        def _fc_cls_logits(self, x):
+            return x @ torch.arange(24, dtype=torch.float32).view(6, 4).t()
+    x = torch.randn(5, 4)
+    h = ClsScoreHandle(FakeHead(), x)
+    z = FakeHead()._fc_cls_logits(x)
+    assert tuple(h.shape) == (5, 6) and h.size(1) == 6 and h.dim() == 2
+    assert torch.equal(torch.cat([h, z], 0), torch.cat([z, z], 0))
+    assert torch.allclose(torch.softmax(h, 1), torch.softmax(z, 1))
+    assert torch.equal(h.argmax(1), z.argmax(1)) and torch.equal(h[:, 1:3], z[:, 1:3])
+    assert torch.equal(torch.stack((h, h)).sum(0), 2 * z)
