@@ -676,8 +676,8 @@ class GSBBoxHead(GSBBoxHeadWith0):
 
 class GSBBoxHeadWith0Reweight(GSBBoxHeadWith0):
     """BAGS head with per-class loss weights inside the bins (gs_bbox_head_with0_reweight.py:14-109; used by
-    configs/ablations/gs_faster_rcnn_r50_fpn_1x_lvis_with0_reweight.py).  EXPERIMENTAL: its device ops have not run on a
-    GPU yet.  Differences from ``GSBBoxHeadWith0``: ``gs_config.bin_cls_weight`` names a pickle holding one weight
+    configs/ablations/gs_faster_rcnn_r50_fpn_1x_lvis_with0_reweight.py).
+    Differences from ``GSBBoxHeadWith0``: ``gs_config.bin_cls_weight`` names a pickle holding one weight
     vector per foreground bin (length = the bin's logit count, index 0 = "others"); the sampled 0/1 weight of every
     RoI is multiplied by the weight of its in-bin label and the per-bin normaliser is the sum of the products
     (``_sample_others`` :57-85, ``_remap_labels`` :87-109).  ``gs_config['cls_weights']`` may pass the vectors directly."""

@@ -160,7 +160,7 @@ def sample_others(labels: torch.Tensor, dt: DeviceTables, ratio: float, seed: in
 
 def reweight(labels: torch.Tensor, dt: DeviceTables, wmask: Optional[torch.Tensor], cls_weight: torch.Tensor
              ) -> Tuple[torch.Tensor, torch.Tensor]:
-    """EXPERIMENTAL (reweight head variant, gs_bbox_head_with0_reweight.py:57-109): (wfloat [G,N] fp32, avg [G]) with
+    """Reweight head variant (gs_bbox_head_with0_reweight.py:57-109): (wfloat [G,N] fp32, avg [G]) with
     wfloat[g,n] = wmask[g,n] * cls_weight[g, in-bin label of n] for g >= 1 and avg[g] = max(sum_n wfloat[g,n], 1).
     ``cls_weight`` is [G, stride] fp32 on the device (row 0 unused; index 0 of a row is the "others" weight)."""
     _require_cuda(labels, wmask, cls_weight)

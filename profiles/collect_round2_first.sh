@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical: the CTA-pair forward and the BAGS_TEST_EXPERIMENTAL gates it exercises were removed later in round 2)
 # First GPU call of the next round (1 GPU, ~3 min): state of the tree + the experiments prepared at the end of round 1.
 #   gpurun --timeout 1200 -- 'bash profiles/collect_round2_first.sh r02_v0'
 tag=${1:-r02_v0}

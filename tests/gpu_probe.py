@@ -194,53 +194,6 @@ def case_fused(name):
 
 
 
-def case_fwdpair(name):
-    """EXPERIMENTAL CTA-pair forward (BAGS_FWD_PAIR=1) against the default fused forward on the same inputs:
-    losses, lse, dz and the column sums must agree to rounding; then a timing A/B of the two kernels."""
-    np, torch, ops, _, O = _setup()
-    _, dts = name.split('.')
-    cdt = torch.bfloat16 if dts == 'bf16' else torch.float32
-    out = {}
-    for N in (4096, 512, 200, 129, 1):
-        t, x, W, b, labels, l2b, ps, remapped = _problem(N)
-        dt = ops.DeviceTables.from_tables(t, 'cuda')
-        wmask = torch.stack([w.to(torch.uint8) for w in remapped[1]]).cuda()
-        avg = ops.mask_avg(wmask)
-        xc, wc, bc, lc = x.cuda().to(cdt), W.cuda().to(cdt), (b + 0.1 * torch.randn_like(b)).cuda(), labels.cuda()
-        got = {}
-        for mode in ('0', '1'):
-            os.environ['BAGS_FWD_PAIR'] = mode
-            loss, _, lse, dz, colsum = ops.fused_fwd(xc, wc, bc, lc, dt, wmask, avg, want_lse=True, want_colsum=True)
-            torch.cuda.synchronize()
-            got[mode] = (loss.cpu(), lse.cpu(), dz[:, :t.num_logits].float().cpu(), colsum.sum(0).cpu())
-        os.environ['BAGS_FWD_PAIR'] = '0'
-        res = dict(loss=rel(got['1'][0], got['0'][0]), lse=rel(got['1'][1], got['0'][1]),
-                   dz=rel(got['1'][2], got['0'][2]), colsum=rel(got['1'][3], got['0'][3]))
-        out['N%d' % N] = res
-        for k_, v in res.items():
-            assert v < 2e-3, (N, k_, v)
-
-    t, x, W, b, labels, l2b, ps, remapped = _problem(4096)
-    dt = ops.DeviceTables.from_tables(t, 'cuda')
-    wmask = torch.stack([w.to(torch.uint8) for w in remapped[1]]).cuda()
-    avg = ops.mask_avg(wmask)
-    xc, wc, bc, lc = x.cuda().to(cdt), W.cuda().to(cdt), b.cuda(), labels.cuda()
-    for mode in ('0', '1', '0', '1'):
-        os.environ['BAGS_FWD_PAIR'] = mode
-        for _ in range(5):
-            ops.fused_fwd(xc, wc, bc, lc, dt, wmask, avg)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(50):
-            ops.fused_fwd(xc, wc, bc, lc, dt, wmask, avg)
-        e1.record()
-        torch.cuda.synchronize()
-        out.setdefault('us_pair%s' % mode, []).append(e0.elapsed_time(e1) / 50 * 1e3)
-    os.environ['BAGS_FWD_PAIR'] = '0'
-    return out
-
-
 def case_fusedk(name):
     """fused forward kernel (logits stay in TMEM) vs the oracle, incl. ragged N and lse output"""
     np, torch, ops, _, O = _setup()
@@ -526,7 +479,6 @@ CASES = {
     'gemm.kk256.f32': case_gemm, 'gemm.kk320.f32': case_gemm, 'gemm.kmn.f32': case_gemm, 'gemm.mnmn.f32': case_gemm,
     'fused.bf16': case_fused, 'fused.f32': case_fused, 'fusedk.bf16': case_fusedk, 'fusedk.f32': case_fusedk,
     'timeline': case_timeline, 'steptimeline': case_steptimeline, 'timing': case_timing,
-    'fwdpair.bf16': case_fwdpair, 'fwdpair.f32': case_fwdpair,
 }
 
 

@@ -1,5 +1,5 @@
-"""GPU, EXPERIMENTAL: the reweight head variant's device ops (bags_reweight, bags_fwd_w / bags_group_ce_w) against the
-oracle restatement of gs_bbox_head_with0_reweight.py.  Gated by BAGS_TEST_EXPERIMENTAL=1 until seen green once."""
+"""GPU: the reweight head variant's device ops (bags_reweight, bags_fwd_w / bags_group_ce_w) against the
+oracle restatement of gs_bbox_head_with0_reweight.py (pinned to the reference class in tests/test_oracle_vs_reference.py)."""
 import os
 
 import numpy as np
