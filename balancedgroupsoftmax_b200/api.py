@@ -135,3 +135,134 @@ class GraphedHeadStep(object):
         if labels is not None:
             self.labels.copy_(labels, non_blocking=True)
         return self.replay()
+
+
+class _GraphedPair(object):
+    """Static buffers + two CUDA graphs (forward: sampler + fused forward; backward: merged backward) for ONE RoI count."""
+
+    def __init__(self, n: int, k: int, c: int, dt: ops.DeviceTables, ratio: float, seed: int, op_dtype: torch.dtype,
+                 has_bias: bool, need_dx: bool, device):
+        self.n = n
+        self.x = torch.zeros((n, k), dtype=op_dtype, device=device)
+        self.labels = torch.zeros((n,), dtype=torch.int64, device=device)
+        self.w = torch.zeros((c, k), dtype=op_dtype, device=device)
+        self.bias = torch.zeros((c,), dtype=torch.float32, device=device) if has_bias else None
+        self.gout = torch.ones((dt.G,), dtype=torch.float32, device=device)
+        self.seed_step = torch.zeros((1,), dtype=torch.int64, device=device)
+        self.dW = torch.zeros((c, k), dtype=torch.float32, device=device)
+        self.db = torch.zeros((c,), dtype=torch.float32, device=device) if has_bias else None
+        self.dX = torch.zeros((n, k), dtype=op_dtype, device=device) if need_dx else None
+        self.wscratch = ops.bwd_scratch(self.w)
+        self.w_version = None
+        self.stream = torch.cuda.Stream(device=device)
+        self.stream.wait_stream(torch.cuda.current_stream(device))
+
+        def fwd():
+            wmask, avg = ops.sample_others(self.labels, dt, ratio, seed, seed_step=self.seed_step)
+            loss, _, _, dz, _ = ops.fused_fwd(self.x, self.w, self.bias, self.labels, dt, wmask, avg, clear=self.dW)
+            return loss, dz
+
+        def bwd(dz):
+            ops.fused_bwd(dz, self.x, self.w, self.gout, dt, None, need_db=has_bias, need_dx=need_dx, dW=self.dW,
+                          dX=self.dX, wscratch=self.wscratch, db=self.db, dw_prezeroed=True)
+
+        with torch.cuda.stream(self.stream):
+            for _ in range(2):
+                loss, dz = fwd()
+                bwd(dz)
+            self.stream.synchronize()
+            self.g_fwd, self.g_bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_fwd, stream=self.stream):
+                self.loss, self.dz = fwd()
+                self.seed_step.add_(1)
+            with torch.cuda.graph(self.g_bwd, stream=self.stream, pool=self.g_fwd.pool()):
+                bwd(self.dz)
+            self.seed_step.zero_()
+        torch.cuda.current_stream(device).wait_stream(self.stream)
+
+
+class _GraphCachedFunction(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, labels, pair: _GraphedPair):
+        with torch.no_grad():
+            pair.x.copy_(x)
+            pair.labels.copy_(labels)
+            if pair.w_version != (id(weight), weight._version):     # the operand copy follows optimizer updates
+                pair.w.copy_(weight)
+                pair.w_version = (id(weight), weight._version)
+            if bias is not None:
+                pair.bias.copy_(bias)
+        pair.g_fwd.replay()
+        ctx.pair = pair
+        ctx.dtypes = (x.dtype, weight.dtype, None if bias is None else bias.dtype)
+        return pair.loss.clone()
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_loss):
+        pair = ctx.pair
+        pair.gout.copy_(grad_loss)
+        pair.g_bwd.replay()
+        xd, wd, bd = ctx.dtypes
+        dX = None
+        if pair.dX is not None and ctx.needs_input_grad[0]:
+            dX = pair.dX.to(xd) if pair.dX.dtype != xd else pair.dX.clone()
+        dW = pair.dW.to(wd) if ctx.needs_input_grad[1] else None      # (a copy: the static buffer is rewritten next step)
+        if dW is not None and dW.data_ptr() == pair.dW.data_ptr():
+            dW = dW.clone()
+        db = None
+        if pair.db is not None and ctx.needs_input_grad[2]:
+            db = pair.db.to(bd).clone() if pair.db.dtype == bd else pair.db.to(bd)
+        return dX, dW, db, None, None
+
+
+class GraphCachedHeadLoss(object):
+    """``bags_head_loss`` for callers whose RoI count is data-dependent (every real detector: up to 512 sampled RoIs per
+    image, in practice almost always exactly that -- ``RandomSampler`` fills up with negatives,
+    mmdet/core/bbox/samplers/base_sampler.py:30-78) but who still want graph-replay host costs inside an ordinary
+    autograd graph (x comes from the trunk, dX flows back into it).
+
+    Per RoI count N it keeps static buffers and two CUDA graphs (sampler + fused forward; merged backward); a call with a
+    cached N costs a few small copies and two graph launches instead of ~220 us of Python / allocator / launch work.  A
+    new N runs the eager path the first ``capture_after`` times it is seen and is captured after that; at most
+    ``max_graphs`` counts stay cached (least recently used first out).  The "others" sampler's seed advances on the device
+    with every replay."""
+
+    def __init__(self, tables: Union[GroupTables, ops.DeviceTables], others_sample_ratio: float = 8.0,
+                 compute_dtype: torch.dtype = torch.bfloat16, seed: Optional[int] = None, max_graphs: int = 4,
+                 capture_after: int = 2, need_dx: bool = True):
+        self.tables = tables
+        self.ratio = float(others_sample_ratio)
+        self.compute_dtype = compute_dtype
+        self.seed = int(seed if seed is not None else
+                        (torch.initial_seed() * 0x9E3779B97F4A7C15 + next(_seed_counter))) & 0xFFFFFFFFFFFFFFFF
+        self.max_graphs, self.capture_after, self.need_dx = int(max_graphs), int(capture_after), bool(need_dx)
+        self._pairs = {}      # N -> _GraphedPair, insertion order = recency
+        self._seen = {}
+        self._dt = None
+        self.stats = {'replays': 0, 'eager': 0, 'captures': 0}
+
+    def __call__(self, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], labels: torch.Tensor):
+        dev = x.device
+        if self._dt is None:
+            self._dt = self.tables if isinstance(self.tables, ops.DeviceTables) else \
+                ops.DeviceTables.from_tables(self.tables, dev)
+        n = int(x.shape[0])
+        pair = self._pairs.pop(n, None)
+        if pair is None:
+            seen = self._seen.get(n, 0) + 1
+            self._seen[n] = seen
+            if n == 0 or seen <= self.capture_after or torch.cuda.is_current_stream_capturing():
+                self.stats['eager'] += 1
+                return bags_head_loss(x, weight, bias, labels, self._dt, self.ratio, compute_dtype=self.compute_dtype)
+            op_dtype = torch.bfloat16 if self.compute_dtype == torch.bfloat16 else torch.float32
+            pair = _GraphedPair(n, int(x.shape[1]), int(weight.shape[0]), self._dt, self.ratio,
+                                (self.seed + 0x9E3779B97F4A7C15 * n) & 0xFFFFFFFFFFFFFFFF, op_dtype, bias is not None,
+                                self.need_dx, dev)
+            self.stats['captures'] += 1
+            while len(self._pairs) >= self.max_graphs:
+                self._pairs.pop(next(iter(self._pairs)))
+        self._pairs[n] = pair                                   # most recently used last
+        self.stats['replays'] += 1
+        return _GraphCachedFunction.apply(x, weight, bias, labels, pair)

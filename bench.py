@@ -742,8 +742,30 @@ def run_ours(args):
                 eager_var_us = (time.perf_counter() - t0) / 200 * 1e6
             except Exception as ex:  # pragma: no cover
                 log('eager variable-N timing failed: %r' % (ex,))
+        cached_var_us = None
+        if world == 1 and eager_var_us is not None:
+            try:    # the same calls through api.GraphCachedHeadLoss (two CUDA graphs per recurring RoI count)
+                from balancedgroupsoftmax_b200.api import GraphCachedHeadLoss
+                cached = GraphCachedHeadLoss(dt, RATIO, compute_dtype=dtype, max_graphs=8, capture_after=1)
+
+                def cached_var(k):
+                    for i in range(k):
+                        m = sizes[i % len(sizes)]
+                        xin = xs[m].detach().requires_grad_(True)
+                        w_param.grad = None
+                        b_param.grad = None
+                        cached(xin, w_param, b_param, ls[m]).sum().backward()
+                cached_var(3 * len(sizes))
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                cached_var(200)
+                torch.cuda.synchronize()
+                cached_var_us = (time.perf_counter() - t0) / 200 * 1e6
+            except Exception as ex:  # pragma: no cover
+                log('graph-cached variable-N timing failed: %r' % (ex,))
         e2e = {'value': world * n / (e2e_ms * 1e-3), 'unit': 'RoIs/s', 'h2d_only_ms_per_step': h2d_ms,
                'eager_api_us_per_step_variable_n_le_1024': eager_var_us,
+               'graph_cached_api_us_per_step_variable_n_le_1024': cached_var_us,
                'h2d_bytes_per_step': int(x_host.numel() * x_host.element_size() + lab_host.numel() * 8),
                'd2h_bytes_per_step': int(loss_host.numel() * 4), 'ms_per_step': e2e_ms, 'steps': e2e_steps,
                'api': ('balancedgroupsoftmax_b200.api.GraphedHeadStep (CUDA-graph replay of bags_head_loss + backward)'

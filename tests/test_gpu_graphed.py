@@ -60,3 +60,49 @@ def test_graphed_step_matches_eager(n):
     assert torch.equal(m0, mp)                  # counter 0 == the plain seed
     assert not torch.equal(m0, m1)
     assert torch.equal(m0.sum(1), m1.sum(1))    # same subset sizes (exact-k sampling)
+
+
+def test_graph_cached_head_loss_matches_eager_for_recurring_roi_counts():
+    """GraphCachedHeadLoss: a data-dependent RoI count inside an ordinary autograd graph -- recurring counts replay two
+    CUDA graphs (forward / backward), new ones run eagerly first; results equal the eager API with the same masks."""
+    from balancedgroupsoftmax_b200 import ops
+    from balancedgroupsoftmax_b200.api import GraphCachedHeadLoss, bags_head_loss
+    dev = torch.device('cuda', 0)
+    t = synthetic_tables(1231, seed=0)
+    dt = ops.DeviceTables.from_tables(t, dev)
+    g = torch.Generator().manual_seed(3)
+    W = torch.nn.Parameter((torch.randn(t.num_logits, 1024, generator=g) * 0.05).to(dev))      # fp32 master
+    b = torch.nn.Parameter((torch.randn(t.num_logits, generator=g) * 0.1).to(dev))
+    fn = GraphCachedHeadLoss(dt, 8.0, seed=77, capture_after=1, max_graphs=2)
+    replays = {}
+    for it, n in enumerate([512, 512, 300, 512, 300, 300, 1000, 1000, 512]):
+        x = torch.relu(torch.randn(n, 1024, generator=g)).to(dev).requires_grad_(True)        # fp32, as a trunk gives it
+        labels = torch.zeros(n, dtype=torch.int64)
+        labels[: n // 4] = torch.randint(1, t.num_classes, (n // 4,), generator=g)
+        labels = labels.to(dev)
+        W.grad = b.grad = None
+        cached_before = n in fn._pairs
+        seen_before = fn._seen.get(n, 0)
+        losses = fn(x, W, b, labels)
+        (losses * torch.tensor([1.0, 0.5, 2.0, 1.0, 0.25], device=dev)).sum().backward()
+        torch.cuda.synchronize()
+        graphed = cached_before or seen_before >= 1
+        if not graphed:
+            continue
+        # the same step through the eager API with the masks this replay's device sampler drew
+        k = replays.get(n, 0)
+        replays[n] = k + 1
+        pair_seed = (77 + 0x9E3779B97F4A7C15 * n) & 0xFFFFFFFFFFFFFFFF
+        if n not in fn._pairs:       # evicted and recaptured: its counter restarted
+            continue
+        wmask, avg = ops.sample_others(labels, dt, 8.0, pair_seed,
+                                       seed_step=torch.tensor([int(fn._pairs[n].seed_step.item()) - 1], device=dev))
+        gW, gb, gx = W.grad.clone(), b.grad.clone(), x.grad.clone()
+        xe = x.detach().clone().requires_grad_(True)
+        W.grad = b.grad = None
+        le = bags_head_loss(xe, W, b, labels, dt, 8.0, wmask=wmask, avg=avg)
+        (le * torch.tensor([1.0, 0.5, 2.0, 1.0, 0.25], device=dev)).sum().backward()
+        torch.cuda.synchronize()
+        assert torch.allclose(losses, le.detach(), rtol=1e-5, atol=1e-6), (it, n)
+        assert rel(gW, W.grad) < 1e-4 and rel(gb, b.grad) < 2e-3 and rel(gx, xe.grad) < 2e-3, (it, n)
+    assert fn.stats['captures'] >= 3 and fn.stats['eager'] >= 3 and len(fn._pairs) <= 2
