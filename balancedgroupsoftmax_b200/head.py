@@ -431,6 +431,10 @@ class GSBBoxHeadWith0(SharedFCBBoxHead):
                           'numpy' (the reference's np.random.choice on the host -- bit-identical
                           masks for a given numpy seed, at the cost of the reference's syncs)
         fuse_loss         True (default): training forward returns a ClsScoreHandle
+        graph_cache       False (default).  True: ``loss`` replays two CUDA graphs per recurring RoI count
+                          (``api.GraphCachedHeadLoss``) -- graph-replay host cost with a data-dependent N
+        native_trunk      True (default): shared FCs / fc_reg on this library's tcgen05 GEMMs
+        eval_compute_dtype 'fp32' (default) / 'bf16' for the test-time logits
     """
 
     def __init__(self, num_fcs=2, fc_out_channels=1024, gs_config=None, *args, **kwargs):
@@ -477,6 +481,9 @@ class GSBBoxHeadWith0(SharedFCBBoxHead):
                                    'float32': torch.float32, 'tf32': torch.float32}[str(ed).lower()]
         # shared FCs + fc_reg on this library's tcgen05 GEMMs (bias + ReLU in the epilogue) instead of nn.Linear / cuBLAS
         self.native_trunk = bool(_cfg_get(gs_config, 'native_trunk', os.environ.get('BAGS_NATIVE_TRUNK', '1') != '0'))
+        # opt-in: CUDA-graph replay per recurring RoI count behind loss() (api.GraphCachedHeadLoss)
+        self.graph_cache = bool(_cfg_get(gs_config, 'graph_cache', os.environ.get('BAGS_GRAPH_CACHE', '0') == '1'))
+        self._graph_loss = None
         self.sampler = str(_cfg_get(gs_config, 'sampler', 'device'))
         assert self.sampler in ('device', 'numpy')
         self.fuse_loss = bool(_cfg_get(gs_config, 'fuse_loss', True))
@@ -606,6 +613,23 @@ class GSBBoxHeadWith0(SharedFCBBoxHead):
         if cls_score is not None:
             assert reduction_override in (None, 'none', 'mean', 'sum')
             dt = self.device_tables(labels.device)
+            if (self.graph_cache and type(self)._remap_labels is GSBBoxHeadWith0._remap_labels and self.sampler == 'device'
+                    and reduction_override in (None, 'mean') and isinstance(cls_score, ClsScoreHandle)
+                    and cls_score._logits is None and torch.is_grad_enabled()):
+                # opt-in (gs_config['graph_cache']): recurring RoI counts replay two CUDA graphs (sampler + fused forward;
+                # merged backward) instead of paying ~220 us of host work per call; new counts run eagerly first
+                if self._graph_loss is None:
+                    from .api import GraphCachedHeadLoss
+                    self._graph_loss = GraphCachedHeadLoss(dt, self.others_sample_ratio, compute_dtype=self.compute_dtype,
+                                                           seed=self._next_seed())
+                loss_vec = self._graph_loss(cls_score.x_cls, self.fc_cls.weight, self.fc_cls.bias, labels)
+                self.last_sample = None
+                for i in range(dt.G):
+                    lw = self.loss_bins[i].loss_weight
+                    losses['loss_cls_bin{}'.format(i)] = loss_vec[i] if lw == 1.0 else loss_vec[i] * lw
+                if bbox_pred is not None:
+                    losses['loss_bbox'] = self._bbox_loss(bbox_pred, labels, bbox_targets, bbox_weights, reduction_override)
+                return losses
             wmask, avg = self._remap_labels(labels)
             self.last_sample = (wmask, avg)
             if reduction_override in ('none', 'sum'):

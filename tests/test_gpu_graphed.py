@@ -106,3 +106,43 @@ def test_graph_cached_head_loss_matches_eager_for_recurring_roi_counts():
         assert torch.allclose(losses, le.detach(), rtol=1e-5, atol=1e-6), (it, n)
         assert rel(gW, W.grad) < 1e-4 and rel(gb, b.grad) < 2e-3 and rel(gx, xe.grad) < 2e-3, (it, n)
     assert fn.stats['captures'] >= 3 and fn.stats['eager'] >= 3 and len(fn._pairs) <= 2
+
+
+def test_head_loss_with_graph_cache_trains_like_the_eager_head():
+    """gs_config['graph_cache']=True: GSBBoxHeadWith0.loss replays CUDA graphs for a recurring RoI count; the losses of
+    a few SGD steps track the eager head's (same initial weights, different "others" draws: statistical agreement)."""
+    from balancedgroupsoftmax_b200.head import GSBBoxHeadWith0
+    t = synthetic_tables(1231, seed=0)
+
+    def make(graph_cache):
+        torch.manual_seed(0)
+        h = GSBBoxHeadWith0(num_fcs=2, in_channels=16, fc_out_channels=1024, roi_feat_size=2, num_classes=1231,
+                            gs_config=dict(tables=t, others_sample_ratio=8.0, num_bins=5, graph_cache=graph_cache,
+                                           loss_bin=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0)))
+        h.init_weights()
+        return h.cuda().train()
+    g = torch.Generator().manual_seed(1)
+    feats = torch.randn(640, 16, 2, 2, generator=g).cuda()
+    labels = torch.zeros(640, dtype=torch.long)
+    labels[:160] = torch.randint(1, 1231, (160,), generator=g)
+    labels = labels.cuda()
+    curves = []
+    for gc in (False, True):
+        head = make(gc)
+        opt = torch.optim.SGD(head.parameters(), lr=0.05)
+        curve = []
+        for it in range(6):
+            opt.zero_grad(set_to_none=True)
+            cls, reg = head(feats)
+            losses = head.loss(cls, None, labels, None, None, None)
+            total = sum(losses.values())
+            total.backward()
+            assert head.fc_cls.weight.grad is not None and head.shared_fcs[0].weight.grad.abs().sum().item() > 0
+            opt.step()
+            curve.append(total.item())
+        curves.append(curve)
+        if gc:
+            assert head._graph_loss.stats['replays'] >= 3 and head._graph_loss.stats['captures'] == 1
+    a, b = curves
+    assert all(abs(x - y) <= 0.05 * abs(x) + 0.05 for x, y in zip(a, b)), (a, b)
+    assert b[-1] < b[0]        # it trains
