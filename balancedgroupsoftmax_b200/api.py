@@ -154,6 +154,7 @@ class _GraphedPair(object):
         self.dX = torch.zeros((n, k), dtype=op_dtype, device=device) if need_dx else None
         self.wscratch = ops.bwd_scratch(self.w)
         self.w_version = None
+        self.b_version = None
         self.stream = torch.cuda.Stream(device=device)
         self.stream.wait_stream(torch.cuda.current_stream(device))
 
@@ -191,8 +192,9 @@ class _GraphCachedFunction(torch.autograd.Function):
             if pair.w_version != (id(weight), weight._version):     # the operand copy follows optimizer updates
                 pair.w.copy_(weight)
                 pair.w_version = (id(weight), weight._version)
-            if bias is not None:
+            if bias is not None and pair.b_version != (id(bias), bias._version):
                 pair.bias.copy_(bias)
+                pair.b_version = (id(bias), bias._version)
         pair.g_fwd.replay()
         ctx.pair = pair
         ctx.dtypes = (x.dtype, weight.dtype, None if bias is None else bias.dtype)
@@ -205,15 +207,16 @@ class _GraphCachedFunction(torch.autograd.Function):
         pair.gout.copy_(grad_loss)
         pair.g_bwd.replay()
         xd, wd, bd = ctx.dtypes
+        # The static buffers are returned as they are (cast only when the dtypes differ): whoever keeps a gradient --
+        # AccumulateGrad for weight / bias / a leaf x -- copies it, because the buffers are referenced here and cannot be
+        # stolen; upstream backward nodes consume dX in stream order, before the next replay rewrites it.
         dX = None
         if pair.dX is not None and ctx.needs_input_grad[0]:
-            dX = pair.dX.to(xd) if pair.dX.dtype != xd else pair.dX.clone()
-        dW = pair.dW.to(wd) if ctx.needs_input_grad[1] else None      # (a copy: the static buffer is rewritten next step)
-        if dW is not None and dW.data_ptr() == pair.dW.data_ptr():
-            dW = dW.clone()
+            dX = pair.dX if pair.dX.dtype == xd else pair.dX.to(xd)
+        dW = (pair.dW if pair.dW.dtype == wd else pair.dW.to(wd)) if ctx.needs_input_grad[1] else None
         db = None
         if pair.db is not None and ctx.needs_input_grad[2]:
-            db = pair.db.to(bd).clone() if pair.db.dtype == bd else pair.db.to(bd)
+            db = pair.db if pair.db.dtype == bd else pair.db.to(bd)
         return dX, dW, db, None, None
 
 
