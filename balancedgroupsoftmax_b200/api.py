@@ -207,16 +207,18 @@ class _GraphCachedFunction(torch.autograd.Function):
         pair.gout.copy_(grad_loss)
         pair.g_bwd.replay()
         xd, wd, bd = ctx.dtypes
-        # The static buffers are returned as they are (cast only when the dtypes differ): whoever keeps a gradient --
-        # AccumulateGrad for weight / bias / a leaf x -- copies it, because the buffers are referenced here and cannot be
-        # stolen; upstream backward nodes consume dX in stream order, before the next replay rewrites it.
+        # gradients leave as fresh tensors (a cast already is one): the static buffers are rewritten by the next replay, and
+        # fresh tensors can be adopted by AccumulateGrad without another copy (measured: 165 vs 195 us per call when the
+        # static buffers themselves were returned and autograd made its own copies)
         dX = None
         if pair.dX is not None and ctx.needs_input_grad[0]:
-            dX = pair.dX if pair.dX.dtype == xd else pair.dX.to(xd)
-        dW = (pair.dW if pair.dW.dtype == wd else pair.dW.to(wd)) if ctx.needs_input_grad[1] else None
+            dX = pair.dX.clone() if pair.dX.dtype == xd else pair.dX.to(xd)
+        dW = None
+        if ctx.needs_input_grad[1]:
+            dW = pair.dW.clone() if pair.dW.dtype == wd else pair.dW.to(wd)
         db = None
         if pair.db is not None and ctx.needs_input_grad[2]:
-            db = pair.db if pair.db.dtype == bd else pair.db.to(bd)
+            db = pair.db.clone() if pair.db.dtype == bd else pair.db.to(bd)
         return dX, dW, db, None, None
 
 
