@@ -60,6 +60,8 @@ SIGNATURES = {
     'bags_debug_max_clusters': (_i, [_i, _i, _i]),
     'bags_cast_bf16': (_i, [_vp, _ll, _vp, _ll, _i, _i, _vp]),
     'bags_linear_act_fwd': (_i, [_vp, _ll, _vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp]),
+    'bags_linear_act_splits': (_i, [_i, _i, _i, _i]),
+    'bags_linear_act_fwd_splitk': (_i, [_vp, _ll, _vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _ll, _i, _vp]),
     'bags_act_bwd': (_i, [_vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _vp]),
     'bags_debug_set_timing': (_i, [_vp]),
     'bags_reload_env': (_i, []),

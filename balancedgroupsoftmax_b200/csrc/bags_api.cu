@@ -359,6 +359,55 @@ extern "C" int bags_linear_act_fwd(const void* x, long long ldx, const void* w, 
   return launch_gemm<256, false, false, EPI_STORE_F32, true, 4>(ga, di, stream);
 }
 
+// Split-K factor worth using for a forward layer (1 = the single-pass kernel): few output tiles and a long contraction --
+// shared_fcs.0 at 2 x 512 RoIs is 8 x 4 tiles of 128 x 256 with K = 12544, i.e. 32 busy SMs out of 148 without it.
+extern "C" int bags_linear_act_splits(int N, int K, int C, int dtype) {
+  DeviceInfo di;
+  if (device_info(di)) return 1;
+  const int tiles = ((N + 127) / 128) * ((C + 255) / 256);
+  const int kblocks = (K + (dtype == BAGS_DTYPE_BF16 ? 63 : 31)) / (dtype == BAGS_DTYPE_BF16 ? 64 : 32);
+  if (tiles <= 0 || tiles * 2 > di.num_sms || kblocks < 16) return 1;
+  int s = di.num_sms / tiles;
+  if (s > kblocks / 4) s = kblocks / 4;
+  return s < 2 ? 1 : (s > 16 ? 16 : s);
+}
+
+// Two-pass forward for such layers: split-K GEMM with red.add into a zeroed fp32 workspace [N, ldws], then
+// out = act(ws + bias) in the output dtype.
+extern "C" int bags_linear_act_fwd_splitk(const void* x, long long ldx, const void* w, long long ldw, const float* bias,
+                                          void* out, long long ldo, int N, int K, int C, int dtype, int out_dtype, int relu,
+                                          float* ws, long long ldws, int splits, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BAGS_REQUIRE(N >= 0 && K >= 1 && C >= 1, "bags_linear_act_fwd_splitk: bad shape N=%d K=%d C=%d", N, K, C);
+  BAGS_REQUIRE(N == 0 || (x && w && out && ws), "bags_linear_act_fwd_splitk: NULL operand");
+  BAGS_REQUIRE(dtype == BAGS_DTYPE_F32 || dtype == BAGS_DTYPE_BF16, "bags_linear_act_fwd_splitk: bad dtype %d", dtype);
+  BAGS_REQUIRE(out_dtype == BAGS_DTYPE_F32 || out_dtype == BAGS_DTYPE_BF16, "bags_linear_act_fwd_splitk: bad output dtype");
+  BAGS_REQUIRE(ldx >= K && ldw >= K && ldo >= C && ldws >= C && (ldws % 4) == 0 && splits >= 2,
+               "bags_linear_act_fwd_splitk: bad leading dimension / split count");
+  BAGS_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "bags_linear_act_fwd_splitk: workspace must be 16-byte aligned");
+  if (N == 0) return BAGS_OK;
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  BAGS_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * static_cast<size_t>(N) * static_cast<size_t>(ldws), stream));
+  GemmArgs ga{};
+  ga.a = x; ga.lda = ldx; ga.a_mn = false;
+  ga.b = w; ga.ldb = ldw; ga.b_mn = false;
+  ga.M = N; ga.N = C; ga.K = K; ga.dtype = dtype; ga.splits = splits;
+  ga.p.out = ws; ga.p.ldo = ldws;
+  int rc = (dtype == BAGS_DTYPE_BF16) ? launch_gemm<256, false, false, EPI_RED_F32, false, 4>(ga, di, stream)
+                                      : launch_gemm<256, false, false, EPI_RED_F32, true, 4>(ga, di, stream);
+  if (rc) return rc;
+  const long long quads = static_cast<long long>(N) * ((C + 3) / 4);
+  long long grid = (quads + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (out_dtype == BAGS_DTYPE_BF16)
+    bias_act_store_kernel<true><<<static_cast<unsigned>(grid), 256, 0, stream>>>(ws, ldws, bias, out, ldo, N, C, relu ? 1 : 0);
+  else
+    bias_act_store_kernel<false><<<static_cast<unsigned>(grid), 256, 0, stream>>>(ws, ldws, bias, out, ldo, N, C, relu ? 1 : 0);
+  BAGS_CUDA(cudaGetLastError());
+  return BAGS_OK;
+}
+
 // g = (y > 0 ? dy : 0) in the operand dtype of the backward contractions (y == NULL: g = dy, i.e. a cast)
 extern "C" int bags_act_bwd(const void* dy, long long lddy, int dy_dtype, const void* y, long long ldy, int y_dtype,
                             void* g, long long ldg, int g_dtype, int rows, int cols, void* stream_) {

@@ -742,6 +742,32 @@ cast_bf16_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __
   }
 }
 
+// Second pass of a split-K forward layer: out = act(ws + bias) in the output dtype (ws: fp32 sums of the split-K GEMM).
+template <bool OUT_BF16>
+__global__ void __launch_bounds__(256)
+bias_act_store_kernel(const float* __restrict__ ws, long long ldws, const float* __restrict__ bias, void* __restrict__ out,
+                      long long ldo, int rows, int cols, int relu) {
+  const int qpr = (cols + 3) >> 2;   // float4 groups per row (the last may be partial)
+  const long long quads = static_cast<long long>(rows) * qpr;
+  for (long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < quads;
+       q += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(q / qpr), c = static_cast<int>(q % qpr) * 4;
+    const float4 v4 = *reinterpret_cast<const float4*>(ws + static_cast<long long>(r) * ldws + c);   // ldws % 4 == 0, padded
+    float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (bias != nullptr && c + e < cols) v[e] += __ldg(bias + c + e);
+      if (relu) v[e] = fmaxf(v[e], 0.f);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (c + e >= cols) break;
+      if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(out)[static_cast<long long>(r) * ldo + c + e] = __float2bfloat16_rn(v[e]);
+      else          reinterpret_cast<float*>(out)[static_cast<long long>(r) * ldo + c + e] = v[e];
+    }
+  }
+}
+
 // Backward of y = act(x W^T + b) up to the two contractions (shared FCs / fc_reg of the head's trunk,
 // convfc_bbox_head.py:138-143,167): g = (y > 0 ? dy : 0) for a ReLU layer (y == nullptr: g = dy), cast to the GEMM
 // operand dtype with a padded leading dimension.  HBM-bound elementwise pass: reads dy (+ y), writes g.

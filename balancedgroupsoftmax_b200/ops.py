@@ -426,6 +426,16 @@ def linear_act(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], r
     if bias is not None:
         bias = bias.contiguous()
         assert bias.dtype == torch.float32
+    splits = nat.lib().bags_linear_act_splits(N, K, Cc, _dtype_code(x.dtype)) if N > 0 else 1
+    if splits > 1:
+        # few output tiles, long contraction (shared_fcs.0): split-K into an fp32 workspace, then bias + activation
+        ws = torch.empty((N, (Cc + 3) // 4 * 4), dtype=torch.float32, device=x.device)
+        nat.check(nat.lib().bags_linear_act_fwd_splitk(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), nat.ptr(bias),
+                                                       out.data_ptr(), out.stride(0), N, K, Cc, _dtype_code(x.dtype),
+                                                       _dtype_code(out.dtype), 1 if relu else 0, ws.data_ptr(),
+                                                       ws.stride(0), splits, _stream_ptr(x.device)),
+                  'bags_linear_act_fwd_splitk')
+        return out
     nat.check(nat.lib().bags_linear_act_fwd(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), nat.ptr(bias),
                                             out.data_ptr(), out.stride(0), N, K, Cc, _dtype_code(x.dtype),
                                             _dtype_code(out.dtype), 1 if relu else 0, _stream_ptr(x.device)),

@@ -228,6 +228,14 @@ int bags_linear_act_fwd(const void* x, long long ldx, const void* w, long long l
                         void* out, long long ldo, int N, int K, int C, int dtype, int out_dtype, int relu,
                         void* stream);
 
+/* The same layer in two passes for shapes with few output tiles and a long contraction (shared_fcs.0: 8 x 4 tiles,
+ * K = 12544): split-K GEMM with red.add into the zeroed fp32 workspace ws [N, ldws] (ldws % 4 == 0, >= C), then
+ * out = act(ws + bias).  bags_linear_act_splits() returns the split count worth using (1: call bags_linear_act_fwd). */
+int bags_linear_act_splits(int N, int K, int C, int dtype);
+int bags_linear_act_fwd_splitk(const void* x, long long ldx, const void* w, long long ldw, const float* bias,
+                               void* out, long long ldo, int N, int K, int C, int dtype, int out_dtype, int relu,
+                               float* ws, long long ldws, int splits, void* stream);
+
 /* Its backward up to the contractions: g[rows, cols] = (y > 0 ? dy : 0) in dtype g_dtype (y == NULL: a plain cast of dy);
  * dW / db / dX then come from bags_bwd(g, ...) with a single slice (0, cols) and gout == NULL.  cols % 4 == 0. */
 int bags_act_bwd(const void* dy, long long lddy, int dy_dtype, const void* y, long long ldy, int y_dtype,
