@@ -55,6 +55,16 @@ def _worker(rank, world, port, q):
         exchange()
         ok = ok and bucket is None and torch.allclose(gW, torch.full((6, 4), 1.5)) and \
             torch.allclose(gb, torch.full((6,), 5.0)) and gW.data_ptr() == flat2.data_ptr()
+        # NcclGradBucket: the bucket object the data-parallel public API takes when the peer-memory path is unavailable
+        # (same interface as PeerGradBucket: views + allreduce_; its stream-forking exchange_overlapped needs a GPU)
+        from balancedgroupsoftmax_b200.dist import NcclGradBucket
+        nb = NcclGradBucket([(5, 3), (5,)], 'cpu')
+        nb.views[0].fill_(3.0 * (rank + 1))
+        nb.views[1].copy_(torch.arange(5, dtype=torch.float32) + rank)
+        nb.allreduce_()
+        ok = ok and torch.allclose(nb.views[0], torch.full((5, 3), 4.5)) and \
+            torch.allclose(nb.views[1], torch.arange(5, dtype=torch.float32) + 0.5) and nb.status() == 0 and \
+            nb.views[0].data_ptr() == nb.flat.data_ptr() and hasattr(nb, 'exchange_overlapped')
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
